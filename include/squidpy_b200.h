@@ -1,0 +1,150 @@
+/*
+ * squidpy_b200.h — C ABI of libsquidpy_b200.so: B200 (sm_100a) kernels for squidpy's spatial-statistics hot
+ * path.  Plain pointers and sizes only (no torch / numpy types).  All array arguments are HOST pointers owned
+ * by the caller unless a parameter is documented as a device pointer; the library never frees caller memory.
+ *
+ * Conventions
+ *   - every function returns 0 (SQB_OK) or a negative sqb_status; sqb_last_error() returns a thread-local
+ *     human-readable message for the last failure on the calling thread;
+ *   - a sqb_ctx binds one CUDA device and one stream (caller-supplied cudaStream_t, or library-owned);
+ *     object handles (sqb_nhood, sqb_autocorr) belong to the ctx they were created on; handles are not
+ *     thread-safe, distinct ctx/handles may be used concurrently (one per GPU);
+ *   - calls are synchronous with respect to the host unless the name ends in _async.
+ *
+ * Each entry point replaces one internal seam of the reference (paths relative to the squidpy tree):
+ *   sqb_nhood_count            <- _test(indices, indptr, clustering)          src/squidpy/gr/_nhood.py:60-61,208-209
+ *   sqb_nhood_permute*         <- _nhood_enrichment_helper(...)               src/squidpy/gr/_nhood.py:516-547
+ *                                 (+ rng.shuffle / _shuffle_group             src/squidpy/gr/_utils.py:185-213,
+ *                                    spawn_generators                         src/squidpy/_utils.py:240-241)
+ *   sqb_autocorr_*             <- scanpy.metrics.morans_i / gearys_c call     src/squidpy/gr/_ppatterns.py:216,267-272
+ *   sqb_cooc_counts            <- _occur_count(x, y, thresholds, labs, n,k,l) src/squidpy/gr/_ppatterns.py:283-310
+ *   sqb_pair_counts_f64        <- KDTree.two_point_correlation(points, r)     src/squidpy/gr/_ripley.py:218-223
+ */
+#ifndef SQUIDPY_B200_H
+#define SQUIDPY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQB_ABI_VERSION 1
+
+typedef enum {
+    SQB_OK = 0,
+    SQB_ERR_INVALID = -1, /* bad argument (message says which) */
+    SQB_ERR_CUDA = -2,    /* CUDA runtime / launch failure */
+    SQB_ERR_OOM = -3,     /* device allocation failed */
+    SQB_ERR_UNSUPPORTED = -4,
+    SQB_ERR_STATE = -5 /* call sequence error (e.g. run before upload) */
+} sqb_status;
+
+typedef struct sqb_ctx sqb_ctx;
+typedef struct sqb_nhood sqb_nhood;
+typedef struct sqb_autocorr sqb_autocorr;
+
+/* ---- library / context --------------------------------------------------------------------------- */
+int sqb_abi_version(void);
+const char* sqb_last_error(void);
+int sqb_device_count(int* count);
+
+/* stream: a cudaStream_t to launch on (e.g. torch's current stream), or NULL for a library-owned stream. */
+int sqb_ctx_create(int device, void* stream, sqb_ctx** out);
+int sqb_ctx_destroy(sqb_ctx* ctx);
+int sqb_ctx_sync(sqb_ctx* ctx);
+int sqb_ctx_stream(sqb_ctx* ctx, void** stream);
+int sqb_ctx_sm_count(sqb_ctx* ctx, int* sm_count);
+/* number of kernels this library launched on ctx so far */
+int sqb_ctx_launch_count(sqb_ctx* ctx, int64_t* launches);
+/* per-kernel-class event timing (synchronises every launch; for roofline passes, not for throughput runs) */
+int sqb_ctx_profile(sqb_ctx* ctx, int enable);
+int sqb_ctx_profile_reset(sqb_ctx* ctx);
+/* kclass: 0 fill, 1 shuffle, 2 transpose, 3 count, 4 autocorr prep, 5 autocorr main, 6 autocorr final, 7 pairs, 8 misc */
+int sqb_ctx_profile_get(sqb_ctx* ctx, int kclass, double* ms, int64_t* launches);
+
+/* page-locked host memory for the host-facing API (so H2D/D2H copies run at full PCIe rate) */
+int sqb_host_alloc(size_t bytes, void** ptr);
+int sqb_host_free(void* ptr);
+
+/* ---- nhood_enrichment ------------------------------------------------------------------------------
+ * Graph = CSR of obsp['spatial_connectivities'] (data ignored; entries counted as stored; reference dtypes
+ * uint32, _nhood.py:52,205).  n_cls = number of categories (labels in [0, n_cls)).                       */
+int sqb_nhood_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const uint32_t* indptr, const uint32_t* indices,
+                     int n_cls, sqb_nhood** out);
+int sqb_nhood_destroy(sqb_nhood* h);
+
+/* observed count: out[a*n_cls+b] = #stored entries (i->j) with labels[i]=a, labels[j]=b   (uint32)       */
+int sqb_nhood_count(sqb_nhood* h, const uint32_t* labels, uint32_t* out);
+
+/* Base labels for the permutation test and the optional library partition (lib_codes[i] in [0,n_libs),
+ * NULL/0 for none).  With libraries each category is shuffled separately, in category order, by the same
+ * generator (gr/_utils.py:208-212).                                                                      */
+int sqb_nhood_set_base(sqb_nhood* h, const uint32_t* base_labels, const int32_t* lib_codes, int n_libs);
+
+/* Permutation test.  states: n_perms x 6 uint64 = numpy PCG64 state of generator p
+ *   {state_hi, state_lo, inc_hi, inc_lo, has_uint32, uinteger}  (has_uint32 must be 0: fresh generators).
+ * Permutation p replays numpy Generator.shuffle bit-exactly on the device and counts.
+ * out_counts: n_perms x n_cls x n_cls uint32.                                                            */
+int sqb_nhood_permute(sqb_nhood* h, const uint64_t* states, int64_t n_perms, uint32_t* out_counts);
+
+/* The same in three steps, for measurement with inputs resident in HBM:
+ * upload (H2D of the generator states), run (kernels only, asynchronous on the ctx stream, results stay on
+ * the device), download (D2H of the counts, synchronises).                                               */
+int sqb_nhood_permute_upload(sqb_nhood* h, const uint64_t* states, int64_t n_perms);
+int sqb_nhood_permute_run_async(sqb_nhood* h);
+int sqb_nhood_permute_download(sqb_nhood* h, uint32_t* out_counts);
+
+/* Test hook: shuffled label vectors of permutations [p0, p1) of the last upload, recomputed on the device
+ * (original node order), out: (p1-p0) x n uint32.                                                        */
+int sqb_nhood_shuffled_labels(sqb_nhood* h, int64_t p0, int64_t p1, uint32_t* out);
+
+/* Tuning / test options.  key: "shuffle_algo" (0 = one thread per permutation, serial replay; 1 = CTA-parallel
+ * replay, default), "shuffle_threads" (256/512/1024), "perm_chunk" (permutations resident at once),
+ * "count_algo" (0 auto, 1 shared-memory lane-private histograms, 2 global atomics).                       */
+int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value);
+/* algorithmic bytes per permutation, SURVEY.md 8(d): 4*nnz + 4*(n+1) + 8*n + 4*n_cls^2                   */
+int sqb_nhood_bytes_per_perm(sqb_nhood* h, int64_t* bytes);
+
+/* ---- spatial_autocorr (Moran's I / Geary's C) -------------------------------------------------------
+ * W = obsp[connectivity_key] (after optional float32 row normalisation on the host) as CSR; w_dtype 0 = f32,
+ * 1 = f64 (cast to f64 like scanpy does).  mode 0 = Moran's I, 1 = Geary's C.
+ * X layout 0: features x obs (row-major dense, or CSR by feature); layout 1: obs x features (row-major
+ * dense, or CSR by observation == CSC of the features x obs matrix, AnnData's native X).
+ * x_dtype 0 = f32, 1 = f64.  row_perm (or NULL): length-n permutation p; row r of the permuted W is row p[r]
+ * (g[idx_shuffle, :], _ppatterns.py:271-272).  out: n_features float64 (NaN for constant features).       */
+int sqb_autocorr_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const int32_t* w_indptr, const int32_t* w_indices,
+                        const void* w_data, int w_dtype, sqb_autocorr** out);
+int sqb_autocorr_destroy(sqb_autocorr* h);
+int sqb_autocorr_load_dense(sqb_autocorr* h, const void* x, int x_dtype, int layout, int64_t n_features);
+int sqb_autocorr_load_csr(sqb_autocorr* h, const int64_t* x_indptr, const int32_t* x_indices, const void* x_data,
+                          int x_dtype, int layout, int64_t n_features);
+int sqb_autocorr_run_async(sqb_autocorr* h, int mode, const int64_t* row_perm);
+int sqb_autocorr_download(sqb_autocorr* h, double* out);
+/* load + run + download */
+int sqb_autocorr_dense(sqb_autocorr* h, int mode, const void* x, int x_dtype, int layout, int64_t n_features,
+                       const int64_t* row_perm, double* out);
+int sqb_autocorr_csr(sqb_autocorr* h, int mode, const int64_t* x_indptr, const int32_t* x_indices,
+                     const void* x_data, int x_dtype, int layout, int64_t n_features, const int64_t* row_perm,
+                     double* out);
+
+/* ---- co_occurrence ------------------------------------------------------------------------------------
+ * out[(a*k+b)*L + r] = #{ordered (i,j), i != j : labs[i]=a, labs[j]=b, d2_ij <= thr[r]}  (int64, cumulative in
+ * r), float32 arithmetic with d2 = fma(dy,dy,dx*dx) (use_fma=1, what the reference's JIT emits on x86-64 with
+ * FMA) or dx*dx+dy*dy (use_fma=0).  thr ascending.  Only tiles t with t % shard_count == shard_index are
+ * evaluated (multi-GPU sharding; pass 0,1 for everything); partial results add up across shards.          */
+int sqb_cooc_counts(sqb_ctx* ctx, const float* x, const float* y, int64_t n, const int32_t* labs, int k,
+                    const float* thr, int L, int use_fma, int shard_index, int shard_count, int64_t* out);
+
+/* ---- ripley L -------------------------------------------------------------------------------------------
+ * For every group g (points group_ptr[g]..group_ptr[g+1] of pts, interleaved x,y float64):
+ * out[g*S + s] = #{ordered (i,j) in group g, INCLUDING i == j : sqrt(dx*dx + dy*dy) <= support[s]}  (int64),
+ * i.e. sklearn KDTree.two_point_correlation(points_g, support).  support ascending.                        */
+int sqb_pair_counts_f64(sqb_ctx* ctx, const double* pts, const int64_t* group_ptr, int n_groups,
+                        const double* support, int S, int shard_index, int shard_count, int64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQUIDPY_B200_H */

@@ -1,0 +1,132 @@
+// capi.cu — context management and error plumbing of the C ABI (include/squidpy_b200.h).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void sqb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+
+int sqb_abi_version(void) { return SQB_ABI_VERSION; }
+
+const char* sqb_last_error(void) { return g_err; }
+
+int sqb_device_count(int* count) {
+    SQB_CHECK(count, SQB_ERR_INVALID, "sqb_device_count: null argument");
+    SQB_CUDA(cudaGetDeviceCount(count));
+    return SQB_OK;
+}
+
+int sqb_ctx_create(int device, void* stream, sqb_ctx** out) {
+    SQB_CHECK(out, SQB_ERR_INVALID, "sqb_ctx_create: null out");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        sqb_set_error("no CUDA device available (%s); squidpy_b200 has no CPU fallback", cudaGetErrorString(e));
+        return SQB_ERR_CUDA;
+    }
+    SQB_CHECK(device >= 0 && device < ndev, SQB_ERR_INVALID, "sqb_ctx_create: device %d not in [0,%d)", device, ndev);
+    SQB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SQB_CUDA(cudaGetDeviceProperties(&prop, device));
+    SQB_CHECK(prop.major >= 10, SQB_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+              prop.major, prop.minor);
+    sqb_ctx* c = new sqb_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+        c->own_stream = false;
+    } else {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete c;
+            sqb_set_error("cudaStreamCreate: %s", cudaGetErrorString(e));
+            return SQB_ERR_CUDA;
+        }
+        c->own_stream = true;
+    }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    *out = c;
+    return SQB_OK;
+}
+
+int sqb_ctx_destroy(sqb_ctx* c) {
+    if (!c) return SQB_OK;
+    cudaSetDevice(c->device);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SQB_OK;
+}
+
+int sqb_ctx_sync(sqb_ctx* c) {
+    SQB_CHECK(c, SQB_ERR_INVALID, "sqb_ctx_sync: null ctx");
+    SQB_CUDA(cudaSetDevice(c->device));
+    SQB_CUDA(cudaStreamSynchronize(c->stream));
+    return SQB_OK;
+}
+
+int sqb_ctx_stream(sqb_ctx* c, void** stream) {
+    SQB_CHECK(c && stream, SQB_ERR_INVALID, "sqb_ctx_stream: null argument");
+    *stream = (void*)c->stream;
+    return SQB_OK;
+}
+
+int sqb_ctx_sm_count(sqb_ctx* c, int* sm_count) {
+    SQB_CHECK(c && sm_count, SQB_ERR_INVALID, "sqb_ctx_sm_count: null argument");
+    *sm_count = c->sm_count;
+    return SQB_OK;
+}
+
+int sqb_ctx_launch_count(sqb_ctx* c, int64_t* launches) {
+    SQB_CHECK(c && launches, SQB_ERR_INVALID, "sqb_ctx_launch_count: null argument");
+    *launches = c->launches;
+    return SQB_OK;
+}
+
+int sqb_ctx_profile(sqb_ctx* c, int enable) {
+    SQB_CHECK(c, SQB_ERR_INVALID, "sqb_ctx_profile: null ctx");
+    c->profile = enable != 0;
+    return SQB_OK;
+}
+
+int sqb_ctx_profile_reset(sqb_ctx* c) {
+    SQB_CHECK(c, SQB_ERR_INVALID, "sqb_ctx_profile_reset: null ctx");
+    for (int k = 0; k < SQB_K_NCLASS; ++k) {
+        c->k_ms[k] = 0.0;
+        c->k_n[k] = 0;
+    }
+    return SQB_OK;
+}
+
+int sqb_ctx_profile_get(sqb_ctx* c, int kclass, double* ms, int64_t* launches) {
+    SQB_CHECK(c && ms && launches, SQB_ERR_INVALID, "sqb_ctx_profile_get: null argument");
+    SQB_CHECK(kclass >= 0 && kclass < SQB_K_NCLASS, SQB_ERR_INVALID, "sqb_ctx_profile_get: bad class %d", kclass);
+    *ms = c->k_ms[kclass];
+    *launches = c->k_n[kclass];
+    return SQB_OK;
+}
+
+int sqb_host_alloc(size_t bytes, void** ptr) {
+    SQB_CHECK(ptr, SQB_ERR_INVALID, "sqb_host_alloc: null argument");
+    SQB_CUDA(cudaHostAlloc(ptr, bytes > 0 ? bytes : 1, cudaHostAllocPortable));
+    return SQB_OK;
+}
+
+int sqb_host_free(void* ptr) {
+    if (ptr) SQB_CUDA(cudaFreeHost(ptr));
+    return SQB_OK;
+}
+
+}  // extern "C"

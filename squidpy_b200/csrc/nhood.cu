@@ -1,0 +1,963 @@
+// nhood.cu — nhood_enrichment permutation test on B200 (sm_100a).
+//
+// Replaces the reference's per-permutation CPU loop (src/squidpy/gr/_nhood.py:516-547): for every permutation
+//   shuffled = base.copy(); rng_p.shuffle(shuffled)        (numpy PCG64 Generator.shuffle, replayed bit-exactly)
+//   perms[p] = count(indices, indptr, shuffled)            (_nenrich kernel, _nhood.py:54-141)
+// with four kernels per chunk of permutations, all integer / byte work (HBM + shared-memory bound, no tensor
+// cores):
+//   1. nhood_fill          broadcast the base labels into one row per permutation            [P][stride]
+//   2. nhood_shuffle_cta   ONE CTA PER PERMUTATION replays Generator.shuffle exactly: the PCG64 stream is
+//                          produced in parallel by jump-ahead (one 64-bit output per thread per batch), masked
+//                          rejection sampling is resolved with ballots + a block prefix sum, and the resulting
+//                          batch of Fisher-Yates swaps is applied in parallel after shared-memory conflict
+//                          detection (conflicting swaps are replayed in order by one thread on the staged
+//                          values).  RNG state and all reductions live in registers / shared memory.
+//   3. nhood_transpose     [P][n] -> [n][PB] (permutation-minor) so that one warp lane = one permutation
+//   4. nhood_count         CSR neighbour-pair histogram: lane = permutation, warp walks the CSR once for 32
+//                          permutations; lane-private shared-memory histogram columns (bank = lane, no
+//                          conflicts), one flush per CTA.
+#include "common.cuh"
+#include "pcg64_jump.h"
+
+typedef unsigned __int128 u128;
+
+__constant__ uint64_t c_jump_M[SQB_PCG_JUMP_BITS][2] = SQB_PCG_JUMP_M_INIT;
+__constant__ uint64_t c_jump_C[SQB_PCG_JUMP_BITS][2] = SQB_PCG_JUMP_C_INIT;
+
+// ------------------------------------------------------------------------------------------------
+// numpy PCG64 (XSL-RR 128/64) on the device.  numpy/random/src/pcg64/pcg64.h: advance first, then output.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u128 mk128(uint64_t hi, uint64_t lo) { return ((u128)hi << 64) | (u128)lo; }
+
+__device__ __forceinline__ uint64_t pcg_output(u128 s) {
+    uint64_t hi = (uint64_t)(s >> 64), lo = (uint64_t)s;
+    uint64_t x = hi ^ lo;
+    unsigned rot = (unsigned)(hi >> 58);
+    return (x >> rot) | (x << ((64u - rot) & 63u));
+}
+
+// state_{k+d} = M * state_k + C * inc
+__device__ __forceinline__ void pcg_jump_consts(uint64_t d, u128& M, u128& C) {
+    M = 1;
+    C = 0;
+    for (int b = 0; d != 0; ++b, d >>= 1) {
+        if (d & 1) {
+            u128 Mb = mk128(c_jump_M[b][0], c_jump_M[b][1]);
+            u128 Cb = mk128(c_jump_C[b][0], c_jump_C[b][1]);
+            C = Mb * C + Cb;
+            M = Mb * M;
+        }
+    }
+}
+
+#define PCG_MULT_HI 0x2360ED051FC65DA4ULL
+#define PCG_MULT_LO 0x4385DF649FCCF645ULL
+
+struct PcgSerial {
+    u128 state, inc;
+    int has32;
+    uint32_t buf;
+    __device__ __forceinline__ uint64_t next64() {
+        state = state * mk128(PCG_MULT_HI, PCG_MULT_LO) + inc;
+        return pcg_output(state);
+    }
+    __device__ __forceinline__ uint32_t next32() {
+        if (has32) {
+            has32 = 0;
+            return buf;
+        }
+        uint64_t v = next64();
+        has32 = 1;
+        buf = (uint32_t)(v >> 32);
+        return (uint32_t)v;
+    }
+    __device__ __forceinline__ uint64_t interval(uint64_t max) {
+        if (max == 0) return 0;
+        uint64_t mask = max;
+        mask |= mask >> 1;
+        mask |= mask >> 2;
+        mask |= mask >> 4;
+        mask |= mask >> 8;
+        mask |= mask >> 16;
+        mask |= mask >> 32;
+        uint64_t v;
+        if (max <= 0xffffffffULL) {
+            do {
+                v = next32() & mask;
+            } while (v > max);
+        } else {
+            do {
+                v = next64() & mask;
+            } while (v > max);
+        }
+        return v;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// 1. fill: labels[p][0..stride) = base[0..stride)   (16-byte vectors; stride*sizeof(LT) % 16 == 0)
+// ------------------------------------------------------------------------------------------------
+__global__ void nhood_fill_kernel(uint4* __restrict__ dst, const uint4* __restrict__ base, int64_t vec_per_row,
+                                  int64_t n_rows) {
+    for (int64_t row = blockIdx.y; row < n_rows; row += gridDim.y) {
+        uint4* __restrict__ d = dst + row * vec_per_row;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < vec_per_row;
+             i += (int64_t)gridDim.x * blockDim.x)
+            d[i] = base[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2a. reference-style serial replay: one thread per permutation (cross-check / fallback option)
+// ------------------------------------------------------------------------------------------------
+template <typename LT>
+__global__ void nhood_shuffle_serial_kernel(LT* __restrict__ labels, int64_t stride, const uint64_t* __restrict__ states,
+                                            int64_t n_perms, int nseg, const int64_t* __restrict__ seg_start,
+                                            const int64_t* __restrict__ seg_len) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n_perms) return;
+    PcgSerial g;
+    g.state = mk128(states[p * 4 + 0], states[p * 4 + 1]);
+    g.inc = mk128(states[p * 4 + 2], states[p * 4 + 3]);
+    g.has32 = 0;
+    g.buf = 0;
+    LT* a = labels + p * stride;
+    for (int s = 0; s < nseg; ++s) {
+        LT* b = a + seg_start[s];
+        for (int64_t i = seg_len[s] - 1; i >= 1; --i) {
+            int64_t j = (int64_t)g.interval((uint64_t)i);
+            LT t = b[i];
+            b[i] = b[j];
+            b[j] = t;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2b. CTA-parallel exact replay of numpy Generator.shuffle (see file header; validated step by step against
+//     numpy by the Python emulation tests/emu_shuffle.py).
+//
+//  Raw stream: v_{2k} = lo32(out_k), v_{2k+1} = hi32(out_k)  (pcg64_next32 hands out the low half first).
+//  Thread t owns out_{b*NT + t} of batch b (LCG jump-ahead by NT per batch), i.e. raw slots 2t, 2t+1.
+//  A window of K raw values is examined at a time; value r is accepted for the current step iff
+//      (v_r & mask) <= i_cur - (#accepted before r)
+//  which is solved as a fixed point of ballots + prefix sums (converges in 1-2 rounds because
+//  K <= min(i/4, 4 sqrt(i))).  The S accepted values are the swap targets j of steps i_cur, i_cur-1, ...
+//  Swaps of one window commute unless they share a position; sharing is detected exactly (targets inside the
+//  window's own index range; duplicate targets through a shared-memory hash table) and the few conflicting
+//  swaps are replayed in step order by one thread on the staged copies.
+// ------------------------------------------------------------------------------------------------
+#define SQB_EMPTY_KEY 0xFFFFFFFFu
+
+__device__ __forceinline__ int sqb_window_size(int64_t i_cur, int raw_left, int raw_total) {
+    int64_t a = i_cur >> 2;
+    int64_t b = (int64_t)(4.0f * sqrtf((float)i_cur));
+    int64_t k = a < b ? a : b;
+    if (k > raw_total) k = raw_total;
+    if (k < 1) k = 1;
+    if (k > raw_left) k = raw_left;
+    return (int)k;
+}
+
+template <typename LT, int NT>
+__global__ void __launch_bounds__(NT) nhood_shuffle_cta_kernel(LT* __restrict__ labels, int64_t stride,
+                                                               const uint64_t* __restrict__ states, int nseg,
+                                                               const int64_t* __restrict__ seg_start,
+                                                               const int64_t* __restrict__ seg_len) {
+    constexpr int RAW = 2 * NT;
+    constexpr int HS = 4 * NT;  // hash slots (load factor <= 0.5)
+    constexpr int NW = NT / 32;
+    constexpr int HS_SHIFT = (NT == 128 ? 23 : NT == 256 ? 22 : NT == 512 ? 21 : 20);  // 32 - log2(HS)
+    static_assert(NT == 128 || NT == 256 || NT == 512 || NT == 1024, "NT");
+
+    __shared__ uint32_t s_sj[RAW];
+    __shared__ LT s_own[RAW];
+    __shared__ uint32_t s_keys[HS];
+    __shared__ LT s_hval[HS];
+    __shared__ uint8_t s_dup[HS];
+    __shared__ uint32_t s_flag[RAW / 32];
+    __shared__ int s_wsum[32];
+    __shared__ int s_rstar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    LT* __restrict__ a = labels + (int64_t)blockIdx.x * stride;
+    const uint64_t* st4 = states + (int64_t)blockIdx.x * 4;
+
+    for (int h = tid; h < HS; h += NT) {
+        s_keys[h] = SQB_EMPTY_KEY;
+        s_dup[h] = 0;
+    }
+    if (tid < RAW / 32) s_flag[tid] = 0;
+    if (tid < 32) s_wsum[tid] = 0;
+
+    // per-thread LCG: state of output index t is state_{t+1}
+    const u128 inc = mk128(st4[2], st4[3]);
+    u128 st;
+    {
+        u128 M, C;
+        pcg_jump_consts((uint64_t)tid + 1, M, C);
+        st = M * mk128(st4[0], st4[1]) + C * inc;
+    }
+    u128 Mn, Cn_inc;
+    {
+        u128 M, C;
+        pcg_jump_consts((uint64_t)NT, M, C);
+        Mn = M;
+        Cn_inc = C * inc;
+    }
+    uint32_t raw0 = 0, raw1 = 0;
+    int pos = RAW;
+    __syncthreads();
+
+    for (int seg = 0; seg < nseg; ++seg) {
+        const int64_t base = seg_start[seg];
+        int64_t i_cur = seg_len[seg] - 1;
+        while (i_cur >= 1) {
+            if (pos >= RAW) {
+                uint64_t o = pcg_output(st);
+                st = Mn * st + Cn_inc;
+                raw0 = (uint32_t)o;
+                raw1 = (uint32_t)(o >> 32);
+                pos = 0;
+            }
+            // ---- phase parameters (uniform) ----
+            uint64_t mask64 = (uint64_t)i_cur;
+            mask64 |= mask64 >> 1;
+            mask64 |= mask64 >> 2;
+            mask64 |= mask64 >> 4;
+            mask64 |= mask64 >> 8;
+            mask64 |= mask64 >> 16;
+            mask64 |= mask64 >> 32;
+            const uint32_t mask = (uint32_t)mask64;  // i_cur < 2^32 (n < 2^32 enforced on the host)
+            const int64_t i_lo = (int64_t)(mask64 >> 1) + 1;
+            const int64_t n_ph = i_cur - i_lo + 1;
+            const int K = sqb_window_size(i_cur, RAW - pos, RAW);
+            const int r0 = 2 * tid, r1 = 2 * tid + 1;
+            const bool in0 = (r0 >= pos) && (r0 < pos + K);
+            const bool in1 = (r1 >= pos) && (r1 < pos + K);
+            const uint32_t u0 = raw0 & mask, u1 = raw1 & mask;
+
+            // ---- acceptance fixed point ----
+            int c0 = 0, c1 = 0, total = 0;
+            bool F0 = in0 && ((int64_t)u0 <= i_cur);
+            bool F1 = in1 && ((int64_t)u1 <= i_cur);
+            while (true) {
+                const uint32_t b0 = __ballot_sync(0xffffffffu, F0);
+                const uint32_t b1 = __ballot_sync(0xffffffffu, F1);
+                if (lane == 0) s_wsum[warp] = __popc(b0) + __popc(b1);
+                __syncthreads();
+                int v = (lane < NW) ? s_wsum[lane] : 0;
+                int incl = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                const int woff = __shfl_sync(0xffffffffu, incl - v, warp);
+                total = __shfl_sync(0xffffffffu, incl, 31);
+                c0 = woff + __popc(b0 & lt_mask) + __popc(b1 & lt_mask);
+                c1 = c0 + (F0 ? 1 : 0);
+                const bool nF0 = in0 && ((int64_t)u0 <= i_cur - (int64_t)c0);
+                const bool nF1 = in1 && ((int64_t)u1 <= i_cur - (int64_t)c1);
+                const int changed = (nF0 != F0) || (nF1 != F1);
+                const int any = __syncthreads_or(changed);
+                if (!any) break;
+                F0 = nF0;
+                F1 = nF1;
+            }
+            int S;
+            const bool phase_ends = ((int64_t)total >= n_ph);
+            if (phase_ends) {
+                S = (int)n_ph;
+                if (F0 && c0 == S - 1) s_rstar = r0;
+                if (F1 && c1 == S - 1) s_rstar = r1;
+            } else {
+                S = total;
+            }
+            if (F0 && c0 < S) s_sj[c0] = u0;
+            if (F1 && c1 < S) s_sj[c1] = u1;
+            __syncthreads();
+            const int newpos = phase_ends ? (s_rstar + 1) : (pos + K);
+
+            // ---- swap phase: steps s = 0..S-1, step s swaps positions (i_cur - s) and s_sj[s] ----
+            if (S > 0) {
+                const int64_t own_lo = i_cur - (int64_t)S;  // targets j > own_lo lie inside the window's own range
+                int slot[2] = {-1, -1};
+                bool owner[2] = {false, false};
+                uint32_t jv[2] = {0, 0};
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int s = tid + q * NT;
+                    if (s < S) {
+                        const uint32_t j = s_sj[s];
+                        jv[q] = j;
+                        if ((int64_t)j > own_lo) {
+                            const int s2 = (int)(i_cur - (int64_t)j);
+                            if (s2 != s) {
+                                atomicOr(&s_flag[s >> 5], 1u << (s & 31));
+                                atomicOr(&s_flag[s2 >> 5], 1u << (s2 & 31));
+                            }
+                        } else {
+                            uint32_t h = (j * 2654435761u) >> HS_SHIFT;
+                            while (true) {
+                                const uint32_t prev = atomicCAS(&s_keys[h], SQB_EMPTY_KEY, j);
+                                if (prev == SQB_EMPTY_KEY) {
+                                    owner[q] = true;
+                                    break;
+                                }
+                                if (prev == j) {
+                                    s_dup[h] = 1;
+                                    atomicOr(&s_flag[s >> 5], 1u << (s & 31));
+                                    break;
+                                }
+                                h = (h + 1) & (HS - 1);
+                            }
+                            slot[q] = (int)h;
+                        }
+                    }
+                }
+                // stage values: own range (coalesced) and distinct external targets (random)
+                LT vo[2], vh[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int s = tid + q * NT;
+                    vo[q] = (s < S) ? a[base + i_cur - s] : (LT)0;
+                    vh[q] = owner[q] ? a[base + (int64_t)jv[q]] : (LT)0;
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int s = tid + q * NT;
+                    if (s < S) s_own[s] = vo[q];
+                    if (owner[q]) s_hval[slot[q]] = vh[q];
+                }
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int s = tid + q * NT;
+                    if (owner[q] && s_dup[slot[q]]) atomicOr(&s_flag[s >> 5], 1u << (s & 31));
+                }
+                __syncthreads();
+                // conflict-free swaps in parallel
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int s = tid + q * NT;
+                    if (s < S && slot[q] >= 0 && !((s_flag[s >> 5] >> (s & 31)) & 1u)) {
+                        const LT t = s_own[s];
+                        s_own[s] = s_hval[slot[q]];
+                        s_hval[slot[q]] = t;
+                    }
+                }
+                // conflicting swaps in step order (disjoint from the conflict-free set)
+                if (tid == 0) {
+                    const int nwords = (S + 31) >> 5;
+                    for (int w = 0; w < nwords; ++w) {
+                        uint32_t bits = s_flag[w];
+                        while (bits) {
+                            const int b = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            const int s = w * 32 + b;
+                            const uint32_t j = s_sj[s];
+                            const LT x = s_own[s];
+                            if ((int64_t)j > own_lo) {
+                                const int s2 = (int)(i_cur - (int64_t)j);
+                                const LT y = s_own[s2];
+                                s_own[s] = y;
+                                s_own[s2] = x;
+                            } else {
+                                uint32_t h = (j * 2654435761u) >> HS_SHIFT;
+                                while (s_keys[h] != j) h = (h + 1) & (HS - 1);
+                                const LT y = s_hval[h];
+                                s_own[s] = y;
+                                s_hval[h] = x;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                // write back + reset the tables for the next window
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int s = tid + q * NT;
+                    if (s < S) a[base + i_cur - s] = s_own[s];
+                    if (owner[q]) {
+                        a[base + (int64_t)jv[q]] = s_hval[slot[q]];
+                        s_keys[slot[q]] = SQB_EMPTY_KEY;
+                        s_dup[slot[q]] = 0;
+                    }
+                }
+                if (tid < RAW / 32) s_flag[tid] = 0;
+                __syncthreads();
+            }
+            i_cur -= S;
+            pos = newpos;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. transpose [P][stride] -> [n][PB]  (32 permutations x 256 nodes per CTA), optional row scatter through
+//    `order` (library-grouped position k -> original node id)
+// ------------------------------------------------------------------------------------------------
+template <typename LT>
+__global__ void __launch_bounds__(256) nhood_transpose_kernel(const LT* __restrict__ lab, LT* __restrict__ labT, int64_t n,
+                                                              int64_t stride, int P, int PB,
+                                                              const uint32_t* __restrict__ order) {
+    __shared__ LT tile[32][256 + 16 / sizeof(LT)];
+    const int tx = threadIdx.x;
+    const int64_t node = (int64_t)blockIdx.x * 256 + tx;
+    const int pg = blockIdx.y * 32;
+#pragma unroll 8
+    for (int pp = 0; pp < 32; ++pp) {
+        const int perm = pg + pp;
+        tile[pp][tx] = (perm < P && node < n) ? lab[(int64_t)perm * stride + node] : (LT)0;
+    }
+    __syncthreads();
+    if (node < n) {
+        const int64_t row = order ? (int64_t)order[node] : node;
+        constexpr int NV = (int)(32 * sizeof(LT) / 16);
+        union {
+            LT e[32];
+            uint4 v[NV];
+        } pack;
+#pragma unroll
+        for (int pp = 0; pp < 32; ++pp) pack.e[pp] = tile[pp][tx];
+        uint4* dst = reinterpret_cast<uint4*>(labT + row * PB + pg);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) dst[k] = pack.v[k];
+    }
+}
+
+// single label vector (uint32 from the host) -> column 0 of a [n][32] permutation-minor matrix
+template <typename LT>
+__global__ void nhood_single_to_T_kernel(const uint32_t* __restrict__ labels, LT* __restrict__ labT, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) labT[i * 32] = (LT)labels[i];
+}
+
+template <typename LT>
+__global__ void nhood_u32_to_lt_kernel(const uint32_t* __restrict__ src, LT* __restrict__ dst, int64_t n, int64_t n_pad) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n_pad) dst[i] = (i < n) ? (LT)src[i] : (LT)0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4. count: hist[(a*C+b)*G + perm_in_group] over the nodes of this CTA's chunk.
+//    G = permutations per CTA; lane = (edge slot = lane / G, perm = lane % G).  With G = 32 every lane owns
+//    its own histogram column (bank == lane): shared-memory atomics never conflict inside a warp.
+// ------------------------------------------------------------------------------------------------
+template <typename LT, int G>
+__global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
+                                   const LT* __restrict__ labT, int PB, int64_t n, int C, int64_t nodes_per_cta, int P,
+                                   uint32_t* __restrict__ counts) {
+    extern __shared__ uint32_t hist[];
+    const int nb = C * C * G;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    constexpr int EPW = 32 / G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int sub = lane / G, pl = lane % G;
+    const int perm = blockIdx.y * G + pl;
+    const bool valid = perm < P;
+    const int64_t node_begin = (int64_t)blockIdx.x * nodes_per_cta;
+    int64_t node_end = node_begin + nodes_per_cta;
+    if (node_end > n) node_end = n;
+    const LT* __restrict__ col = labT + perm;  // column of this lane's permutation (padded columns exist up to PB)
+    for (int64_t i = node_begin + warp; i < node_end; i += nwarps) {
+        const uint32_t beg = indptr[i], end = indptr[i + 1];
+        const uint32_t a = (uint32_t)col[i * PB];
+        const uint32_t rowbase = a * (uint32_t)C;
+#pragma unroll 4
+        for (uint32_t e = beg + sub; e < end; e += EPW) {
+            const uint32_t j = indices[e];
+            const uint32_t b = (uint32_t)col[(int64_t)j * PB];
+            if (valid) atomicAdd(&hist[(rowbase + b) * G + pl], 1u);
+        }
+    }
+    __syncthreads();
+    const int CC = C * C;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        const uint32_t v = hist[i];
+        const int p = blockIdx.y * G + (i % G);
+        if (v != 0 && p < P) atomicAdd(&counts[(int64_t)p * CC + (i / G)], v);
+    }
+}
+
+// fallback for very large n_cls: global atomics, lane = permutation
+template <typename LT>
+__global__ void nhood_count_global_kernel(const uint32_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
+                                          const LT* __restrict__ labT, int PB, int64_t n, int C, int64_t nodes_per_cta,
+                                          int P, uint32_t* __restrict__ counts) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int perm = blockIdx.y * 32 + lane;
+    const bool valid = perm < P;
+    const int64_t node_begin = (int64_t)blockIdx.x * nodes_per_cta;
+    int64_t node_end = node_begin + nodes_per_cta;
+    if (node_end > n) node_end = n;
+    const LT* __restrict__ col = labT + perm;
+    const int64_t CC = (int64_t)C * C;
+    for (int64_t i = node_begin + warp; i < node_end; i += nwarps) {
+        const uint32_t beg = indptr[i], end = indptr[i + 1];
+        const uint32_t a = (uint32_t)col[i * PB];
+        for (uint32_t e = beg; e < end; ++e) {
+            const uint32_t b = (uint32_t)col[(int64_t)indices[e] * PB];
+            if (valid) atomicAdd(&counts[(int64_t)perm * CC + (int64_t)a * C + b], 1u);
+        }
+    }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+struct sqb_nhood {
+    sqb_ctx* ctx = nullptr;
+    int64_t n = 0, nnz = 0, stride = 0;
+    int n_cls = 0;
+    int lt_bytes = 1;  // 1: uint8 labels (n_cls <= 256), 2: uint16
+    DevBuf<uint32_t> d_indptr, d_indices;
+    DevBuf<uint8_t> d_base;   // stride * lt_bytes, library-grouped order
+    DevBuf<uint32_t> d_order;  // grouped position -> node id (only with libraries)
+    bool has_order = false;
+    DevBuf<int64_t> d_seg_start, d_seg_len;
+    int nseg = 0;
+    bool base_set = false;
+    DevBuf<uint64_t> d_states;  // P x 4
+    int64_t n_perms = 0;
+    bool uploaded = false, ran = false;
+    DevBuf<uint8_t> d_lab;   // [chunk][stride] LT
+    DevBuf<uint8_t> d_labT;  // [n][PB] LT
+    DevBuf<uint32_t> d_counts;  // [P][C*C]
+    DevBuf<uint32_t> d_tmp_u32;
+    std::vector<uint32_t> h_order;
+    // options
+    int shuffle_algo = 1;
+    int shuffle_threads = 512;
+    int64_t perm_chunk = 0;  // 0 = auto
+    int count_algo = 0;
+};
+
+template <typename LT>
+static int launch_count(sqb_nhood* h, const LT* labT, int PB, int P, uint32_t* d_counts) {
+    sqb_ctx* c = h->ctx;
+    const int C = h->n_cls;
+    const size_t smem_limit = c->smem_optin > 8192 ? c->smem_optin - 4096 : 40000;
+    int G = 0;
+    if (h->count_algo != 2) {
+        for (int g = 32; g >= 1; g >>= 1) {
+            if ((size_t)C * C * g * 4 <= smem_limit) {
+                G = g;
+                break;
+            }
+        }
+    }
+    const int ngroups_of = (G > 0) ? G : 32;
+    const int ngroups = (P + ngroups_of - 1) / ngroups_of;
+    int64_t nchunk = ceil_div64((int64_t)4 * c->sm_count, ngroups);
+    const int64_t max_chunk = ceil_div64(h->n, 512);
+    if (nchunk > max_chunk) nchunk = max_chunk;
+    if (nchunk < 1) nchunk = 1;
+    const int64_t nodes_per_cta = ceil_div64(h->n, nchunk);
+    nchunk = ceil_div64(h->n, nodes_per_cta);
+    dim3 grid((unsigned)nchunk, (unsigned)ngroups);
+    SqbLaunchScope scope(c, SQB_K_NHOOD_COUNT);
+    if (G == 0) {
+        nhood_count_global_kernel<LT><<<grid, 256, 0, c->stream>>>(h->d_indptr.p, h->d_indices.p, labT, PB, h->n, C,
+                                                                   nodes_per_cta, P, d_counts);
+        SQB_POST_LAUNCH();
+        return SQB_OK;
+    }
+    const size_t smem = (size_t)C * C * G * 4;
+    const int threads = smem > 100 * 1024 ? 1024 : 512;
+#define SQB_COUNT_CASE(GV)                                                                                        \
+    case GV: {                                                                                                    \
+        auto k = nhood_count_kernel<LT, GV>;                                                                      \
+        SQB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+        k<<<grid, threads, smem, c->stream>>>(h->d_indptr.p, h->d_indices.p, labT, PB, h->n, C, nodes_per_cta, P, \
+                                              d_counts);                                                          \
+    } break;
+    switch (G) {
+        SQB_COUNT_CASE(32)
+        SQB_COUNT_CASE(16)
+        SQB_COUNT_CASE(8)
+        SQB_COUNT_CASE(4)
+        SQB_COUNT_CASE(2)
+        SQB_COUNT_CASE(1)
+    }
+#undef SQB_COUNT_CASE
+    SQB_POST_LAUNCH();
+    return SQB_OK;
+}
+
+template <typename LT>
+static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np) {
+    sqb_ctx* c = h->ctx;
+    SqbLaunchScope scope(c, SQB_K_NHOOD_SHUFFLE);
+    if (h->shuffle_algo == 0) {
+        nhood_shuffle_serial_kernel<LT><<<(unsigned)ceil_div64(np, 32), 32, 0, c->stream>>>(
+            lab, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p);
+    } else {
+        switch (h->shuffle_threads) {
+            case 128:
+                nhood_shuffle_cta_kernel<LT, 128><<<(unsigned)np, 128, 0, c->stream>>>(lab, h->stride, states, h->nseg,
+                                                                                       h->d_seg_start.p, h->d_seg_len.p);
+                break;
+            case 256:
+                nhood_shuffle_cta_kernel<LT, 256><<<(unsigned)np, 256, 0, c->stream>>>(lab, h->stride, states, h->nseg,
+                                                                                       h->d_seg_start.p, h->d_seg_len.p);
+                break;
+            case 1024:
+                nhood_shuffle_cta_kernel<LT, 1024><<<(unsigned)np, 1024, 0, c->stream>>>(
+                    lab, h->stride, states, h->nseg, h->d_seg_start.p, h->d_seg_len.p);
+                break;
+            default:
+                nhood_shuffle_cta_kernel<LT, 512><<<(unsigned)np, 512, 0, c->stream>>>(lab, h->stride, states, h->nseg,
+                                                                                       h->d_seg_start.p, h->d_seg_len.p);
+                break;
+        }
+    }
+    SQB_POST_LAUNCH();
+    return SQB_OK;
+}
+
+static int64_t auto_chunk(sqb_nhood* h) {
+    if (h->perm_chunk > 0) return ((h->perm_chunk + 31) / 32) * 32;
+    // keep [chunk][stride] + [n][chunk] under ~8 GB
+    int64_t per_perm = 2 * h->stride * h->lt_bytes;
+    int64_t ch = (int64_t)8e9 / (per_perm > 0 ? per_perm : 1);
+    if (ch < 32) ch = 32;
+    if (ch > 16384) ch = 16384;
+    return (ch / 32) * 32;
+}
+
+template <typename LT>
+static int run_chunk(sqb_nhood* h, int64_t p0, int64_t np, bool do_count) {
+    sqb_ctx* c = h->ctx;
+    LT* lab = reinterpret_cast<LT*>(h->d_lab.p);
+    LT* labT = reinterpret_cast<LT*>(h->d_labT.p);
+    const int64_t vec_per_row = h->stride * (int64_t)sizeof(LT) / 16;
+    {
+        SqbLaunchScope scope(c, SQB_K_NHOOD_FILL);
+        unsigned gx = (unsigned)ceil_div64(vec_per_row, 256 * 4);
+        if (gx < 1) gx = 1;
+        if (gx > 64) gx = 64;
+        dim3 fgrid(gx, (unsigned)(np < 4096 ? np : 4096));
+        nhood_fill_kernel<<<fgrid, 256, 0, c->stream>>>(reinterpret_cast<uint4*>(lab),
+                                                                  reinterpret_cast<const uint4*>(h->d_base.p),
+                                                                  vec_per_row, np);
+        SQB_POST_LAUNCH();
+    }
+    SQB_TRY(launch_shuffle<LT>(h, lab, h->d_states.p + p0 * 4, np));
+    if (!do_count) return SQB_OK;
+    const int PB = (int)(((np + 31) / 32) * 32);
+    {
+        SqbLaunchScope scope(c, SQB_K_NHOOD_TRANSPOSE);
+        dim3 grid((unsigned)ceil_div64(h->n, 256), (unsigned)(PB / 32));
+        nhood_transpose_kernel<LT><<<grid, 256, 0, c->stream>>>(lab, labT, h->n, h->stride, (int)np, PB,
+                                                                h->has_order ? h->d_order.p : nullptr);
+        SQB_POST_LAUNCH();
+    }
+    SQB_TRY(launch_count<LT>(h, labT, PB, (int)np, h->d_counts.p + p0 * (int64_t)h->n_cls * h->n_cls));
+    return SQB_OK;
+}
+
+static int ensure_buffers(sqb_nhood* h, int64_t chunk) {
+    SQB_TRY(h->d_lab.alloc((size_t)chunk * h->stride * h->lt_bytes));
+    SQB_TRY(h->d_labT.alloc((size_t)h->n * chunk * h->lt_bytes));
+    return SQB_OK;
+}
+
+extern "C" {
+
+int sqb_nhood_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const uint32_t* indptr, const uint32_t* indices, int n_cls,
+                     sqb_nhood** out) {
+    SQB_CHECK(ctx && out, SQB_ERR_INVALID, "sqb_nhood_create: null ctx/out");
+    SQB_CHECK(n >= 1 && n < 0xFFFFFFFFLL, SQB_ERR_INVALID, "sqb_nhood_create: n=%lld out of range [1, 2^32-1)", (long long)n);
+    SQB_CHECK(nnz >= 0 && nnz < 0xFFFFFFFFLL, SQB_ERR_INVALID, "sqb_nhood_create: nnz=%lld does not fit uint32",
+              (long long)nnz);
+    // same message as the reference (_nhood.py:107-108)
+    SQB_CHECK(n_cls >= 2, SQB_ERR_INVALID, "Expected at least `2` clusters, found `%d`.", n_cls);
+    SQB_CHECK(n_cls <= 65535, SQB_ERR_UNSUPPORTED, "sqb_nhood_create: n_cls=%d > 65535 unsupported", n_cls);
+    SQB_CHECK(indptr && (indices || nnz == 0), SQB_ERR_INVALID, "sqb_nhood_create: null CSR arrays");
+    SQB_CHECK(indptr[0] == 0 && (int64_t)indptr[n] == nnz, SQB_ERR_INVALID,
+              "sqb_nhood_create: indptr[0]=%u indptr[n]=%u inconsistent with nnz=%lld", indptr[0], indptr[n],
+              (long long)nnz);
+    SQB_CUDA(cudaSetDevice(ctx->device));
+    sqb_nhood* h = new sqb_nhood();
+    h->ctx = ctx;
+    h->n = n;
+    h->nnz = nnz;
+    h->n_cls = n_cls;
+    h->lt_bytes = n_cls <= 256 ? 1 : 2;
+    h->stride = ((n + 15) / 16) * 16;
+    int rc;
+    if ((rc = h->d_indptr.alloc(n + 1)) != SQB_OK || (rc = h->d_indices.alloc(nnz > 0 ? nnz : 1)) != SQB_OK) {
+        sqb_nhood_destroy(h);
+        return rc;
+    }
+    SQB_CUDA(cudaMemcpyAsync(h->d_indptr.p, indptr, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz > 0)
+        SQB_CUDA(cudaMemcpyAsync(h->d_indices.p, indices, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    SQB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = h;
+    return SQB_OK;
+}
+
+int sqb_nhood_destroy(sqb_nhood* h) {
+    if (!h) return SQB_OK;
+    cudaSetDevice(h->ctx->device);
+    h->d_indptr.release();
+    h->d_indices.release();
+    h->d_base.release();
+    h->d_order.release();
+    h->d_seg_start.release();
+    h->d_seg_len.release();
+    h->d_states.release();
+    h->d_lab.release();
+    h->d_labT.release();
+    h->d_counts.release();
+    h->d_tmp_u32.release();
+    delete h;
+    return SQB_OK;
+}
+
+int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value) {
+    SQB_CHECK(h && key, SQB_ERR_INVALID, "sqb_nhood_set_option: null argument");
+    if (!strcmp(key, "shuffle_algo")) {
+        SQB_CHECK(value == 0 || value == 1, SQB_ERR_INVALID, "shuffle_algo must be 0 or 1");
+        h->shuffle_algo = (int)value;
+    } else if (!strcmp(key, "shuffle_threads")) {
+        SQB_CHECK(value == 128 || value == 256 || value == 512 || value == 1024, SQB_ERR_INVALID,
+                  "shuffle_threads must be 128, 256, 512 or 1024");
+        h->shuffle_threads = (int)value;
+    } else if (!strcmp(key, "perm_chunk")) {
+        SQB_CHECK(value >= 0, SQB_ERR_INVALID, "perm_chunk must be >= 0");
+        h->perm_chunk = value;
+    } else if (!strcmp(key, "count_algo")) {
+        SQB_CHECK(value >= 0 && value <= 2, SQB_ERR_INVALID, "count_algo must be 0, 1 or 2");
+        h->count_algo = (int)value;
+    } else {
+        sqb_set_error("sqb_nhood_set_option: unknown key '%s'", key);
+        return SQB_ERR_INVALID;
+    }
+    return SQB_OK;
+}
+
+int sqb_nhood_bytes_per_perm(sqb_nhood* h, int64_t* bytes) {
+    SQB_CHECK(h && bytes, SQB_ERR_INVALID, "sqb_nhood_bytes_per_perm: null argument");
+    *bytes = 4 * h->nnz + 4 * (h->n + 1) + 8 * h->n + 4 * (int64_t)h->n_cls * h->n_cls;
+    return SQB_OK;
+}
+
+int sqb_nhood_count(sqb_nhood* h, const uint32_t* labels, uint32_t* out) {
+    SQB_CHECK(h && labels && out, SQB_ERR_INVALID, "sqb_nhood_count: null argument");
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    for (int64_t i = 0; i < h->n; ++i)
+        SQB_CHECK(labels[i] < (uint32_t)h->n_cls, SQB_ERR_INVALID, "sqb_nhood_count: labels[%lld]=%u >= n_cls=%d",
+                  (long long)i, labels[i], h->n_cls);
+    const int64_t CC = (int64_t)h->n_cls * h->n_cls;
+    DevBuf<uint8_t> labT;
+    DevBuf<uint32_t> cnt;
+    int rc = SQB_OK;
+    if ((rc = h->d_tmp_u32.alloc(h->n)) != SQB_OK) return rc;
+    if ((rc = labT.alloc((size_t)h->n * 32 * h->lt_bytes)) != SQB_OK) return rc;
+    if ((rc = cnt.alloc(CC)) != SQB_OK) {
+        labT.release();
+        return rc;
+    }
+    auto cleanup = [&]() {
+        labT.release();
+        cnt.release();
+    };
+    cudaError_t e;
+    e = cudaMemcpyAsync(h->d_tmp_u32.p, labels, h->n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(labT.p, 0, (size_t)h->n * 32 * h->lt_bytes, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(cnt.p, 0, CC * sizeof(uint32_t), c->stream);
+    if (e != cudaSuccess) {
+        cleanup();
+        sqb_set_error("sqb_nhood_count: %s", cudaGetErrorString(e));
+        return SQB_ERR_CUDA;
+    }
+    {
+        SqbLaunchScope scope(c, SQB_K_MISC);
+        unsigned g = (unsigned)ceil_div64(h->n, 256);
+        if (h->lt_bytes == 1)
+            nhood_single_to_T_kernel<uint8_t><<<g, 256, 0, c->stream>>>(h->d_tmp_u32.p, labT.p, h->n);
+        else
+            nhood_single_to_T_kernel<uint16_t><<<g, 256, 0, c->stream>>>(h->d_tmp_u32.p, reinterpret_cast<uint16_t*>(labT.p), h->n);
+    }
+    rc = (h->lt_bytes == 1) ? launch_count<uint8_t>(h, labT.p, 32, 1, cnt.p)
+                            : launch_count<uint16_t>(h, reinterpret_cast<uint16_t*>(labT.p), 32, 1, cnt.p);
+    if (rc == SQB_OK) {
+        e = cudaMemcpyAsync(out, cnt.p, CC * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            sqb_set_error("sqb_nhood_count: %s", cudaGetErrorString(e));
+            rc = SQB_ERR_CUDA;
+        }
+    }
+    cleanup();
+    return rc;
+}
+
+int sqb_nhood_set_base(sqb_nhood* h, const uint32_t* base_labels, const int32_t* lib_codes, int n_libs) {
+    SQB_CHECK(h && base_labels, SQB_ERR_INVALID, "sqb_nhood_set_base: null argument");
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    const int64_t n = h->n;
+    for (int64_t i = 0; i < n; ++i)
+        SQB_CHECK(base_labels[i] < (uint32_t)h->n_cls, SQB_ERR_INVALID, "sqb_nhood_set_base: labels[%lld]=%u >= n_cls=%d",
+                  (long long)i, base_labels[i], h->n_cls);
+    std::vector<int64_t> seg_start, seg_len;
+    std::vector<uint32_t> grouped(n);
+    h->h_order.clear();
+    h->has_order = false;
+    if (lib_codes && n_libs > 0) {
+        // category order, ascending index inside a category: np.where(libraries == c)[0]  (gr/_utils.py:208-209)
+        std::vector<int64_t> cnt(n_libs + 1, 0);
+        for (int64_t i = 0; i < n; ++i) {
+            SQB_CHECK(lib_codes[i] >= 0 && lib_codes[i] < n_libs, SQB_ERR_INVALID,
+                      "sqb_nhood_set_base: lib_codes[%lld]=%d outside [0,%d) (NaN libraries are unsupported)",
+                      (long long)i, lib_codes[i], n_libs);
+            cnt[lib_codes[i] + 1]++;
+        }
+        for (int l = 0; l < n_libs; ++l) cnt[l + 1] += cnt[l];
+        h->h_order.resize(n);
+        std::vector<int64_t> cur(cnt.begin(), cnt.end() - 1);
+        for (int64_t i = 0; i < n; ++i) {
+            int64_t k = cur[lib_codes[i]]++;
+            h->h_order[k] = (uint32_t)i;
+            grouped[k] = base_labels[i];
+        }
+        for (int l = 0; l < n_libs; ++l) {
+            seg_start.push_back(cnt[l]);
+            seg_len.push_back(cnt[l + 1] - cnt[l]);
+        }
+        h->has_order = true;
+    } else {
+        for (int64_t i = 0; i < n; ++i) grouped[i] = base_labels[i];
+        seg_start.push_back(0);
+        seg_len.push_back(n);
+    }
+    h->nseg = (int)seg_start.size();
+    SQB_TRY(h->d_seg_start.alloc(h->nseg));
+    SQB_TRY(h->d_seg_len.alloc(h->nseg));
+    SQB_TRY(h->d_tmp_u32.alloc(n));
+    SQB_TRY(h->d_base.alloc((size_t)h->stride * h->lt_bytes));
+    SQB_CUDA(cudaMemcpyAsync(h->d_seg_start.p, seg_start.data(), h->nseg * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    SQB_CUDA(cudaMemcpyAsync(h->d_seg_len.p, seg_len.data(), h->nseg * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    SQB_CUDA(cudaMemcpyAsync(h->d_tmp_u32.p, grouped.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    if (h->has_order) {
+        SQB_TRY(h->d_order.alloc(n));
+        SQB_CUDA(cudaMemcpyAsync(h->d_order.p, h->h_order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    {
+        SqbLaunchScope scope(c, SQB_K_MISC);
+        unsigned g = (unsigned)ceil_div64(h->stride, 256);
+        if (h->lt_bytes == 1)
+            nhood_u32_to_lt_kernel<uint8_t><<<g, 256, 0, c->stream>>>(h->d_tmp_u32.p, h->d_base.p, n, h->stride);
+        else
+            nhood_u32_to_lt_kernel<uint16_t><<<g, 256, 0, c->stream>>>(h->d_tmp_u32.p, reinterpret_cast<uint16_t*>(h->d_base.p), n, h->stride);
+        SQB_POST_LAUNCH();
+    }
+    SQB_CUDA(cudaStreamSynchronize(c->stream));  // host vectors go out of scope
+    h->base_set = true;
+    return SQB_OK;
+}
+
+int sqb_nhood_permute_upload(sqb_nhood* h, const uint64_t* states, int64_t n_perms) {
+    SQB_CHECK(h && states, SQB_ERR_INVALID, "sqb_nhood_permute_upload: null argument");
+    SQB_CHECK(n_perms >= 1, SQB_ERR_INVALID, "sqb_nhood_permute_upload: n_perms=%lld must be positive", (long long)n_perms);
+    SQB_CHECK(h->base_set, SQB_ERR_STATE, "sqb_nhood_permute_upload: call sqb_nhood_set_base first");
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    std::vector<uint64_t> packed((size_t)n_perms * 4);
+    for (int64_t p = 0; p < n_perms; ++p) {
+        SQB_CHECK(states[p * 6 + 4] == 0, SQB_ERR_UNSUPPORTED,
+                  "sqb_nhood_permute: generator %lld has a buffered uint32 (has_uint32=1); only fresh generators are supported",
+                  (long long)p);
+        for (int k = 0; k < 4; ++k) packed[p * 4 + k] = states[p * 6 + k];
+    }
+    SQB_TRY(h->d_states.alloc((size_t)n_perms * 4));
+    SQB_TRY(h->d_counts.alloc((size_t)n_perms * h->n_cls * h->n_cls));
+    int64_t chunk = auto_chunk(h);
+    if (chunk > ((n_perms + 31) / 32) * 32) chunk = ((n_perms + 31) / 32) * 32;
+    SQB_TRY(ensure_buffers(h, chunk));
+    SQB_CUDA(cudaMemcpyAsync(h->d_states.p, packed.data(), packed.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    SQB_CUDA(cudaStreamSynchronize(c->stream));
+    h->n_perms = n_perms;
+    h->uploaded = true;
+    h->ran = false;
+    return SQB_OK;
+}
+
+int sqb_nhood_permute_run_async(sqb_nhood* h) {
+    SQB_CHECK(h, SQB_ERR_INVALID, "sqb_nhood_permute_run_async: null handle");
+    SQB_CHECK(h->uploaded, SQB_ERR_STATE, "sqb_nhood_permute_run_async: call sqb_nhood_permute_upload first");
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    const int64_t CC = (int64_t)h->n_cls * h->n_cls;
+    SQB_CUDA(cudaMemsetAsync(h->d_counts.p, 0, (size_t)h->n_perms * CC * sizeof(uint32_t), c->stream));
+    int64_t chunk = auto_chunk(h);
+    for (int64_t p0 = 0; p0 < h->n_perms; p0 += chunk) {
+        int64_t np = h->n_perms - p0 < chunk ? h->n_perms - p0 : chunk;
+        if (h->lt_bytes == 1)
+            SQB_TRY(run_chunk<uint8_t>(h, p0, np, true));
+        else
+            SQB_TRY(run_chunk<uint16_t>(h, p0, np, true));
+    }
+    h->ran = true;
+    return SQB_OK;
+}
+
+int sqb_nhood_permute_download(sqb_nhood* h, uint32_t* out_counts) {
+    SQB_CHECK(h && out_counts, SQB_ERR_INVALID, "sqb_nhood_permute_download: null argument");
+    SQB_CHECK(h->ran, SQB_ERR_STATE, "sqb_nhood_permute_download: nothing has run");
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    const int64_t CC = (int64_t)h->n_cls * h->n_cls;
+    SQB_CUDA(cudaMemcpyAsync(out_counts, h->d_counts.p, (size_t)h->n_perms * CC * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    SQB_CUDA(cudaStreamSynchronize(c->stream));
+    return SQB_OK;
+}
+
+int sqb_nhood_permute(sqb_nhood* h, const uint64_t* states, int64_t n_perms, uint32_t* out_counts) {
+    SQB_TRY(sqb_nhood_permute_upload(h, states, n_perms));
+    SQB_TRY(sqb_nhood_permute_run_async(h));
+    return sqb_nhood_permute_download(h, out_counts);
+}
+
+int sqb_nhood_shuffled_labels(sqb_nhood* h, int64_t p0, int64_t p1, uint32_t* out) {
+    SQB_CHECK(h && out, SQB_ERR_INVALID, "sqb_nhood_shuffled_labels: null argument");
+    SQB_CHECK(h->uploaded, SQB_ERR_STATE, "sqb_nhood_shuffled_labels: call sqb_nhood_permute_upload first");
+    SQB_CHECK(p0 >= 0 && p0 < p1 && p1 <= h->n_perms, SQB_ERR_INVALID, "sqb_nhood_shuffled_labels: bad range [%lld,%lld)",
+              (long long)p0, (long long)p1);
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    const size_t row_bytes = (size_t)h->stride * h->lt_bytes;
+    int64_t step = auto_chunk(h);
+    const int64_t cap = (int64_t)(h->d_lab.n / row_bytes);
+    if (step > cap) step = cap;
+    SQB_CHECK(step >= 1, SQB_ERR_STATE, "sqb_nhood_shuffled_labels: label buffer not allocated");
+    std::vector<uint8_t> host(row_bytes);
+    for (int64_t q0 = p0; q0 < p1; q0 += step) {
+        const int64_t np = p1 - q0 < step ? p1 - q0 : step;
+        if (h->lt_bytes == 1)
+            SQB_TRY(run_chunk<uint8_t>(h, q0, np, false));
+        else
+            SQB_TRY(run_chunk<uint16_t>(h, q0, np, false));
+        for (int64_t p = 0; p < np; ++p) {
+            SQB_CUDA(cudaMemcpyAsync(host.data(), h->d_lab.p + (size_t)p * row_bytes, row_bytes, cudaMemcpyDeviceToHost,
+                                     c->stream));
+            SQB_CUDA(cudaStreamSynchronize(c->stream));
+            uint32_t* row = out + (size_t)(q0 - p0 + p) * h->n;
+            for (int64_t k = 0; k < h->n; ++k) {
+                uint32_t v = h->lt_bytes == 1 ? host[k] : reinterpret_cast<uint16_t*>(host.data())[k];
+                row[h->has_order ? h->h_order[k] : k] = v;
+            }
+        }
+    }
+    return SQB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+"""``nhood_enrichment`` — drop-in for ``squidpy.gr.nhood_enrichment`` (``src/squidpy/gr/_nhood.py:146-242``) running the
+permutation test on a B200 through ``libsquidpy_b200.so``.
+
+Same signature, same ``adata.uns`` keys, same exceptions.  ``numba_parallel``, ``n_jobs``, ``backend`` and
+``show_progress_bar`` are accepted for compatibility and ignored (the joblib fan-out over permutations is replaced by
+one CTA per permutation on the GPU).  Extra keyword-only argument: ``device``.
+Z-scores are computed on the host from the per-permutation uint32 counts exactly like the reference
+(float64 ``mean``/``std`` over permutations, :231), so with the same ``seed`` they are identical to the reference's.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Any, NamedTuple
+
+import numpy as np
+
+from .._constants import Key
+from .._dist import all_gather_rows, shard_range, world
+from .._lib import Context, check, default_context, load
+from .._rng import spawn_states
+from .._validators import assert_categorical_obs, assert_connectivity_key, assert_positive, extract_adata_if_sdata
+from ._utils import _save_data, as_csr, category_codes, logg
+
+__all__ = ["nhood_enrichment", "NhoodEnrichmentResult", "NhoodPlan"]
+
+
+class NhoodEnrichmentResult(NamedTuple):
+    """Result of :func:`nhood_enrichment` (``_nhood.py:44-48``)."""
+
+    zscore: np.ndarray
+    counts: np.ndarray  # 'count' clashes with tuple.count
+
+
+def _as_u32(a) -> np.ndarray:
+    """uint32 view of a CSR index array (reference: ``.astype(uint32)``, ``_nhood.py:205``).  int32 input is
+    re-interpreted in place — no copy, so page-locked caller buffers stay page-locked for the H2D copy."""
+    a = np.asarray(a)
+    if a.dtype == np.int32 and a.flags.c_contiguous:
+        if a.size and a.min() < 0:
+            raise ValueError("Negative CSR index.")
+        return a.view(np.uint32)
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+class NhoodPlan:
+    """Device-resident neighbour graph (CSR) + kernels: the object behind the C-ABI handle ``sqb_nhood``.
+
+    ``count(labels)`` replaces ``_test(indices, indptr, clustering)`` (``_nhood.py:208-209``);
+    ``permute(states)`` replaces ``_nhood_enrichment_helper`` over all permutations (``_nhood.py:516-547``)."""
+
+    def __init__(self, indptr: np.ndarray, indices: np.ndarray, n_cls: int, ctx: Context | None = None):
+        self._lib = load()
+        self.ctx = ctx or default_context()
+        self.indptr = _as_u32(indptr)
+        self.indices = _as_u32(indices)
+        self.n = self.indptr.size - 1
+        self.n_cls = int(n_cls)
+        h = C.c_void_p()
+        check(
+            self._lib.sqb_nhood_create(self.ctx.handle, self.n, self.indices.size, self.indptr.ctypes.data,
+                                       self.indices.ctypes.data, self.n_cls, C.byref(h))
+        )
+        self._h = h
+        self.n_perms = 0
+
+    def set_option(self, key: str, value: int) -> None:
+        check(self._lib.sqb_nhood_set_option(self._h, key.encode(), int(value)))
+
+    @property
+    def bytes_per_perm(self) -> int:
+        b = C.c_int64()
+        check(self._lib.sqb_nhood_bytes_per_perm(self._h, C.byref(b)))
+        return b.value
+
+    def count(self, labels: np.ndarray) -> np.ndarray:
+        labels = np.ascontiguousarray(labels, dtype=np.uint32)
+        if labels.size != self.n:
+            raise ValueError(f"Expected `{self.n}` labels, found `{labels.size}`.")
+        out = np.empty((self.n_cls, self.n_cls), dtype=np.uint32)
+        check(self._lib.sqb_nhood_count(self._h, labels.ctypes.data, out.ctypes.data))
+        return out
+
+    def set_base(self, labels: np.ndarray, lib_codes: np.ndarray | None = None, n_libs: int = 0) -> None:
+        labels = np.ascontiguousarray(labels, dtype=np.uint32)
+        if labels.size != self.n:
+            raise ValueError(f"Expected `{self.n}` labels, found `{labels.size}`.")
+        lc = None if lib_codes is None else np.ascontiguousarray(lib_codes, dtype=np.int32)
+        check(self._lib.sqb_nhood_set_base(self._h, labels.ctypes.data, None if lc is None else lc.ctypes.data, int(n_libs)))
+
+    def upload(self, states: np.ndarray) -> None:
+        states = np.ascontiguousarray(states, dtype=np.uint64)
+        if states.ndim != 2 or states.shape[1] != 6:
+            raise ValueError("Expected generator states of shape (n_perms, 6).")
+        check(self._lib.sqb_nhood_permute_upload(self._h, states.ctypes.data, states.shape[0]))
+        self.n_perms = states.shape[0]
+
+    def run_async(self) -> None:
+        check(self._lib.sqb_nhood_permute_run_async(self._h))
+
+    def download(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.n_perms, self.n_cls, self.n_cls), dtype=np.uint32)
+        check(self._lib.sqb_nhood_permute_download(self._h, out.ctypes.data))
+        return out
+
+    def permute(self, states: np.ndarray) -> np.ndarray:
+        """uint32 (n_perms, n_cls, n_cls) neighbour-pair counts of every permutation."""
+        states = np.ascontiguousarray(states, dtype=np.uint64)
+        out = np.empty((states.shape[0], self.n_cls, self.n_cls), dtype=np.uint32)
+        check(self._lib.sqb_nhood_permute(self._h, states.ctypes.data, states.shape[0], out.ctypes.data))
+        self.n_perms = states.shape[0]
+        return out
+
+    def shuffled_labels(self, p0: int, p1: int) -> np.ndarray:
+        out = np.empty((p1 - p0, self.n), dtype=np.uint32)
+        check(self._lib.sqb_nhood_shuffled_labels(self._h, p0, p1, out.ctypes.data))
+        return out
+
+    def close(self) -> None:
+        if self._h is not None:
+            self._lib.sqb_nhood_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def nhood_enrichment(
+    adata: Any,
+    cluster_key: str,
+    library_key: str | None = None,
+    connectivity_key: str | None = None,
+    n_perms: int = 1000,
+    numba_parallel: bool = False,
+    seed: int | None = None,
+    copy: bool = False,
+    n_jobs: int | None = None,
+    backend: str = "loky",
+    show_progress_bar: bool = True,
+    *,
+    table_key: str | None = None,
+    device: int | None = None,
+) -> NhoodEnrichmentResult | None:
+    """Compute neighborhood enrichment by permutation test (see module docstring).
+
+    Returns ``NhoodEnrichmentResult(zscore, counts)`` if ``copy=True``; otherwise writes
+    ``adata.uns[f'{cluster_key}_nhood_enrichment'] = {'zscore': float64[C,C], 'count': uint32[C,C]}``.
+    Under an initialised ``torch.distributed`` process group (one process per GPU) the permutations are sharded
+    over the ranks and the per-permutation counts all-gathered once; every rank gets the full result."""
+    adata = extract_adata_if_sdata(adata, table_key=table_key)
+    connectivity_key = Key.obsp.spatial_conn(connectivity_key)
+    assert_categorical_obs(adata, cluster_key)
+    assert_connectivity_key(adata, connectivity_key)
+    assert_positive(n_perms, name="n_perms")
+
+    adj = as_csr(adata.obsp[connectivity_key])
+    int_clust, n_cls = category_codes(adata.obs[cluster_key], dtype=np.uint32)
+    if n_cls <= 1:
+        raise ValueError(f"Expected at least `2` clusters, found `{n_cls}`.")  # _nhood.py:107-108
+
+    lib_codes, n_libs = None, 0
+    if library_key is not None:
+        assert_categorical_obs(adata, key=library_key)
+        libs = adata.obs[library_key]
+        lib_codes = np.asarray(libs.cat.codes).astype(np.int32)
+        n_libs = len(libs.cat.categories)
+
+    start = time.perf_counter()
+    ctx = default_context(device)
+    plan = NhoodPlan(adj.indptr, adj.indices, n_cls, ctx)
+    try:
+        count = plan.count(int_clust)
+        rank, ws = world()
+        lo, hi = shard_range(int(n_perms), rank, ws)
+        logg.info("Calculating neighborhood enrichment on cuda:%d (rank %d/%d, permutations %d..%d)", ctx.device, rank, ws, lo, hi)
+        if hi > lo:
+            plan.set_base(int_clust, lib_codes, n_libs)
+            perms_local = plan.permute(spawn_states(seed, int(n_perms), lo, hi))
+        else:
+            perms_local = np.empty((0, n_cls, n_cls), dtype=np.uint32)
+        perms = all_gather_rows(perms_local, int(n_perms)).astype(np.float64)
+    finally:
+        plan.close()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        zscore = (count - perms.mean(axis=0)) / perms.std(axis=0)  # _nhood.py:231 (no zero-std guard there either)
+
+    if copy:
+        return NhoodEnrichmentResult(zscore=zscore, counts=count)
+    _save_data(adata, attr="uns", key=Key.uns.nhood_enrichment(cluster_key), data={"zscore": zscore, "count": count},
+               time_start=start)
+    return None

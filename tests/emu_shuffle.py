@@ -1,0 +1,154 @@
+"""Python emulation of the CTA-parallel exact numpy-shuffle replay implemented in squidpy_b200/csrc/nhood.cu.
+
+It mirrors the device algorithm phase by phase (RNG batch by jump-ahead, windowed acceptance fixed point,
+hash-based conflict detection, parallel swaps + ordered serial pass) so the *algorithm* can be validated on
+the CPU against numpy's ``Generator.shuffle`` (tests/test_shuffle_emulation.py).  Not used by the product.
+"""
+from __future__ import annotations
+
+import math
+import random
+
+A = 0x2360ED051FC65DA44385DF649FCCF645
+M128 = (1 << 128) - 1
+M64 = (1 << 64) - 1
+
+
+def _jump_consts(d):
+    M, C = A, 1
+    Mt, Ct = 1, 0
+    while d:
+        if d & 1:
+            Mt, Ct = (M * Mt) & M128, (M * Ct + C) & M128
+        M, C = (M * M) & M128, (M * C + C) & M128
+        d >>= 1
+    return Mt, Ct
+
+
+def _out(s):
+    hi, lo = s >> 64, s & M64
+    x = hi ^ lo
+    rot = hi >> 58
+    return ((x >> rot) | (x << ((-rot) & 63))) & M64
+
+
+def window_size(i_cur, raw_left, raw_total):
+    """K: number of raw values examined per acceptance window (mirrors sqb_window_size in nhood.cu)."""
+    k = min(i_cur // 4, int(4.0 * math.sqrt(float(i_cur))))
+    k = max(1, min(k, raw_total))
+    return min(k, raw_left)
+
+
+def emu_shuffle(arr, state, inc, segs, NT=8, rng=None, stats=None):
+    """arr: list (group-contiguous); segs: list of (start, length).  Returns shuffled list."""
+    a = list(arr)
+    RAW = 2 * NT
+    rng = rng or random.Random(0)
+    Mn, Cn = _jump_consts(NT)
+    # thread t starts at state_{t+1}
+    st = []
+    for t in range(NT):
+        Mt, Ct = _jump_consts(t + 1)
+        st.append((Mt * state + Ct * inc) & M128)
+    raw = [0] * RAW
+    pos = RAW  # force generation
+
+    def gen():
+        nonlocal pos
+        for t in range(NT):
+            o = _out(st[t])
+            raw[2 * t] = o & 0xFFFFFFFF
+            raw[2 * t + 1] = o >> 32
+            st[t] = (Mn * st[t] + Cn * inc) & M128
+        pos = 0
+
+    for (base, m) in segs:
+        i_cur = m - 1
+        while i_cur >= 1:
+            if pos == RAW:
+                gen()
+            mask = (1 << i_cur.bit_length()) - 1
+            i_lo = (mask >> 1) + 1
+            n_ph = i_cur - i_lo + 1
+            K = window_size(i_cur, RAW - pos, RAW)
+            win = list(range(pos, pos + K))
+            u = {r: raw[r] & mask for r in win}
+            # fixed point on acceptance flags
+            c = {r: 0 for r in win}
+            F = {r: u[r] <= i_cur - c[r] for r in win}
+            iters = 0
+            while True:
+                iters += 1
+                run = 0
+                for r in win:  # exclusive prefix of F
+                    c[r] = run
+                    run += 1 if F[r] else 0
+                F2 = {r: u[r] <= i_cur - c[r] for r in win}
+                if F2 == F:
+                    break
+                F = F2
+            total = sum(F.values())
+            if stats is not None:
+                stats["iters"] = stats.get("iters", 0) + iters
+                stats["windows"] = stats.get("windows", 0) + 1
+            if total >= n_ph:
+                S = n_ph
+                rstar = next(r for r in win if F[r] and c[r] == n_ph - 1)
+                newpos = rstar + 1
+            else:
+                S = total
+                newpos = pos + K
+            sj = [0] * S
+            for r in win:
+                if F[r] and c[r] < S:
+                    sj[c[r]] = u[r]
+            # ---- swap phase -------------------------------------------------------------------
+            own = [a[base + i_cur - s] for s in range(S)]
+            flags = [False] * S
+            table = {}  # key -> [owner step, value, dup]
+            order = list(range(S))
+            rng.shuffle(order)  # arbitrary thread interleaving for the CAS race
+            for s in order:
+                j = sj[s]
+                if j > i_cur - S:
+                    s2 = i_cur - j
+                    if s2 != s:
+                        flags[s] = True
+                        flags[s2] = True
+                else:
+                    if j not in table:
+                        table[j] = [s, a[base + j], False]
+                    else:
+                        table[j][2] = True
+                        flags[s] = True
+            for j, (s_own, _, dup) in table.items():
+                if dup:
+                    flags[s_own] = True
+            # parallel part
+            for s in order:
+                j = sj[s]
+                if flags[s] or j > i_cur - S:
+                    continue
+                own[s], table[j][1] = table[j][1], own[s]
+            # serial part (ascending s)
+            nconf = 0
+            for s in range(S):
+                if not flags[s]:
+                    continue
+                nconf += 1
+                j = sj[s]
+                if j > i_cur - S:
+                    s2 = i_cur - j
+                    own[s], own[s2] = own[s2], own[s]
+                else:
+                    own[s], table[j][1] = table[j][1], own[s]
+            if stats is not None:
+                stats["conf"] = stats.get("conf", 0) + nconf
+                stats["steps"] = stats.get("steps", 0) + S
+            for s in range(S):
+                a[base + i_cur - s] = own[s]
+            for j, (_, v, _) in table.items():
+                a[base + j] = v
+            i_cur -= S
+            pos = newpos
+    return a

@@ -1,0 +1,64 @@
+"""world_size-2 gloo tests of the multi-GPU host logic (sharding + the single collective per call)."""
+
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent(
+    """
+    import os, sys, numpy as np
+    sys.path.insert(0, os.environ["SQB_ROOT"])
+    import torch.distributed as dist
+    dist.init_process_group("gloo")
+    from squidpy_b200._dist import world, shard_range, all_gather_rows, all_reduce_sum
+    from squidpy_b200._rng import spawn_states
+    from oracle import ref
+    from tools import synth
+    rank, ws = world()
+    assert ws == 2
+    # permutations sharded like nhood_enrichment does it; the oracle stands in for the per-rank GPU work
+    g = synth.hex_graph(13, 17); n = g.shape[0]
+    lab = np.random.default_rng(0).integers(0, 4, n).astype(np.uint32)
+    P = 11
+    lo, hi = shard_range(P, rank, ws)
+    local = ref.nhood_perm_counts(g.indptr, g.indices, lab, 4, spawn_states(5, P, lo, hi))
+    full = all_gather_rows(local, P)
+    exp = ref.nhood_perm_counts(g.indptr, g.indices, lab, 4, spawn_states(5, P))
+    assert full.shape == exp.shape and (full == exp).all(), "gathered permutation counts differ"
+    # float64 feature scores (spatial_autocorr sharding)
+    sc = np.arange(7, dtype=np.float64) * 1.5
+    lo, hi = shard_range(7, rank, ws)
+    assert (all_gather_rows(sc[lo:hi].copy(), 7) == sc).all()
+    # int64 partial pair counts (co_occurrence / ripley tile sharding)
+    part = np.full((3, 3, 5), rank + 1, dtype=np.int64)
+    assert (all_reduce_sum(part) == 3).all()
+    dist.destroy_process_group()
+    print("RANK_OK", rank)
+    """
+)
+
+
+def test_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, SQB_ROOT=ROOT, PYTHONPATH=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", str(script)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.stdout.count("RANK_OK") == 2, out.stdout
+
+
+def test_single_process_passthrough():
+    from squidpy_b200._dist import all_gather_rows, all_reduce_sum, world
+
+    assert world() == (0, 1)
+    a = np.arange(6).reshape(3, 2)
+    assert all_gather_rows(a, 3) is a and all_reduce_sum(a) is a

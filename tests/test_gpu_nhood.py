@@ -1,0 +1,182 @@
+"""GPU parity tests for nhood_enrichment (through the C ABI): bit-exact integer counts and numpy-identical shuffles."""
+
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.sparse as sp
+
+import squidpy_b200 as sq
+from oracle import ref
+from squidpy_b200._rng import spawn_states
+from squidpy_b200.gr import NhoodPlan
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _plan(g, n_cls):
+    return NhoodPlan(g.indptr, g.indices, n_cls)
+
+
+def test_kat1_count():
+    plan = NhoodPlan(np.array([0, 2, 3, 5, 7, 9]), np.array([1, 2, 4, 0, 1, 1, 4, 2, 3]), 2)
+    out = plan.count(np.array([0, 0, 0, 1, 1]))
+    assert out.dtype == np.uint32
+    np.testing.assert_array_equal(out, [[4, 1], [2, 2]])
+
+
+@pytest.mark.parametrize("n_cls", [2, 3, 10, 30, 45, 70, 120, 230, 300])
+def test_count_vs_oracle(n_cls):
+    # n_cls sweeps every histogram layout: 32/16/8/2 permutations per CTA in shared memory, global atomics (230),
+    # uint16 labels (300)
+    g = synth.hex_graph(61, 53)
+    lab = np.random.default_rng(n_cls).integers(0, n_cls, g.shape[0]).astype(np.uint32)
+    np.testing.assert_array_equal(_plan(g, n_cls).count(lab), ref.nhood_count(g.indptr, g.indices, lab, n_cls))
+
+
+def test_count_directed_selfloops_empty_rows():
+    rng = np.random.default_rng(0)
+    n = 3001
+    a = sp.random(n, n, density=0.002, format="csr", random_state=1, dtype=np.float32)
+    a = (a + sp.eye(n, format="csr", dtype=np.float32) * (rng.random(n) < 0.3)).tocsr()
+    a.sort_indices()
+    assert (np.diff(a.indptr) == 0).any() and a.diagonal().sum() > 0 and (a != a.T).nnz > 0
+    lab = rng.integers(0, 7, n).astype(np.uint32)
+    np.testing.assert_array_equal(_plan(a, 7).count(lab), ref.nhood_count(a.indptr, a.indices, lab, 7))
+    empty = sp.csr_matrix((5, 5), dtype=np.float32)
+    np.testing.assert_array_equal(_plan(empty, 2).count(np.array([0, 1, 0, 1, 1])), np.zeros((2, 2), np.uint32))
+
+
+def test_create_errors():
+    with pytest.raises(ValueError, match="Expected at least `2` clusters, found `1`"):
+        NhoodPlan(np.array([0, 1]), np.array([0]), 1)
+    plan = NhoodPlan(np.array([0, 1, 2]), np.array([1, 0]), 2)
+    with pytest.raises(ValueError, match="n_cls"):
+        plan.count(np.array([0, 5]))
+    with pytest.raises(sq.SquidpyB200Error, match="set_base"):
+        plan.upload(spawn_states(0, 2))
+
+
+@pytest.mark.parametrize("algo,threads", [(0, 512), (1, 128), (1, 256), (1, 512), (1, 1024)])
+@pytest.mark.parametrize("n", [2, 3, 5, 33, 100, 1000, 1025, 5041, 70001])
+def test_shuffle_is_numpy_exact(algo, threads, n):
+    """Shuffled label vectors equal numpy Generator.shuffle of the same spawned generators (oracle = exact replay,
+    pinned to numpy in tests/test_oracle_golden.py)."""
+    if algo == 0 and n > 6000:
+        pytest.skip("serial cross-check kernel: small sizes only")
+    g = sp.csr_matrix((np.ones(n - 1, np.float32), (np.arange(n - 1), np.arange(1, n))), shape=(n, n))
+    n_cls = 251
+    base = (np.arange(n) % n_cls).astype(np.uint32)
+    plan = _plan(g, n_cls)
+    plan.set_option("shuffle_algo", algo)
+    plan.set_option("shuffle_threads", threads)
+    plan.set_base(base)
+    P = 7
+    st = spawn_states(1234 + n, P)
+    plan.upload(st)
+    got = plan.shuffled_labels(0, P)
+    np.testing.assert_array_equal(got, ref.shuffle_labels(base, st))
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+def test_shuffle_library_groups(algo):
+    n = 4000
+    g = synth.hex_graph(40, 100)
+    rng = np.random.default_rng(3)
+    base = rng.integers(0, 9, n).astype(np.uint32)
+    lib = rng.integers(0, 4, n).astype(np.int32)
+    lib[:7] = 3  # unbalanced, interleaved membership
+    plan = _plan(g, 9)
+    plan.set_option("shuffle_algo", algo)
+    plan.set_base(base, lib, 5)  # category 4 is empty
+    st = spawn_states(99, 6)
+    plan.upload(st)
+    np.testing.assert_array_equal(plan.shuffled_labels(0, 6), ref.shuffle_labels(base, st, lib, 5))
+    np.testing.assert_array_equal(plan.permute(st), ref.nhood_perm_counts(g.indptr, g.indices, base, 9, st, lib, 5))
+
+
+@pytest.mark.parametrize("n_cls,P", [(10, 100), (30, 70), (64, 33), (300, 5)])
+def test_perm_counts_vs_oracle(n_cls, P):
+    g = synth.hex_graph(71, 71)
+    base = np.random.default_rng(0).integers(0, n_cls, g.shape[0]).astype(np.uint32)
+    plan = _plan(g, n_cls)
+    plan.set_base(base)
+    st = spawn_states(42, P)
+    got = plan.permute(st)
+    assert got.dtype == np.uint32 and got.shape == (P, n_cls, n_cls)
+    np.testing.assert_array_equal(got, ref.nhood_perm_counts(g.indptr, g.indices, base, n_cls, st))
+
+
+def test_perm_chunking_and_resident_api():
+    g = synth.knn_graph(np.random.default_rng(1).random((3000, 2)), 6)
+    base = np.random.default_rng(2).integers(0, 5, 3000).astype(np.uint32)
+    st = spawn_states(7, 70)
+    plan = _plan(g, 5)
+    plan.set_base(base)
+    full = plan.permute(st)
+    plan.set_option("perm_chunk", 32)  # 3 chunks
+    np.testing.assert_array_equal(plan.permute(st), full)
+    plan.upload(st)
+    plan.run_async()
+    plan.run_async()  # re-running is idempotent
+    np.testing.assert_array_equal(plan.download(), full)
+    np.testing.assert_array_equal(full, ref.nhood_perm_counts(g.indptr, g.indices, base, 5, st))
+    assert plan.bytes_per_perm == 4 * g.nnz + 4 * 3001 + 8 * 3000 + 4 * 25
+
+
+def test_api_matches_reference_golden(golden_dummy, dummy_adata):
+    """Public API on the reference's dummy_adata recipe: z-scores IDENTICAL to the reference (same permutations, same
+    float64 mean/std), counts bit-exact, keys/dtypes as in reference tests/graph/test_nhood.py:20-25."""
+    res = sq.gr.nhood_enrichment(dummy_adata, "cluster", n_perms=20, seed=42, copy=True)
+    np.testing.assert_array_equal(res.counts, golden_dummy["nhood_count"])
+    np.testing.assert_array_equal(res.zscore, golden_dummy["nhood_z"])
+    assert res.zscore[0, 0] == 0.4957188836779417
+    out = sq.gr.nhood_enrichment(dummy_adata, "cluster", library_key="library", n_perms=20, seed=42)
+    assert out is None
+    d = dummy_adata.uns["cluster_nhood_enrichment"]
+    assert d["zscore"].dtype == np.float64 and d["count"].dtype == np.uint32 and d["zscore"].shape == (3, 3)
+    np.testing.assert_array_equal(d["zscore"], golden_dummy["nhood_lib_z"])
+    np.testing.assert_array_equal(d["count"], golden_dummy["nhood_lib_count"])
+
+
+def test_api_cfg1_visium_grid_golden(golden_cfg1):
+    """BASELINE.json configs[0]: 5 041-spot Visium grid, 10 clusters, n_perms=100 — against the reference's output."""
+    g = synth.hex_graph(71, 71)
+    assert g.nnz == int(golden_cfg1["nnz"])
+    lab = pd.Series(pd.Categorical.from_codes(golden_cfg1["codes"].astype(int), categories=[f"c{i:03d}" for i in range(10)]))
+    ad = synth.make_adata(synth.hex_coords(71, 71), g, lab)
+    res = sq.gr.nhood_enrichment(ad, "cluster", n_perms=100, seed=42, copy=True)
+    np.testing.assert_array_equal(res.counts, golden_cfg1["nhood_count"])
+    np.testing.assert_array_equal(res.zscore, golden_cfg1["nhood_z"])
+
+
+def test_api_reproducibility(dummy_adata):
+    # reference tests/graph/test_nhood.py:41-59
+    a = sq.gr.nhood_enrichment(dummy_adata, "cluster", n_perms=30, seed=42, copy=True)
+    b = sq.gr.nhood_enrichment(dummy_adata, "cluster", n_perms=30, seed=42, copy=True, n_jobs=2, backend="threading")
+    c = sq.gr.nhood_enrichment(dummy_adata, "cluster", n_perms=30, seed=43, copy=True)
+    np.testing.assert_array_equal(a.zscore, b.zscore)
+    np.testing.assert_array_equal(a.counts, c.counts)
+    assert not np.allclose(a.zscore, c.zscore)
+
+
+def test_full_size_1m_spots():
+    """BASELINE.json configs[1] shape (1M spots, 30 clusters, k=6): direct parity on a few permutations plus
+    size-independent properties on all of them."""
+    g = synth.hex_graph(1000, 1000)
+    n = g.shape[0]
+    base = np.random.default_rng(0).integers(0, 30, n).astype(np.uint32)
+    plan = _plan(g, 30)
+    np.testing.assert_array_equal(plan.count(base), ref.nhood_count(g.indptr, g.indices, base, 30))
+    plan.set_base(base)
+    P = 48
+    st = spawn_states(0, P)
+    got = plan.permute(st)
+    np.testing.assert_array_equal(got[:6], ref.nhood_perm_counts(g.indptr, g.indices, base, 30, st[:6]))
+    assert (got.reshape(P, -1).sum(axis=1, dtype=np.int64) == g.nnz).all()  # every stored entry counted once
+    np.testing.assert_array_equal(got, got.transpose(0, 2, 1))  # symmetric graph -> symmetric counts
+    lab = plan.shuffled_labels(40, 42)
+    np.testing.assert_array_equal(np.sort(lab, axis=1), np.sort(np.broadcast_to(base, lab.shape), axis=1))  # a permutation
+    np.testing.assert_array_equal(lab, ref.shuffle_labels(base, st[40:42]))

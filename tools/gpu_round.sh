@@ -1,0 +1,31 @@
+#!/bin/bash
+# One GPU-box session: smoke, GPU tests, sanitizer pass, bench, ncu launch list.  Everything is logged under gpurun_out/.
+# Each stage has its own timeout so a hung kernel cannot eat the whole lease.
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+OUT=gpurun_out
+nvidia-smi --query-gpu=name,driver_version,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu_info.txt 2>&1
+echo "nproc=$(nproc)" >> $OUT/gpu_info.txt; grep -m1 'model name' /proc/cpuinfo >> $OUT/gpu_info.txt
+STAGES="${1:-smoke tests sanitizer bench ncu}"
+for st in $STAGES; do
+  case $st in
+    smoke)
+      timeout 600 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/summary.txt ;;
+    tests)
+      timeout 2400 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 900 -rf --durations=15 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/summary.txt
+      tail -n 60 $OUT/pytest_gpu.log ;;
+    sanitizer)
+      timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python __graft_entry__.py smoke > $OUT/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $OUT/summary.txt
+      timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_nhood.py -q -p no:cacheprovider -k "shuffle_is_numpy_exact and 1000 and 256 or library" > $OUT/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?" | tee -a $OUT/summary.txt
+      tail -n 5 $OUT/sanitizer_memcheck.log $OUT/sanitizer_racecheck.log ;;
+    bench)
+      timeout 1500 python bench.py --steps 5 --warmup 3 --all > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/summary.txt
+      tail -c 6000 $OUT/bench.json; tail -n 20 $OUT/bench.err ;;
+    ncu)
+      timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 1 --skip-cpu --skip-moran > $OUT/ncu_bench.log 2>&1; echo "ncu-list rc=$?" | tee -a $OUT/summary.txt ;;
+    ncufull)
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"nhood_shuffle_cta|nhood_count_kernel" -c 2 -o $OUT/prof_nhood python bench.py --steps 1 --warmup 0 --perms 256 --skip-cpu --skip-moran > $OUT/ncu_full.log 2>&1; echo "ncu-full rc=$?" | tee -a $OUT/summary.txt ;;
+  esac
+done
+cat $OUT/summary.txt
