@@ -227,7 +227,7 @@ def bench_moran(ctx, rank, ws, steps, warmup, flush):
             from oracle import ref
 
             cores = len(os.sched_getaffinity(0))
-            ns = 64
+            ns = 2 * cores
             t0 = time.perf_counter()
             exp = ref.morans_i(g, x[:, :ns].T.tocsr(), n_threads=cores)
             dt = time.perf_counter() - t0
@@ -315,7 +315,11 @@ def main():
     from tools import synth
 
     rank, ws, local = _dist_setup(args.gpus)
-    ctx = sq.Context(local, torch.cuda.current_stream().cuda_stream)  # library kernels run on torch's current stream
+    # the library launches on a torch-owned stream made current here, so torch.cuda.Event timing sees its kernels
+    # (torch's default stream has handle 0, which the C ABI reads as "create your own stream")
+    bench_stream = torch.cuda.Stream()
+    torch.cuda.set_stream(bench_stream)
+    ctx = sq.Context(local, bench_stream.cuda_stream)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def flush():

@@ -147,11 +147,9 @@ __global__ void nhood_shuffle_serial_kernel(LT* __restrict__ labels, int64_t str
 //  window's own index range; duplicate targets through a shared-memory hash table) and the few conflicting
 //  swaps are replayed in step order by one thread on the staged copies.
 // ------------------------------------------------------------------------------------------------
-#define SQB_EMPTY_KEY 0xFFFFFFFFu
-
-__device__ __forceinline__ int sqb_window_size(int64_t i_cur, int raw_left, int raw_total) {
+__device__ __forceinline__ int sqb_window_size(int64_t i_cur, int raw_left, int raw_total, float wfactor) {
     int64_t a = i_cur >> 2;
-    int64_t b = (int64_t)(4.0f * sqrtf((float)i_cur));
+    int64_t b = (int64_t)(wfactor * sqrtf((float)i_cur));
     int64_t k = a < b ? a : b;
     if (k > raw_total) k = raw_total;
     if (k < 1) k = 1;
@@ -159,238 +157,251 @@ __device__ __forceinline__ int sqb_window_size(int64_t i_cur, int raw_left, int 
     return (int)k;
 }
 
+template <typename LT>
+__device__ __forceinline__ LT ld_cg(const LT* p) {
+    return __ldcg(p);
+}
+template <typename LT>
+__device__ __forceinline__ LT ld_cs(const LT* p) {
+    return __ldcs(p);
+}
+template <typename LT>
+__device__ __forceinline__ void st_cs(LT* p, LT v) {
+    __stcs(p, v);
+}
+
+#define SQB_EMPTY64 0xFFFFFFFFFFFFFFFFULL
+
 template <typename LT, int NT>
 __global__ void __launch_bounds__(NT) nhood_shuffle_cta_kernel(LT* __restrict__ labels, int64_t stride,
-                                                               const uint64_t* __restrict__ states, int nseg,
-                                                               const int64_t* __restrict__ seg_start,
-                                                               const int64_t* __restrict__ seg_len) {
+                                                               const uint64_t* __restrict__ states, int64_t n_perms,
+                                                               int nseg, const int64_t* __restrict__ seg_start,
+                                                               const int64_t* __restrict__ seg_len, float wfactor) {
     constexpr int RAW = 2 * NT;
     constexpr int HS = 4 * NT;  // hash slots (load factor <= 0.5)
     constexpr int NW = NT / 32;
     constexpr int HS_SHIFT = (NT == 128 ? 23 : NT == 256 ? 22 : NT == 512 ? 21 : 20);  // 32 - log2(HS)
     static_assert(NT == 128 || NT == 256 || NT == 512 || NT == 1024, "NT");
 
-    __shared__ uint32_t s_sj[RAW];
-    __shared__ LT s_own[RAW];
-    __shared__ uint32_t s_keys[HS];
-    __shared__ LT s_hval[HS];
-    __shared__ uint8_t s_dup[HS];
-    __shared__ uint32_t s_flag[RAW / 32];
-    __shared__ int s_wsum[32];
-    __shared__ int s_rstar;
+    extern __shared__ __align__(16) unsigned char sqb_shuffle_smem[];
+    unsigned long long* s_tab = reinterpret_cast<unsigned long long*>(sqb_shuffle_smem);  // (target << 32) | owner step, or EMPTY
+    uint32_t* s_sj = reinterpret_cast<uint32_t*>(s_tab + HS);
+    uint32_t* s_flag = s_sj + RAW;
+    int* s_wsum = reinterpret_cast<int*>(s_flag + RAW / 32);
+    int& s_rstar = s_wsum[32];
+    LT* s_own = reinterpret_cast<LT*>(s_wsum + 36);
+    LT* s_hval = s_own + RAW;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    LT* __restrict__ a = labels + (int64_t)blockIdx.x * stride;
-    const uint64_t* st4 = states + (int64_t)blockIdx.x * 4;
 
-    for (int h = tid; h < HS; h += NT) {
-        s_keys[h] = SQB_EMPTY_KEY;
-        s_dup[h] = 0;
-    }
+    for (int h = tid; h < HS; h += NT) s_tab[h] = SQB_EMPTY64;
     if (tid < RAW / 32) s_flag[tid] = 0;
     if (tid < 32) s_wsum[tid] = 0;
-
-    // per-thread LCG: state of output index t is state_{t+1}
-    const u128 inc = mk128(st4[2], st4[3]);
-    u128 st;
-    {
-        u128 M, C;
-        pcg_jump_consts((uint64_t)tid + 1, M, C);
-        st = M * mk128(st4[0], st4[1]) + C * inc;
-    }
-    u128 Mn, Cn_inc;
-    {
-        u128 M, C;
-        pcg_jump_consts((uint64_t)NT, M, C);
-        Mn = M;
-        Cn_inc = C * inc;
-    }
-    uint32_t raw0 = 0, raw1 = 0;
-    int pos = RAW;
+    u128 Mn, Cn;
+    pcg_jump_consts((uint64_t)NT, Mn, Cn);
+    u128 Mt, Ct;
+    pcg_jump_consts((uint64_t)tid + 1, Mt, Ct);
     __syncthreads();
 
-    for (int seg = 0; seg < nseg; ++seg) {
-        const int64_t base = seg_start[seg];
-        int64_t i_cur = seg_len[seg] - 1;
-        while (i_cur >= 1) {
-            if (pos >= RAW) {
-                uint64_t o = pcg_output(st);
-                st = Mn * st + Cn_inc;
-                raw0 = (uint32_t)o;
-                raw1 = (uint32_t)(o >> 32);
-                pos = 0;
-            }
-            // ---- phase parameters (uniform) ----
-            uint64_t mask64 = (uint64_t)i_cur;
-            mask64 |= mask64 >> 1;
-            mask64 |= mask64 >> 2;
-            mask64 |= mask64 >> 4;
-            mask64 |= mask64 >> 8;
-            mask64 |= mask64 >> 16;
-            mask64 |= mask64 >> 32;
-            const uint32_t mask = (uint32_t)mask64;  // i_cur < 2^32 (n < 2^32 enforced on the host)
-            const int64_t i_lo = (int64_t)(mask64 >> 1) + 1;
-            const int64_t n_ph = i_cur - i_lo + 1;
-            const int K = sqb_window_size(i_cur, RAW - pos, RAW);
-            const int r0 = 2 * tid, r1 = 2 * tid + 1;
-            const bool in0 = (r0 >= pos) && (r0 < pos + K);
-            const bool in1 = (r1 >= pos) && (r1 < pos + K);
-            const uint32_t u0 = raw0 & mask, u1 = raw1 & mask;
+    // persistent CTA: permutations blockIdx.x, blockIdx.x + gridDim.x, ...  (the grid size bounds how many label
+    // arrays are live at once, i.e. the L2 working set)
+    for (int64_t perm = blockIdx.x; perm < n_perms; perm += gridDim.x) {
+        LT* __restrict__ a = labels + perm * stride;
+        const uint64_t* st4 = states + perm * 4;
+        // per-thread LCG: state of output index t is state_{t+1}
+        const u128 inc = mk128(st4[2], st4[3]);
+        u128 st = Mt * mk128(st4[0], st4[1]) + Ct * inc;
+        const u128 Cn_inc = Cn * inc;
+        uint32_t raw0 = 0, raw1 = 0;
+        int pos = RAW;
 
-            // ---- acceptance fixed point ----
-            int c0 = 0, c1 = 0, total = 0;
-            bool F0 = in0 && ((int64_t)u0 <= i_cur);
-            bool F1 = in1 && ((int64_t)u1 <= i_cur);
-            while (true) {
-                const uint32_t b0 = __ballot_sync(0xffffffffu, F0);
-                const uint32_t b1 = __ballot_sync(0xffffffffu, F1);
-                if (lane == 0) s_wsum[warp] = __popc(b0) + __popc(b1);
-                __syncthreads();
-                int v = (lane < NW) ? s_wsum[lane] : 0;
-                int incl = v;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    int t = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += t;
+        for (int seg = 0; seg < nseg; ++seg) {
+            const int64_t base = seg_start[seg];
+            int64_t i_cur = seg_len[seg] - 1;
+            while (i_cur >= 1) {
+                if (pos >= RAW) {
+                    uint64_t o = pcg_output(st);
+                    st = Mn * st + Cn_inc;
+                    raw0 = (uint32_t)o;
+                    raw1 = (uint32_t)(o >> 32);
+                    pos = 0;
                 }
-                const int woff = __shfl_sync(0xffffffffu, incl - v, warp);
-                total = __shfl_sync(0xffffffffu, incl, 31);
-                c0 = woff + __popc(b0 & lt_mask) + __popc(b1 & lt_mask);
-                c1 = c0 + (F0 ? 1 : 0);
-                const bool nF0 = in0 && ((int64_t)u0 <= i_cur - (int64_t)c0);
-                const bool nF1 = in1 && ((int64_t)u1 <= i_cur - (int64_t)c1);
-                const int changed = (nF0 != F0) || (nF1 != F1);
-                const int any = __syncthreads_or(changed);
-                if (!any) break;
-                F0 = nF0;
-                F1 = nF1;
-            }
-            int S;
-            const bool phase_ends = ((int64_t)total >= n_ph);
-            if (phase_ends) {
-                S = (int)n_ph;
-                if (F0 && c0 == S - 1) s_rstar = r0;
-                if (F1 && c1 == S - 1) s_rstar = r1;
-            } else {
-                S = total;
-            }
-            if (F0 && c0 < S) s_sj[c0] = u0;
-            if (F1 && c1 < S) s_sj[c1] = u1;
-            __syncthreads();
-            const int newpos = phase_ends ? (s_rstar + 1) : (pos + K);
+                // ---- phase parameters (uniform) ----
+                uint64_t mask64 = (uint64_t)i_cur;
+                mask64 |= mask64 >> 1;
+                mask64 |= mask64 >> 2;
+                mask64 |= mask64 >> 4;
+                mask64 |= mask64 >> 8;
+                mask64 |= mask64 >> 16;
+                mask64 |= mask64 >> 32;
+                const uint32_t mask = (uint32_t)mask64;  // i_cur < 2^32 (n < 2^32 enforced on the host)
+                const int64_t i_lo = (int64_t)(mask64 >> 1) + 1;
+                const int64_t n_ph = i_cur - i_lo + 1;
+                const int K = sqb_window_size(i_cur, RAW - pos, RAW, wfactor);
+                const int r0 = 2 * tid, r1 = 2 * tid + 1;
+                const bool in0 = (r0 >= pos) && (r0 < pos + K);
+                const bool in1 = (r1 >= pos) && (r1 < pos + K);
+                const uint32_t u0 = raw0 & mask, u1 = raw1 & mask;
 
-            // ---- swap phase: steps s = 0..S-1, step s swaps positions (i_cur - s) and s_sj[s] ----
-            if (S > 0) {
-                const int64_t own_lo = i_cur - (int64_t)S;  // targets j > own_lo lie inside the window's own range
-                int slot[2] = {-1, -1};
-                bool owner[2] = {false, false};
-                uint32_t jv[2] = {0, 0};
+                // ---- acceptance fixed point ----
+                int c0 = 0, c1 = 0, total = 0;
+                bool F0 = in0 && ((int64_t)u0 <= i_cur);
+                bool F1 = in1 && ((int64_t)u1 <= i_cur);
+                while (true) {
+                    const uint32_t b0 = __ballot_sync(0xffffffffu, F0);
+                    const uint32_t b1 = __ballot_sync(0xffffffffu, F1);
+                    if (lane == 0) s_wsum[warp] = __popc(b0) + __popc(b1);
+                    __syncthreads();
+                    int v = (lane < NW) ? s_wsum[lane] : 0;
+                    int incl = v;
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int s = tid + q * NT;
-                    if (s < S) {
-                        const uint32_t j = s_sj[s];
-                        jv[q] = j;
-                        if ((int64_t)j > own_lo) {
-                            const int s2 = (int)(i_cur - (int64_t)j);
-                            if (s2 != s) {
-                                atomicOr(&s_flag[s >> 5], 1u << (s & 31));
-                                atomicOr(&s_flag[s2 >> 5], 1u << (s2 & 31));
-                            }
-                        } else {
-                            uint32_t h = (j * 2654435761u) >> HS_SHIFT;
-                            while (true) {
-                                const uint32_t prev = atomicCAS(&s_keys[h], SQB_EMPTY_KEY, j);
-                                if (prev == SQB_EMPTY_KEY) {
-                                    owner[q] = true;
-                                    break;
-                                }
-                                if (prev == j) {
-                                    s_dup[h] = 1;
-                                    atomicOr(&s_flag[s >> 5], 1u << (s & 31));
-                                    break;
-                                }
-                                h = (h + 1) & (HS - 1);
-                            }
-                            slot[q] = (int)h;
-                        }
+                    for (int d = 1; d < 32; d <<= 1) {
+                        int t = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += t;
                     }
+                    const int woff = __shfl_sync(0xffffffffu, incl - v, warp);
+                    total = __shfl_sync(0xffffffffu, incl, 31);
+                    c0 = woff + __popc(b0 & lt_mask) + __popc(b1 & lt_mask);
+                    c1 = c0 + (F0 ? 1 : 0);
+                    const bool nF0 = in0 && ((int64_t)u0 <= i_cur - (int64_t)c0);
+                    const bool nF1 = in1 && ((int64_t)u1 <= i_cur - (int64_t)c1);
+                    const int changed = (nF0 != F0) || (nF1 != F1);
+                    const int any = __syncthreads_or(changed);
+                    if (!any) break;
+                    F0 = nF0;
+                    F1 = nF1;
                 }
-                // stage values: own range (coalesced) and distinct external targets (random)
-                LT vo[2], vh[2];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int s = tid + q * NT;
-                    vo[q] = (s < S) ? a[base + i_cur - s] : (LT)0;
-                    vh[q] = owner[q] ? a[base + (int64_t)jv[q]] : (LT)0;
+                int S;
+                const bool phase_ends = ((int64_t)total >= n_ph);
+                if (phase_ends) {
+                    S = (int)n_ph;
+                    if (F0 && c0 == S - 1) s_rstar = r0;
+                    if (F1 && c1 == S - 1) s_rstar = r1;
+                } else {
+                    S = total;
                 }
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int s = tid + q * NT;
-                    if (s < S) s_own[s] = vo[q];
-                    if (owner[q]) s_hval[slot[q]] = vh[q];
-                }
+                if (F0 && c0 < S) s_sj[c0] = u0;
+                if (F1 && c1 < S) s_sj[c1] = u1;
                 __syncthreads();
+                const int newpos = phase_ends ? (s_rstar + 1) : (pos + K);
+
+                // ---- swap phase: steps s = 0..S-1, step s swaps positions (i_cur - s) and s_sj[s] ----
+                if (S > 0) {
+                    const int64_t own_lo = i_cur - (int64_t)S;  // targets j > own_lo lie inside the window's own range
+                    int slot[2] = {-1, -1};
+                    bool owner[2] = {false, false};
+                    uint32_t jv[2] = {0, 0};
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int s = tid + q * NT;
-                    if (owner[q] && s_dup[slot[q]]) atomicOr(&s_flag[s >> 5], 1u << (s & 31));
-                }
-                __syncthreads();
-                // conflict-free swaps in parallel
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int s = tid + q * NT;
-                    if (s < S && slot[q] >= 0 && !((s_flag[s >> 5] >> (s & 31)) & 1u)) {
-                        const LT t = s_own[s];
-                        s_own[s] = s_hval[slot[q]];
-                        s_hval[slot[q]] = t;
-                    }
-                }
-                // conflicting swaps in step order (disjoint from the conflict-free set)
-                if (tid == 0) {
-                    const int nwords = (S + 31) >> 5;
-                    for (int w = 0; w < nwords; ++w) {
-                        uint32_t bits = s_flag[w];
-                        while (bits) {
-                            const int b = __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            const int s = w * 32 + b;
+                    for (int q = 0; q < 2; ++q) {
+                        const int s = tid + q * NT;
+                        if (s < S) {
                             const uint32_t j = s_sj[s];
-                            const LT x = s_own[s];
+                            jv[q] = j;
                             if ((int64_t)j > own_lo) {
                                 const int s2 = (int)(i_cur - (int64_t)j);
-                                const LT y = s_own[s2];
-                                s_own[s] = y;
-                                s_own[s2] = x;
+                                if (s2 != s) {
+                                    atomicOr(&s_flag[s >> 5], 1u << (s & 31));
+                                    atomicOr(&s_flag[s2 >> 5], 1u << (s2 & 31));
+                                }
                             } else {
                                 uint32_t h = (j * 2654435761u) >> HS_SHIFT;
-                                while (s_keys[h] != j) h = (h + 1) & (HS - 1);
-                                const LT y = s_hval[h];
-                                s_own[s] = y;
-                                s_hval[h] = x;
+                                const unsigned long long mine = ((unsigned long long)j << 32) | (unsigned)s;
+                                while (true) {
+                                    const unsigned long long prev = atomicCAS(&s_tab[h], SQB_EMPTY64, mine);
+                                    if (prev == SQB_EMPTY64) {
+                                        owner[q] = true;
+                                        break;
+                                    }
+                                    if ((uint32_t)(prev >> 32) == j) {  // duplicate target: both steps conflict
+                                        const int so = (int)(uint32_t)prev;
+                                        atomicOr(&s_flag[s >> 5], 1u << (s & 31));
+                                        atomicOr(&s_flag[so >> 5], 1u << (so & 31));
+                                        break;
+                                    }
+                                    h = (h + 1) & (HS - 1);
+                                }
+                                slot[q] = (int)h;
                             }
                         }
                     }
-                }
-                __syncthreads();
-                // write back + reset the tables for the next window
+                    // stage values: own range (coalesced, streaming) and distinct external targets (random, L2)
+                    LT vo[2], vh[2];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int s = tid + q * NT;
-                    if (s < S) a[base + i_cur - s] = s_own[s];
-                    if (owner[q]) {
-                        a[base + (int64_t)jv[q]] = s_hval[slot[q]];
-                        s_keys[slot[q]] = SQB_EMPTY_KEY;
-                        s_dup[slot[q]] = 0;
+                    for (int q = 0; q < 2; ++q) {
+                        const int s = tid + q * NT;
+                        vo[q] = (s < S) ? ld_cs<LT>(a + base + i_cur - s) : (LT)0;
+                        vh[q] = owner[q] ? ld_cg<LT>(a + base + (int64_t)jv[q]) : (LT)0;
                     }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int s = tid + q * NT;
+                        if (s < S) s_own[s] = vo[q];
+                        if (owner[q]) s_hval[slot[q]] = vh[q];
+                    }
+                    __syncthreads();
+                    // conflict-free swaps in parallel
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int s = tid + q * NT;
+                        if (s < S && slot[q] >= 0 && !((s_flag[s >> 5] >> (s & 31)) & 1u)) {
+                            const LT t = s_own[s];
+                            s_own[s] = s_hval[slot[q]];
+                            s_hval[slot[q]] = t;
+                        }
+                    }
+                    // conflicting swaps in step order (disjoint from the conflict-free set); warp 0 finds them with
+                    // ballots, lane 0 replays them on the staged copies
+                    if (warp == 0) {
+                        const int nwords = (S + 31) >> 5;
+                        for (int wb = 0; wb < nwords; wb += 32) {
+                            const uint32_t myw = (wb + lane < nwords) ? s_flag[wb + lane] : 0u;
+                            uint32_t nz = __ballot_sync(0xffffffffu, myw != 0u);
+                            while (nz) {
+                                const int wl = __ffs(nz) - 1;
+                                nz &= nz - 1;
+                                uint32_t bits = __shfl_sync(0xffffffffu, myw, wl);
+                                if (lane == 0) {
+                                    while (bits) {
+                                        const int b = __ffs(bits) - 1;
+                                        bits &= bits - 1;
+                                        const int s = (wb + wl) * 32 + b;
+                                        const uint32_t j = s_sj[s];
+                                        const LT x = s_own[s];
+                                        if ((int64_t)j > own_lo) {
+                                            const int s2 = (int)(i_cur - (int64_t)j);
+                                            const LT y = s_own[s2];
+                                            s_own[s] = y;
+                                            s_own[s2] = x;
+                                        } else {
+                                            uint32_t h = (j * 2654435761u) >> HS_SHIFT;
+                                            while ((uint32_t)(s_tab[h] >> 32) != j) h = (h + 1) & (HS - 1);
+                                            const LT y = s_hval[h];
+                                            s_own[s] = y;
+                                            s_hval[h] = x;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    // write back + reset the tables for the next window
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int s = tid + q * NT;
+                        if (s < S) st_cs<LT>(a + base + i_cur - s, s_own[s]);  // final: never read again by this kernel
+                        if (owner[q]) {
+                            a[base + (int64_t)jv[q]] = s_hval[slot[q]];
+                            s_tab[slot[q]] = SQB_EMPTY64;
+                        }
+                    }
+                    if (tid < RAW / 32) s_flag[tid] = 0;
+                    __syncthreads();
                 }
-                if (tid < RAW / 32) s_flag[tid] = 0;
-                __syncthreads();
+                i_cur -= S;
+                pos = newpos;
             }
-            i_cur -= S;
-            pos = newpos;
         }
     }
 }
@@ -448,30 +459,76 @@ __global__ void nhood_u32_to_lt_kernel(const uint32_t* __restrict__ src, LT* __r
 // ------------------------------------------------------------------------------------------------
 template <typename LT, int G>
 __global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
-                                   const LT* __restrict__ labT, int PB, int64_t n, int C, int64_t nodes_per_cta, int P,
-                                   uint32_t* __restrict__ counts) {
+                                                           const LT* __restrict__ labT, int PB, int64_t n, int C,
+                                                           int64_t nodes_per_cta, int P, uint32_t* __restrict__ counts) {
     extern __shared__ uint32_t hist[];
     const int nb = C * C * G;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    constexpr int EPW = 32 / G;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int sub = lane / G, pl = lane % G;
-    const int perm = blockIdx.y * G + pl;
-    const bool valid = perm < P;
     const int64_t node_begin = (int64_t)blockIdx.x * nodes_per_cta;
     int64_t node_end = node_begin + nodes_per_cta;
     if (node_end > n) node_end = n;
-    const LT* __restrict__ col = labT + perm;  // column of this lane's permutation (padded columns exist up to PB)
-    for (int64_t i = node_begin + warp; i < node_end; i += nwarps) {
-        const uint32_t beg = indptr[i], end = indptr[i + 1];
-        const uint32_t a = (uint32_t)col[i * PB];
-        const uint32_t rowbase = a * (uint32_t)C;
+
+    if (G == 32) {
+        // lane = permutation.  A warp takes 32 consecutive nodes: their CSR segment is one contiguous index range that
+        // is loaded coalesced (one index per lane), the source node of every edge is found by a shuffle binary search
+        // over the 32 row ends, and the label gathers of 8 edges are issued back to back before the 8 atomics
+        // (memory-level parallelism 16 per warp instead of 1).
+        const int perm = blockIdx.y * 32 + lane;
+        const bool valid = perm < P;
+        const LT* __restrict__ col = labT + perm;
+        for (int64_t i0 = node_begin + (int64_t)warp * 32; i0 < node_end; i0 += (int64_t)nwarps * 32) {
+            const int64_t myn = i0 + lane;
+            const uint32_t p1 = indptr[(myn < node_end ? myn : node_end - 1) + 1];  // row end (clamped: empty tail rows)
+            const uint32_t E0 = indptr[i0];
+            const uint32_t E1 = __shfl_sync(0xffffffffu, p1, 31);
+            for (uint32_t eb = E0; eb < E1; eb += 32) {
+                const uint32_t e = eb + lane;
+                const uint32_t jl = (e < E1) ? indices[e] : 0u;
+                // source node of edge e: number of rows (of this block) that end at or before e
+                int lo = 0;
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const uint32_t v = __shfl_sync(0xffffffffu, p1, lo + step - 1);
+                    if (v <= e) lo += step;
+                }
+                const uint32_t srcl = (uint32_t)lo;  // < 32 whenever e < E1
+                const int cnt = (int)((E1 - eb) < 32u ? (E1 - eb) : 32u);
+                for (int t0 = 0; t0 < cnt; t0 += 8) {
+                    uint32_t av[8], bv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int t = t0 + k;
+                        const uint32_t j = __shfl_sync(0xffffffffu, jl, t & 31);
+                        const uint32_t sn = __shfl_sync(0xffffffffu, srcl, t & 31);
+                        const bool ok = t < cnt;
+                        av[k] = ok ? (uint32_t)col[(i0 + sn) * PB] : 0u;
+                        bv[k] = ok ? (uint32_t)col[(int64_t)j * PB] : 0u;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (valid && (t0 + k) < cnt) atomicAdd(&hist[(av[k] * (uint32_t)C + bv[k]) * 32 + lane], 1u);
+                    }
+                }
+            }
+        }
+    } else {
+        constexpr int EPW = 32 / G;
+        const int sub = lane / G, pl = lane % G;
+        const int perm = blockIdx.y * G + pl;
+        const bool valid = perm < P;
+        const LT* __restrict__ col = labT + perm;  // column of this lane's permutation (padded columns exist up to PB)
+        for (int64_t i = node_begin + warp; i < node_end; i += nwarps) {
+            const uint32_t beg = indptr[i], end = indptr[i + 1];
+            const uint32_t a = (uint32_t)col[i * PB];
+            const uint32_t rowbase = a * (uint32_t)C;
 #pragma unroll 4
-        for (uint32_t e = beg + sub; e < end; e += EPW) {
-            const uint32_t j = indices[e];
-            const uint32_t b = (uint32_t)col[(int64_t)j * PB];
-            if (valid) atomicAdd(&hist[(rowbase + b) * G + pl], 1u);
+            for (uint32_t e = beg + sub; e < end; e += EPW) {
+                const uint32_t j = indices[e];
+                const uint32_t b = (uint32_t)col[(int64_t)j * PB];
+                if (valid) atomicAdd(&hist[(rowbase + b) * G + pl], 1u);
+            }
         }
     }
     __syncthreads();
@@ -534,6 +591,8 @@ struct sqb_nhood {
     int shuffle_threads = 512;
     int64_t perm_chunk = 0;  // 0 = auto
     int count_algo = 0;
+    int64_t shuffle_ctas = 0;          // persistent CTAs of the shuffle kernel (0 = occupancy x SM count)
+    int shuffle_wfactor_x100 = 400;    // window = min(i/4, wfactor * sqrt(i)) raw values
 };
 
 template <typename LT>
@@ -588,6 +647,26 @@ static int launch_count(sqb_nhood* h, const LT* labT, int PB, int P, uint32_t* d
     return SQB_OK;
 }
 
+template <typename LT, int NT>
+static int launch_shuffle_nt(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np) {
+    sqb_ctx* c = h->ctx;
+    auto k = nhood_shuffle_cta_kernel<LT, NT>;
+    // [tab u64 x 4NT][sj u32 x 2NT][flag u32 x NT/16][wsum int x 36][own LT x 2NT][hval LT x 4NT]
+    const size_t smem = (size_t)4 * NT * 8 + (size_t)2 * NT * 4 + (size_t)(NT / 16) * 4 + 36 * 4 + (size_t)6 * NT * sizeof(LT);
+    SQB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = h->shuffle_ctas;
+    if (grid <= 0) {
+        int per_sm = 1;
+        SQB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, smem));
+        if (per_sm < 1) per_sm = 1;
+        grid = (int64_t)per_sm * c->sm_count;
+    }
+    if (grid > np) grid = np;
+    k<<<(unsigned)grid, NT, smem, c->stream>>>(lab, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p,
+                                            (float)h->shuffle_wfactor_x100 / 100.0f);
+    return SQB_OK;
+}
+
 template <typename LT>
 static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np) {
     sqb_ctx* c = h->ctx;
@@ -598,20 +677,16 @@ static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t
     } else {
         switch (h->shuffle_threads) {
             case 128:
-                nhood_shuffle_cta_kernel<LT, 128><<<(unsigned)np, 128, 0, c->stream>>>(lab, h->stride, states, h->nseg,
-                                                                                       h->d_seg_start.p, h->d_seg_len.p);
+                SQB_TRY((launch_shuffle_nt<LT, 128>(h, lab, states, np)));
                 break;
             case 256:
-                nhood_shuffle_cta_kernel<LT, 256><<<(unsigned)np, 256, 0, c->stream>>>(lab, h->stride, states, h->nseg,
-                                                                                       h->d_seg_start.p, h->d_seg_len.p);
+                SQB_TRY((launch_shuffle_nt<LT, 256>(h, lab, states, np)));
                 break;
             case 1024:
-                nhood_shuffle_cta_kernel<LT, 1024><<<(unsigned)np, 1024, 0, c->stream>>>(
-                    lab, h->stride, states, h->nseg, h->d_seg_start.p, h->d_seg_len.p);
+                SQB_TRY((launch_shuffle_nt<LT, 1024>(h, lab, states, np)));
                 break;
             default:
-                nhood_shuffle_cta_kernel<LT, 512><<<(unsigned)np, 512, 0, c->stream>>>(lab, h->stride, states, h->nseg,
-                                                                                       h->d_seg_start.p, h->d_seg_len.p);
+                SQB_TRY((launch_shuffle_nt<LT, 512>(h, lab, states, np)));
                 break;
         }
     }
@@ -732,6 +807,12 @@ int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "perm_chunk")) {
         SQB_CHECK(value >= 0, SQB_ERR_INVALID, "perm_chunk must be >= 0");
         h->perm_chunk = value;
+    } else if (!strcmp(key, "shuffle_ctas")) {
+        SQB_CHECK(value >= 0 && value <= 1000000, SQB_ERR_INVALID, "shuffle_ctas must be in [0, 1e6]");
+        h->shuffle_ctas = value;
+    } else if (!strcmp(key, "shuffle_wfactor_x100")) {
+        SQB_CHECK(value >= 25 && value <= 6400, SQB_ERR_INVALID, "shuffle_wfactor_x100 must be in [25, 6400]");
+        h->shuffle_wfactor_x100 = (int)value;
     } else if (!strcmp(key, "count_algo")) {
         SQB_CHECK(value >= 0 && value <= 2, SQB_ERR_INVALID, "count_algo must be 0, 1 or 2");
         h->count_algo = (int)value;

@@ -89,7 +89,7 @@ def test_midsize_sparse_20k():
     exp = ref.morans_i(g, x.T.tocsr())
     assert np.abs(got - exp).max() <= (RTOL * np.abs(exp) + ATOL).min()
     np.testing.assert_allclose(got, exp, **TIGHT)
-    assert exp.max() > 0.3  # the smooth genes really are autocorrelated
+    assert np.nanmax(exp) > 0.3 and np.isfinite(exp).sum() > 500  # the smooth genes are autocorrelated, none is constant
     np.testing.assert_allclose(plan.score("geary"), ref.gearys_c(g, x.T.tocsr()), **TIGHT)
 
 

@@ -71,26 +71,26 @@ def make_adata(coords: np.ndarray, graph: sp.csr_matrix | None, labels: pd.Serie
 
 def expression_csr(n_obs: int, n_genes: int, density: float = 0.1, smooth_frac: float = 0.01, coords: np.ndarray | None = None,
                    seed: int = 0, dtype=np.float32) -> sp.csr_matrix:
-    """cells x genes CSR float32, ~`density` non-zeros: log1p of thinned counts; a fraction of genes carries a smooth
-    spatial field so Moran's I spans ~0..0.7."""
+    """cells x genes CSR float32 with exactly round(n_genes*density) sorted, distinct non-zeros per cell (log1p of
+    Poisson counts).  Gene columns are split into strides; a cell expresses one gene per stride.  In a fraction
+    `smooth_frac` of the strides the expressed gene is chosen by a smooth spatial field, so those genes live in
+    contiguous spatial bands and their Moran's I spans ~0.1..0.9; everywhere else it is iid (I ~ E[I] ~ 0)."""
     rng = np.random.default_rng(seed)
     nnz_per_row = max(1, int(round(n_genes * density)))
     indptr = np.arange(0, (n_obs + 1) * nnz_per_row, nnz_per_row, dtype=np.int64)
-    # distinct sorted gene indices per cell: random offsets on a strided base (cheap, no per-row choice())
     base = (np.arange(nnz_per_row, dtype=np.int64) * n_genes) // nnz_per_row
     width = max(1, n_genes // nnz_per_row)
     off = rng.integers(0, width, size=(n_obs, nnz_per_row), dtype=np.int64)
+    if coords is not None and smooth_frac > 0 and width > 1:
+        n_s = max(1, int(round(nnz_per_row * smooth_frac)))
+        strides = rng.choice(nnz_per_row, n_s, replace=False)
+        xy = (coords - coords.min(0)) / (np.ptp(coords, axis=0) + 1e-9)
+        for q, k in enumerate(strides):
+            fx, fy, ph = 1 + q % 3, 1 + (q // 3) % 3, rng.random() * 6.28
+            field = 0.5 + 0.5 * np.sin(2 * np.pi * (fx * xy[:, 0] + 0.5 * fy * xy[:, 1]) + ph) * np.cos(np.pi * fy * xy[:, 1])
+            off[:, k] = np.minimum((field * width).astype(np.int64), width - 1)
     indices = np.minimum(base[None, :] + off, n_genes - 1)
     vals = np.log1p(rng.poisson(1.5, size=(n_obs, nnz_per_row)) + 1.0).astype(dtype)
-    if coords is not None and smooth_frac > 0:
-        n_s = max(1, int(n_genes * smooth_frac))
-        sg = rng.choice(n_genes, n_s, replace=False)
-        is_s = np.zeros(n_genes, bool)
-        is_s[sg] = True
-        xy = (coords - coords.min(0)) / (np.ptp(coords, axis=0) + 1e-9)
-        field = (np.sin(4 * np.pi * xy[:, 0]) * np.cos(3 * np.pi * xy[:, 1]) + 1.5).astype(dtype)
-        m = is_s[indices]
-        vals = np.where(m, vals * field[:, None], vals).astype(dtype)
     x = sp.csr_matrix((vals.reshape(-1), indices.reshape(-1).astype(np.int32), indptr), shape=(n_obs, n_genes))
     x.has_sorted_indices = True
     return x
