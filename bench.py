@@ -134,7 +134,7 @@ def cpu_reference_nhood(g, base, n_cls, seed, budget_s=20.0):
     t0 = time.perf_counter()
     ref.nhood_perm_counts(g.indptr, g.indices, base, n_cls, spawn_states(seed, 1), n_threads=1)
     t1 = time.perf_counter() - t0
-    p_s = int(max(cores, min(64 * cores, budget_s / max(t1, 1e-3) * cores * 0.6)))
+    p_s = int(max(cores, min(12 * cores, budget_s / max(t1, 1e-3) * cores * 0.6)))
     t0 = time.perf_counter()
     ref.nhood_perm_counts(g.indptr, g.indices, base, n_cls, spawn_states(seed, p_s), n_threads=cores)
     dt = time.perf_counter() - t0
@@ -298,7 +298,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--perms", type=int, default=CFG2["n_perms"])
     ap.add_argument("--shuffle-threads", type=int, default=0)
-    ap.add_argument("--shuffle-algo", type=int, default=1)
+    ap.add_argument("--shuffle-algo", type=int, default=2)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 

@@ -407,6 +407,211 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta_kernel(LT* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2c. WARP-per-permutation exact replay (default).  Same algorithm as 2b, but every synchronisation is warp level
+//     (ballots, shuffles, __syncwarp): no block barriers at all.  A lane owns Q consecutive-by-32 PCG64 outputs
+//     (2Q raw 32-bit values) per batch and executes the Fisher-Yates steps of the values IT drew; the swaps act on
+//     global memory directly (L2): conflict-free steps in parallel, conflicting ones (own-range targets, duplicate
+//     targets found through a per-warp shared-memory hash table) afterwards by lane 0 in step order.
+//     ~4 warp instructions per shuffle step instead of ~12 for the CTA version, and thousands of permutations in
+//     flight per GPU, so the random label accesses of different permutations overlap.
+// ------------------------------------------------------------------------------------------------
+template <typename LT, int Q>
+__global__ void __launch_bounds__(128) nhood_shuffle_warp_kernel(LT* __restrict__ labels, int64_t stride,
+                                                                 const uint64_t* __restrict__ states, int64_t n_perms,
+                                                                 int nseg, const int64_t* __restrict__ seg_start,
+                                                                 const int64_t* __restrict__ seg_len, float wfactor) {
+    constexpr int RAW = 64 * Q;   // raw 32-bit values per batch
+    constexpr int HS = 256 * Q;   // hash slots per warp (load factor <= 0.25)
+    constexpr int HS_SHIFT = (Q == 1 ? 24 : Q == 2 ? 23 : 22);
+    static_assert(Q == 1 || Q == 2 || Q == 4, "Q");
+    __shared__ unsigned long long s_tab_all[4][HS];
+    __shared__ uint32_t s_sj_all[4][RAW];
+    __shared__ uint32_t s_flag_all[4][2 * Q];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    unsigned long long* s_tab = s_tab_all[warp];
+    uint32_t* s_sj = s_sj_all[warp];
+    uint32_t* s_flag = s_flag_all[warp];
+    for (int h = lane; h < HS; h += 32) s_tab[h] = SQB_EMPTY64;
+    if (lane < 2 * Q) s_flag[lane] = 0;
+    u128 M32, C32, Mt, Ct;
+    pcg_jump_consts(32, M32, C32);
+    pcg_jump_consts((uint64_t)lane + 1, Mt, Ct);
+    __syncwarp();
+
+    const int64_t warps_total = (int64_t)gridDim.x * 4;
+    for (int64_t perm = (int64_t)blockIdx.x * 4 + warp; perm < n_perms; perm += warps_total) {
+        LT* __restrict__ a = labels + perm * stride;
+        const uint64_t* st4 = states + perm * 4;
+        const u128 inc = mk128(st4[2], st4[3]);
+        u128 st = Mt * mk128(st4[0], st4[1]) + Ct * inc;  // state of output index `lane`
+        const u128 C32_inc = C32 * inc;
+        uint32_t raw[2 * Q];
+#pragma unroll
+        for (int k = 0; k < 2 * Q; ++k) raw[k] = 0;
+        int pos = RAW;
+
+        for (int seg = 0; seg < nseg; ++seg) {
+            const int64_t base = seg_start[seg];
+            int i_cur = (int)(seg_len[seg] - 1);  // n < 2^31 enforced on the host for this kernel
+            while (i_cur >= 1) {
+                if (pos >= RAW) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {  // outputs q*32 + lane of this batch
+                        const uint64_t o = pcg_output(st);
+                        st = M32 * st + C32_inc;
+                        raw[2 * q] = (uint32_t)o;
+                        raw[2 * q + 1] = (uint32_t)(o >> 32);
+                    }
+                    pos = 0;
+                }
+                // ---- phase parameters (warp uniform) ----
+                const uint32_t mask = 0xFFFFFFFFu >> __clz(i_cur);
+                const int i_lo = (int)(mask >> 1) + 1;
+                const int n_ph = i_cur - i_lo + 1;
+                const int K = sqb_window_size((int64_t)i_cur, RAW - pos, RAW, wfactor);
+                // raw index of (q, h) on this lane: q*64 + 2*lane + h
+                uint32_t u[2 * Q];
+                bool inw[2 * Q], F[2 * Q];
+                int c[2 * Q];
+#pragma unroll
+                for (int k = 0; k < 2 * Q; ++k) {
+                    const int r = (k >> 1) * 64 + 2 * lane + (k & 1);
+                    inw[k] = (r >= pos) && (r < pos + K);
+                    u[k] = raw[k] & mask;
+                    F[k] = inw[k] && (u[k] <= (uint32_t)i_cur);
+                    c[k] = 0;
+                }
+                // ---- acceptance fixed point: (v_r & mask) <= i_cur - #accepted before r ----
+                int total = 0;
+                while (true) {
+                    int run = 0;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const uint32_t blo = __ballot_sync(0xffffffffu, F[2 * q]);
+                        const uint32_t bhi = __ballot_sync(0xffffffffu, F[2 * q + 1]);
+                        c[2 * q] = run + __popc(blo & lt_mask) + __popc(bhi & lt_mask);
+                        c[2 * q + 1] = c[2 * q] + (F[2 * q] ? 1 : 0);
+                        run += __popc(blo) + __popc(bhi);
+                    }
+                    total = run;
+                    bool changed = false;
+#pragma unroll
+                    for (int k = 0; k < 2 * Q; ++k) {
+                        const bool nf = inw[k] && ((int)u[k] <= i_cur - c[k]) && (u[k] <= (uint32_t)i_cur);
+                        changed |= (nf != F[k]);
+                        F[k] = nf;
+                    }
+                    if (!__any_sync(0xffffffffu, changed)) break;
+                }
+                int S, newpos;
+                if (total >= n_ph) {  // the phase (same mask / same segment) ends inside this window
+                    S = n_ph;
+                    int myr = -1;
+#pragma unroll
+                    for (int k = 0; k < 2 * Q; ++k)
+                        if (F[k] && c[k] == S - 1) myr = (k >> 1) * 64 + 2 * lane + (k & 1);
+                    const uint32_t who = __ballot_sync(0xffffffffu, myr >= 0);
+                    newpos = __shfl_sync(0xffffffffu, myr, __ffs(who) - 1) + 1;
+                } else {
+                    S = total;
+                    newpos = pos + K;
+                }
+                if (S > 0) {
+                    const int own_lo = i_cur - S;  // targets j > own_lo lie inside the window's own index range
+                    bool act[2 * Q], ins[2 * Q];
+                    int slot[2 * Q];
+#pragma unroll
+                    for (int k = 0; k < 2 * Q; ++k) {
+                        act[k] = F[k] && c[k] < S;
+                        ins[k] = false;
+                        slot[k] = 0;
+                        if (act[k]) {
+                            const int s = c[k];
+                            const uint32_t j = u[k];
+                            s_sj[s] = j;
+                            if ((int)j > own_lo) {
+                                const int s2 = i_cur - (int)j;
+                                if (s2 != s) {
+                                    atomicOr(&s_flag[s >> 5], 1u << (s & 31));
+                                    atomicOr(&s_flag[s2 >> 5], 1u << (s2 & 31));
+                                } else {
+                                    act[k] = false;  // self swap: nothing to do
+                                }
+                            } else {
+                                uint32_t h = (j * 2654435761u) >> HS_SHIFT;
+                                const unsigned long long mine = ((unsigned long long)j << 32) | (unsigned)s;
+                                while (true) {
+                                    const unsigned long long prev = atomicCAS(&s_tab[h], SQB_EMPTY64, mine);
+                                    if (prev == SQB_EMPTY64) {
+                                        ins[k] = true;
+                                        slot[k] = (int)h;
+                                        break;
+                                    }
+                                    if ((uint32_t)(prev >> 32) == j) {  // duplicate target: both steps conflict
+                                        const int so = (int)(uint32_t)prev;
+                                        atomicOr(&s_flag[s >> 5], 1u << (s & 31));
+                                        atomicOr(&s_flag[so >> 5], 1u << (so & 31));
+                                        break;
+                                    }
+                                    h = (h + 1) & (HS - 1);
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    // conflict-free swaps: loads first (memory-level parallelism), then stores
+                    LT vi[2 * Q], vj[2 * Q];
+#pragma unroll
+                    for (int k = 0; k < 2 * Q; ++k) {
+                        if (act[k]) act[k] = !((s_flag[c[k] >> 5] >> (c[k] & 31)) & 1u);
+                        if (act[k]) {
+                            vi[k] = ld_cg<LT>(a + base + (i_cur - c[k]));
+                            vj[k] = ld_cg<LT>(a + base + (int64_t)u[k]);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2 * Q; ++k) {
+                        if (act[k]) {
+                            a[base + (i_cur - c[k])] = vj[k];
+                            a[base + (int64_t)u[k]] = vi[k];
+                        }
+                    }
+                    // conflicting swaps, in step order, straight on global memory (disjoint from the set above)
+                    uint32_t fw = (lane < 2 * Q) ? s_flag[lane] : 0u;
+                    uint32_t nz = __ballot_sync(0xffffffffu, fw != 0u);
+                    if (nz) {
+                        if (lane == 0) {
+                            for (int w = 0; w < 2 * Q; ++w) {
+                                uint32_t bits = s_flag[w];
+                                while (bits) {
+                                    const int b = __ffs(bits) - 1;
+                                    bits &= bits - 1;
+                                    const int s = w * 32 + b;
+                                    const int64_t pi = base + (i_cur - s), pj = base + (int64_t)s_sj[s];
+                                    const LT x = ld_cg<LT>(a + pi), y = ld_cg<LT>(a + pj);
+                                    a[pi] = y;
+                                    a[pj] = x;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (lane < 2 * Q) s_flag[lane] = 0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2 * Q; ++k)
+                        if (ins[k]) s_tab[slot[k]] = SQB_EMPTY64;
+                    __syncwarp();  // orders this window's global stores before the next window's loads (same warp)
+                }
+                i_cur -= S;
+                pos = newpos;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 3. transpose [P][stride] -> [n][PB]  (32 permutations x 256 nodes per CTA), optional row scatter through
 //    `order` (library-grouped position k -> original node id)
 // ------------------------------------------------------------------------------------------------
@@ -471,46 +676,39 @@ __global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __res
     if (node_end > n) node_end = n;
 
     if (G == 32) {
-        // lane = permutation.  A warp takes 32 consecutive nodes: their CSR segment is one contiguous index range that
-        // is loaded coalesced (one index per lane), the source node of every edge is found by a shuffle binary search
-        // over the 32 row ends, and the label gathers of 8 edges are issued back to back before the 8 atomics
-        // (memory-level parallelism 16 per warp instead of 1).
+        // lane = permutation; a warp walks UN consecutive CSR rows at once so that UN independent index loads, then UN
+        // independent label gathers (one 32-byte sector each) are in flight before the UN shared-memory atomics:
+        // ~7 instructions per (edge x 32 permutations), memory-level parallelism UN per warp.
+        constexpr int UN = 8;
         const int perm = blockIdx.y * 32 + lane;
         const bool valid = perm < P;
         const LT* __restrict__ col = labT + perm;
-        for (int64_t i0 = node_begin + (int64_t)warp * 32; i0 < node_end; i0 += (int64_t)nwarps * 32) {
-            const int64_t myn = i0 + lane;
-            const uint32_t p1 = indptr[(myn < node_end ? myn : node_end - 1) + 1];  // row end (clamped: empty tail rows)
-            const uint32_t E0 = indptr[i0];
-            const uint32_t E1 = __shfl_sync(0xffffffffu, p1, 31);
-            for (uint32_t eb = E0; eb < E1; eb += 32) {
-                const uint32_t e = eb + lane;
-                const uint32_t jl = (e < E1) ? indices[e] : 0u;
-                // source node of edge e: number of rows (of this block) that end at or before e
-                int lo = 0;
+        for (int64_t i0 = node_begin + (int64_t)warp * UN; i0 < node_end; i0 += (int64_t)nwarps * UN) {
+            uint32_t beg[UN], deg[UN], rowb[UN];
+            uint32_t maxdeg = 0;
 #pragma unroll
-                for (int step = 16; step >= 1; step >>= 1) {
-                    const uint32_t v = __shfl_sync(0xffffffffu, p1, lo + step - 1);
-                    if (v <= e) lo += step;
+            for (int u = 0; u < UN; ++u) {
+                const int64_t i = i0 + u;
+                if (i < node_end) {
+                    beg[u] = indptr[i];
+                    deg[u] = indptr[i + 1] - beg[u];
+                    rowb[u] = (uint32_t)col[i * PB] * (uint32_t)C;
+                } else {
+                    beg[u] = 0;
+                    deg[u] = 0;
+                    rowb[u] = 0;
                 }
-                const uint32_t srcl = (uint32_t)lo;  // < 32 whenever e < E1
-                const int cnt = (int)((E1 - eb) < 32u ? (E1 - eb) : 32u);
-                for (int t0 = 0; t0 < cnt; t0 += 8) {
-                    uint32_t av[8], bv[8];
+                maxdeg = deg[u] > maxdeg ? deg[u] : maxdeg;
+            }
+            for (uint32_t k = 0; k < maxdeg; ++k) {
+                uint32_t j[UN], bl[UN];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int t = t0 + k;
-                        const uint32_t j = __shfl_sync(0xffffffffu, jl, t & 31);
-                        const uint32_t sn = __shfl_sync(0xffffffffu, srcl, t & 31);
-                        const bool ok = t < cnt;
-                        av[k] = ok ? (uint32_t)col[(i0 + sn) * PB] : 0u;
-                        bv[k] = ok ? (uint32_t)col[(int64_t)j * PB] : 0u;
-                    }
+                for (int u = 0; u < UN; ++u) j[u] = (k < deg[u]) ? indices[beg[u] + k] : 0u;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        if (valid && (t0 + k) < cnt) atomicAdd(&hist[(av[k] * (uint32_t)C + bv[k]) * 32 + lane], 1u);
-                    }
-                }
+                for (int u = 0; u < UN; ++u) bl[u] = (k < deg[u]) ? (uint32_t)col[(int64_t)j[u] * PB] : 0u;
+#pragma unroll
+                for (int u = 0; u < UN; ++u)
+                    if (valid && k < deg[u]) atomicAdd(&hist[(rowb[u] + bl[u]) * 32 + lane], 1u);
             }
         }
     } else {
@@ -587,7 +785,8 @@ struct sqb_nhood {
     DevBuf<uint32_t> d_tmp_u32;
     std::vector<uint32_t> h_order;
     // options
-    int shuffle_algo = 1;
+    int shuffle_algo = 2;  // 0 serial thread-per-permutation, 1 CTA per permutation, 2 warp per permutation (default)
+    int shuffle_q = 4;     // algo 2: PCG64 outputs per lane per batch (window = 64*q raw values)
     int shuffle_threads = 512;
     int64_t perm_chunk = 0;  // 0 = auto
     int count_algo = 0;
@@ -674,6 +873,24 @@ static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t
     if (h->shuffle_algo == 0) {
         nhood_shuffle_serial_kernel<LT><<<(unsigned)ceil_div64(np, 32), 32, 0, c->stream>>>(
             lab, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p);
+    } else if (h->shuffle_algo == 2) {
+        const float wf = (float)h->shuffle_wfactor_x100 / 100.0f;
+        int64_t ctas = h->shuffle_ctas > 0 ? h->shuffle_ctas : (int64_t)c->sm_count * 8;
+        if (ctas > ceil_div64(np, 4)) ctas = ceil_div64(np, 4);
+        switch (h->shuffle_q) {
+            case 1:
+                nhood_shuffle_warp_kernel<LT, 1><<<(unsigned)ctas, 128, 0, c->stream>>>(lab, h->stride, states, np, h->nseg,
+                                                                                       h->d_seg_start.p, h->d_seg_len.p, wf);
+                break;
+            case 2:
+                nhood_shuffle_warp_kernel<LT, 2><<<(unsigned)ctas, 128, 0, c->stream>>>(lab, h->stride, states, np, h->nseg,
+                                                                                       h->d_seg_start.p, h->d_seg_len.p, wf);
+                break;
+            default:
+                nhood_shuffle_warp_kernel<LT, 4><<<(unsigned)ctas, 128, 0, c->stream>>>(lab, h->stride, states, np, h->nseg,
+                                                                                       h->d_seg_start.p, h->d_seg_len.p, wf);
+                break;
+        }
     } else {
         switch (h->shuffle_threads) {
             case 128:
@@ -746,7 +963,7 @@ extern "C" {
 int sqb_nhood_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const uint32_t* indptr, const uint32_t* indices, int n_cls,
                      sqb_nhood** out) {
     SQB_CHECK(ctx && out, SQB_ERR_INVALID, "sqb_nhood_create: null ctx/out");
-    SQB_CHECK(n >= 1 && n < 0xFFFFFFFFLL, SQB_ERR_INVALID, "sqb_nhood_create: n=%lld out of range [1, 2^32-1)", (long long)n);
+    SQB_CHECK(n >= 1 && n < 0x7FFFFFFFLL, SQB_ERR_INVALID, "sqb_nhood_create: n=%lld out of range [1, 2^31-1)", (long long)n);
     SQB_CHECK(nnz >= 0 && nnz < 0xFFFFFFFFLL, SQB_ERR_INVALID, "sqb_nhood_create: nnz=%lld does not fit uint32",
               (long long)nnz);
     // same message as the reference (_nhood.py:107-108)
@@ -798,8 +1015,11 @@ int sqb_nhood_destroy(sqb_nhood* h) {
 int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value) {
     SQB_CHECK(h && key, SQB_ERR_INVALID, "sqb_nhood_set_option: null argument");
     if (!strcmp(key, "shuffle_algo")) {
-        SQB_CHECK(value == 0 || value == 1, SQB_ERR_INVALID, "shuffle_algo must be 0 or 1");
+        SQB_CHECK(value >= 0 && value <= 2, SQB_ERR_INVALID, "shuffle_algo must be 0, 1 or 2");
         h->shuffle_algo = (int)value;
+    } else if (!strcmp(key, "shuffle_q")) {
+        SQB_CHECK(value == 1 || value == 2 || value == 4, SQB_ERR_INVALID, "shuffle_q must be 1, 2 or 4");
+        h->shuffle_q = (int)value;
     } else if (!strcmp(key, "shuffle_threads")) {
         SQB_CHECK(value == 128 || value == 256 || value == 512 || value == 1024, SQB_ERR_INVALID,
                   "shuffle_threads must be 128, 256, 512 or 1024");

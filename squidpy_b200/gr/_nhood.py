@@ -167,7 +167,7 @@ def nhood_enrichment(
     if library_key is not None:
         assert_categorical_obs(adata, key=library_key)
         libs = adata.obs[library_key]
-        lib_codes = np.asarray(libs.cat.codes).astype(np.int32)
+        lib_codes = np.asarray(libs.array.codes).astype(np.int32)
         n_libs = len(libs.cat.categories)
 
     start = time.perf_counter()

@@ -22,7 +22,8 @@ def _save_data(adata: Any, *, attr: str, key: str, data: Any, prefix: bool = Tru
 def category_codes(series, *, dtype) -> tuple[np.ndarray, int]:
     """Category -> code mapping of the reference (``clust_map`` dict loop, ``gr/_nhood.py:194-197``): code = position in
     ``cat.categories``.  A missing value has no entry in that dict and raises ``KeyError`` there; same here."""
-    codes = np.asarray(series.cat.codes)
+    # the Categorical's own code array: `series.cat.codes` would build a Series carrying the (string) obs index first
+    codes = np.asarray(series.array.codes if hasattr(series, "array") else series.cat.codes)
     if (codes < 0).any():
         raise KeyError(float("nan"))
     return codes.astype(dtype), len(series.cat.categories)

@@ -60,9 +60,9 @@ def test_create_errors():
         plan.upload(spawn_states(0, 2))
 
 
-@pytest.mark.parametrize("algo,threads", [(0, 512), (1, 128), (1, 256), (1, 512), (1, 1024)])
+@pytest.mark.parametrize("algo,threads,q", [(0, 512, 4), (1, 128, 4), (1, 256, 4), (1, 512, 4), (1, 1024, 4), (2, 512, 1), (2, 512, 2), (2, 512, 4)])
 @pytest.mark.parametrize("n", [2, 3, 5, 33, 100, 1000, 1025, 5041, 70001])
-def test_shuffle_is_numpy_exact(algo, threads, n):
+def test_shuffle_is_numpy_exact(algo, threads, q, n):
     """Shuffled label vectors equal numpy Generator.shuffle of the same spawned generators (oracle = exact replay,
     pinned to numpy in tests/test_oracle_golden.py)."""
     if algo == 0 and n > 6000:
@@ -73,6 +73,7 @@ def test_shuffle_is_numpy_exact(algo, threads, n):
     plan = _plan(g, n_cls)
     plan.set_option("shuffle_algo", algo)
     plan.set_option("shuffle_threads", threads)
+    plan.set_option("shuffle_q", q)
     plan.set_base(base)
     P = 7
     st = spawn_states(1234 + n, P)
@@ -81,7 +82,7 @@ def test_shuffle_is_numpy_exact(algo, threads, n):
     np.testing.assert_array_equal(got, ref.shuffle_labels(base, st))
 
 
-@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("algo", [0, 1, 2])
 def test_shuffle_library_groups(algo):
     n = 4000
     g = synth.hex_graph(40, 100)

@@ -33,13 +33,13 @@ def main():
     ref_counts = plan.download()
     results = []
     ctx.profile(True)
-    variants = []
-    for nt in (256, 512, 1024):
-        for ctas in (0, 148, 222, 296, 444, 592):
-            variants.append(dict(shuffle_threads=nt, shuffle_ctas=ctas, shuffle_wfactor_x100=400))
-    for wf in (200, 800, 1600):
-        variants.append(dict(shuffle_threads=512, shuffle_ctas=0, shuffle_wfactor_x100=wf))
-        variants.append(dict(shuffle_threads=1024, shuffle_ctas=0, shuffle_wfactor_x100=wf))
+    variants = [dict(shuffle_algo=1, shuffle_threads=512, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4)]
+    for q in (1, 2, 4):
+        for ctas in (0, 64, 125):
+            variants.append(dict(shuffle_algo=2, shuffle_q=q, shuffle_ctas=ctas, shuffle_wfactor_x100=400, shuffle_threads=512))
+    for wf in (100, 200, 800, 1600):
+        variants.append(dict(shuffle_algo=2, shuffle_q=4, shuffle_ctas=0, shuffle_wfactor_x100=wf, shuffle_threads=512))
+        variants.append(dict(shuffle_algo=2, shuffle_q=2, shuffle_ctas=0, shuffle_wfactor_x100=wf, shuffle_threads=512))
     for v in variants:
         for k, val in v.items():
             plan.set_option(k, val)
