@@ -612,6 +612,287 @@ __global__ void __launch_bounds__(128) nhood_shuffle_warp_kernel(LT* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2d. CTA per permutation, LARGE windows (default for big n).  ncu showed 2b/2c to be bound by the dependent
+//     instruction chain of a window (~600-1200 instructions per warp per window at IPC ~0.1-0.3), not by HBM or issue
+//     slots, so this version (a) makes a window R x larger (every thread draws R PCG64 outputs = 2R raw values per
+//     batch and executes the Fisher-Yates steps of the values IT drew, the per-value work being independent chains),
+//     (b) swaps conflict-free steps straight in global memory and stages only the conflicting ones in shared memory
+//     for the ordered replay, (c) needs 8-9 block barriers per ~3000 steps instead of per ~750.
+// ------------------------------------------------------------------------------------------------
+template <typename LT, int NT, int R>
+__global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__ labels, int64_t stride,
+                                                                const uint64_t* __restrict__ states, int64_t n_perms,
+                                                                int nseg, const int64_t* __restrict__ seg_start,
+                                                                const int64_t* __restrict__ seg_len, float wfactor) {
+    constexpr int V = 2 * R;          // raw values per thread per batch
+    constexpr int RAW = V * NT;       // raw values per batch
+    constexpr int HS = 2 * RAW;       // hash slots (load factor <= 0.5), power of two
+    constexpr int NW = NT / 32;
+    constexpr int LOG_HS = (HS == 1024 ? 10 : HS == 2048 ? 11 : HS == 4096 ? 12 : HS == 8192 ? 13 : HS == 16384 ? 14 : 15);
+    static_assert(HS == (1 << LOG_HS), "HS must be a power of two");
+    constexpr int HS_SHIFT = 32 - LOG_HS;
+
+    extern __shared__ __align__(16) unsigned char sqb_shuffle_smem[];
+    unsigned long long* s_tab = reinterpret_cast<unsigned long long*>(sqb_shuffle_smem);  // (target << 32) | step, or EMPTY
+    uint32_t* s_sj = reinterpret_cast<uint32_t*>(s_tab + HS);
+    uint32_t* s_flag = s_sj + RAW;
+    int* s_wsum = reinterpret_cast<int*>(s_flag + RAW / 32);  // [R][32]
+    int* s_misc = s_wsum + R * 32;                             // [4]
+    LT* s_own = reinterpret_cast<LT*>(s_misc + 4);
+    LT* s_hval = s_own + RAW;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int h = tid; h < HS; h += NT) s_tab[h] = SQB_EMPTY64;
+    for (int w = tid; w < RAW / 32; w += NT) s_flag[w] = 0;
+    for (int w = tid; w < R * 32; w += NT) s_wsum[w] = 0;
+    u128 Mn, Cn, Mt, Ct;
+    pcg_jump_consts((uint64_t)NT, Mn, Cn);
+    pcg_jump_consts((uint64_t)tid + 1, Mt, Ct);
+    __syncthreads();
+
+    for (int64_t perm = blockIdx.x; perm < n_perms; perm += gridDim.x) {
+        LT* __restrict__ a = labels + perm * stride;
+        const uint64_t* st4 = states + perm * 4;
+        const u128 inc = mk128(st4[2], st4[3]);
+        u128 st = Mt * mk128(st4[0], st4[1]) + Ct * inc;  // state of output index `tid`
+        const u128 Cn_inc = Cn * inc;
+        uint32_t raw[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) raw[k] = 0;
+        int pos = RAW;
+
+        for (int seg = 0; seg < nseg; ++seg) {
+            const int64_t base = seg_start[seg];
+            int i_cur = (int)(seg_len[seg] - 1);  // n < 2^31
+            while (i_cur >= 1) {
+                if (pos >= RAW) {
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {  // output q*NT + tid of this batch -> raw 2*(q*NT+tid) + {0,1}
+                        const uint64_t o = pcg_output(st);
+                        st = Mn * st + Cn_inc;
+                        raw[2 * q] = (uint32_t)o;
+                        raw[2 * q + 1] = (uint32_t)(o >> 32);
+                    }
+                    pos = 0;
+                }
+                const uint32_t mask = 0xFFFFFFFFu >> __clz(i_cur);
+                const int i_lo = (int)(mask >> 1) + 1;
+                const int n_ph = i_cur - i_lo + 1;
+                const int K = sqb_window_size((int64_t)i_cur, RAW - pos, RAW, wfactor);
+                uint32_t inmask = 0, fmask = 0;  // bit k: value k inside the window / accepted
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const int r = (k >> 1) * (2 * NT) + 2 * tid + (k & 1);
+                    if (r >= pos && r < pos + K) {
+                        inmask |= 1u << k;
+                        if ((raw[k] & mask) <= (uint32_t)i_cur) fmask |= 1u << k;
+                    }
+                }
+                // ---- acceptance fixed point; c(k) = cb[k>>1] + (k odd ? bit(k-1) : 0) ----
+                int cb[R];
+                int total = 0;
+                while (true) {
+                    uint32_t blo[R], bhi[R];
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        blo[q] = __ballot_sync(0xffffffffu, (fmask >> (2 * q)) & 1u);
+                        bhi[q] = __ballot_sync(0xffffffffu, (fmask >> (2 * q + 1)) & 1u);
+                        if (lane == 0) s_wsum[q * 32 + warp] = __popc(blo[q]) + __popc(bhi[q]);
+                    }
+                    __syncthreads();
+                    int run = 0;
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        const int v = (lane < NW) ? s_wsum[q * 32 + lane] : 0;
+                        int incl = v;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                            if (lane >= d) incl += t;
+                        }
+                        const int woff = __shfl_sync(0xffffffffu, incl - v, warp);
+                        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+                        cb[q] = run + woff + __popc(blo[q] & lt_mask) + __popc(bhi[q] & lt_mask);
+                        run += tot;
+                    }
+                    total = run;
+                    uint32_t nf = 0;
+#pragma unroll
+                    for (int k = 0; k < V; ++k) {
+                        const int ck = cb[k >> 1] + ((k & 1) ? (int)((fmask >> (k - 1)) & 1u) : 0);
+                        const uint32_t uk = raw[k] & mask;
+                        if (((inmask >> k) & 1u) && uk <= (uint32_t)i_cur && (int)uk <= i_cur - ck) nf |= 1u << k;
+                    }
+                    const int any = __syncthreads_or(nf != fmask);
+                    if (!any) break;
+                    fmask = nf;
+                }
+                const bool phase_ends = total >= n_ph;
+                const int S = phase_ends ? n_ph : total;
+                const int own_lo = i_cur - S;
+                // ---- B1: conflict detection (steps are executed by the thread that drew them) ----
+                uint32_t actmask = 0, insmask = 0;
+                bool any_flag_local = false;
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    if ((fmask >> k) & 1u) {
+                        const int ck = cb[k >> 1] + ((k & 1) ? (int)((fmask >> (k - 1)) & 1u) : 0);
+                        if (phase_ends && ck == S - 1) s_misc[0] = (k >> 1) * (2 * NT) + 2 * tid + (k & 1);
+                        if (ck < S) {
+                            const uint32_t j = raw[k] & mask;
+                            s_sj[ck] = j;
+                            if ((int)j > own_lo) {
+                                const int s2 = i_cur - (int)j;
+                                if (s2 != ck) {
+                                    actmask |= 1u << k;
+                                    atomicOr(&s_flag[ck >> 5], 1u << (ck & 31));
+                                    atomicOr(&s_flag[s2 >> 5], 1u << (s2 & 31));
+                                }
+                            } else {
+                                actmask |= 1u << k;
+                                uint32_t h = (j * 2654435761u) >> HS_SHIFT;
+                                const unsigned long long mine = ((unsigned long long)j << 32) | (unsigned)ck;
+                                while (true) {
+                                    const unsigned long long prev = atomicCAS(&s_tab[h], SQB_EMPTY64, mine);
+                                    if (prev == SQB_EMPTY64) {
+                                        insmask |= 1u << k;
+                                        break;
+                                    }
+                                    if ((uint32_t)(prev >> 32) == j) {
+                                        const int so = (int)(uint32_t)prev;
+                                        atomicOr(&s_flag[ck >> 5], 1u << (ck & 31));
+                                        atomicOr(&s_flag[so >> 5], 1u << (so & 31));
+                                        break;
+                                    }
+                                    h = (h + 1) & (HS - 1);
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                const int newpos = phase_ends ? (s_misc[0] + 1) : (pos + K);
+                // ---- B2: conflict-free steps swap directly in global memory; conflicting ones are staged ----
+                {
+                    LT vi[V], vj[V];
+                    uint32_t direct = 0, staged = 0;
+#pragma unroll
+                    for (int k = 0; k < V; ++k) {
+                        if ((fmask >> k) & 1u) {
+                            const int ck = cb[k >> 1] + ((k & 1) ? (int)((fmask >> (k - 1)) & 1u) : 0);
+                            if (ck < S) {
+                                const uint32_t j = raw[k] & mask;
+                                const bool flagged = (s_flag[ck >> 5] >> (ck & 31)) & 1u;
+                                if (flagged) {  // includes self swaps that another step targets
+                                    staged |= 1u << k;
+                                    vi[k] = ld_cs<LT>(a + base + (i_cur - ck));
+                                    if ((insmask >> k) & 1u) vj[k] = ld_cg<LT>(a + base + (int64_t)j);
+                                } else if ((actmask >> k) & 1u) {
+                                    direct |= 1u << k;
+                                    vi[k] = ld_cs<LT>(a + base + (i_cur - ck));
+                                    vj[k] = ld_cg<LT>(a + base + (int64_t)j);
+                                }
+                            }
+                        }
+                    }
+                    any_flag_local = staged != 0;
+#pragma unroll
+                    for (int k = 0; k < V; ++k) {
+                        if (((direct | staged) >> k) & 1u) {
+                            const int ck = cb[k >> 1] + ((k & 1) ? (int)((fmask >> (k - 1)) & 1u) : 0);
+                            const uint32_t j = raw[k] & mask;
+                            if ((direct >> k) & 1u) {
+                                st_cs<LT>(a + base + (i_cur - ck), vj[k]);  // final position: never read again here
+                                a[base + (int64_t)j] = vi[k];
+                            } else {
+                                s_own[ck] = vi[k];
+                                if ((insmask >> k) & 1u) {
+                                    uint32_t h = (j * 2654435761u) >> HS_SHIFT;
+                                    while ((uint32_t)(s_tab[h] >> 32) != j) h = (h + 1) & (HS - 1);
+                                    s_hval[h] = vj[k];
+                                }
+                            }
+                        }
+                    }
+                }
+                const int any_flag = __syncthreads_or(any_flag_local);
+                if (any_flag) {
+                    // ---- B3: ordered replay of the conflicting steps on the staged values (warp 0, lane 0) ----
+                    if (warp == 0) {
+                        const int nwords = (S + 31) >> 5;
+                        for (int wb = 0; wb < nwords; wb += 32) {
+                            const uint32_t myw = (wb + lane < nwords) ? s_flag[wb + lane] : 0u;
+                            uint32_t nz = __ballot_sync(0xffffffffu, myw != 0u);
+                            while (nz) {
+                                const int wl = __ffs(nz) - 1;
+                                nz &= nz - 1;
+                                uint32_t bits = __shfl_sync(0xffffffffu, myw, wl);
+                                if (lane == 0) {
+                                    while (bits) {
+                                        const int b = __ffs(bits) - 1;
+                                        bits &= bits - 1;
+                                        const int s = (wb + wl) * 32 + b;
+                                        const uint32_t j = s_sj[s];
+                                        const LT x = s_own[s];
+                                        if ((int)j > own_lo) {
+                                            const int s2 = i_cur - (int)j;
+                                            if (s2 != s) {
+                                                const LT y = s_own[s2];
+                                                s_own[s] = y;
+                                                s_own[s2] = x;
+                                            }
+                                        } else {
+                                            uint32_t h = (j * 2654435761u) >> HS_SHIFT;
+                                            while ((uint32_t)(s_tab[h] >> 32) != j) h = (h + 1) & (HS - 1);
+                                            const LT y = s_hval[h];
+                                            s_own[s] = y;
+                                            s_hval[h] = x;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    // ---- B4: write the staged values back ----
+#pragma unroll
+                    for (int k = 0; k < V; ++k) {
+                        if ((fmask >> k) & 1u) {
+                            const int ck = cb[k >> 1] + ((k & 1) ? (int)((fmask >> (k - 1)) & 1u) : 0);
+                            if (ck < S && ((s_flag[ck >> 5] >> (ck & 31)) & 1u)) {
+                                const uint32_t j = raw[k] & mask;
+                                st_cs<LT>(a + base + (i_cur - ck), s_own[ck]);
+                                if ((insmask >> k) & 1u) {
+                                    uint32_t h = (j * 2654435761u) >> HS_SHIFT;
+                                    while ((uint32_t)(s_tab[h] >> 32) != j) h = (h + 1) & (HS - 1);
+                                    a[base + (int64_t)j] = s_hval[h];
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    for (int w = tid; w < ((S + 31) >> 5); w += NT) s_flag[w] = 0;
+                }
+                // reset the hash table entries this thread inserted
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    if ((insmask >> k) & 1u) {
+                        const uint32_t j = raw[k] & mask;
+                        uint32_t h = (j * 2654435761u) >> HS_SHIFT;
+                        while ((uint32_t)(s_tab[h] >> 32) != j) h = (h + 1) & (HS - 1);
+                        s_tab[h] = SQB_EMPTY64;
+                    }
+                }
+                __syncthreads();
+                i_cur -= S;
+                pos = newpos;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 3. transpose [P][stride] -> [n][PB]  (32 permutations x 256 nodes per CTA), optional row scatter through
 //    `order` (library-grouped position k -> original node id)
 // ------------------------------------------------------------------------------------------------
@@ -681,34 +962,49 @@ __global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __res
         // ~7 instructions per (edge x 32 permutations), memory-level parallelism UN per warp.
         constexpr int UN = 8;
         const int perm = blockIdx.y * 32 + lane;
-        const bool valid = perm < P;
         const LT* __restrict__ col = labT + perm;
-        for (int64_t i0 = node_begin + (int64_t)warp * UN; i0 < node_end; i0 += (int64_t)nwarps * UN) {
+        // all element offsets are 32 x 32 -> 64 bit products (one IMAD.WIDE.U32 each): n < 2^31, PB < 2^31
+        const uint32_t PBu = (uint32_t)PB, Cu = (uint32_t)C;
+        const uint32_t nb32 = (uint32_t)node_begin, ne32 = (uint32_t)node_end;
+        uint32_t* __restrict__ myhist = hist + lane;
+        for (uint32_t i0 = nb32 + (uint32_t)warp * UN; i0 < ne32; i0 += (uint32_t)nwarps * UN) {
             uint32_t beg[UN], deg[UN], rowb[UN];
-            uint32_t maxdeg = 0;
+            uint32_t maxdeg = 0, mindeg = 0xFFFFFFFFu;
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
-                const int64_t i = i0 + u;
-                if (i < node_end) {
+                const uint32_t i = i0 + u;
+                beg[u] = 0;
+                deg[u] = 0;
+                rowb[u] = 0;
+                if (i < ne32) {
                     beg[u] = indptr[i];
                     deg[u] = indptr[i + 1] - beg[u];
-                    rowb[u] = (uint32_t)col[i * PB] * (uint32_t)C;
-                } else {
-                    beg[u] = 0;
-                    deg[u] = 0;
-                    rowb[u] = 0;
+                    rowb[u] = (uint32_t)col[(uint64_t)i * PBu] * Cu;
                 }
                 maxdeg = deg[u] > maxdeg ? deg[u] : maxdeg;
+                mindeg = deg[u] < mindeg ? deg[u] : mindeg;
             }
-            for (uint32_t k = 0; k < maxdeg; ++k) {
+            // rows of a spatial graph have (nearly) equal degree: unpredicated fast path up to the smallest degree,
+            // predicated tail for the rest.  Lanes of padded permutations (perm >= P) count into columns nobody reads.
+            uint32_t k = 0;
+            for (; k < mindeg; ++k) {
                 uint32_t j[UN], bl[UN];
 #pragma unroll
-                for (int u = 0; u < UN; ++u) j[u] = (k < deg[u]) ? indices[beg[u] + k] : 0u;
+                for (int u = 0; u < UN; ++u) j[u] = indices[beg[u] + k];
 #pragma unroll
-                for (int u = 0; u < UN; ++u) bl[u] = (k < deg[u]) ? (uint32_t)col[(int64_t)j[u] * PB] : 0u;
+                for (int u = 0; u < UN; ++u) bl[u] = (uint32_t)col[(uint64_t)j[u] * PBu];
 #pragma unroll
-                for (int u = 0; u < UN; ++u)
-                    if (valid && k < deg[u]) atomicAdd(&hist[(rowb[u] + bl[u]) * 32 + lane], 1u);
+                for (int u = 0; u < UN; ++u) atomicAdd(myhist + (rowb[u] + bl[u]) * 32u, 1u);
+            }
+            for (; k < maxdeg; ++k) {
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    if (k < deg[u]) {
+                        const uint32_t j = indices[beg[u] + k];
+                        const uint32_t bl = (uint32_t)col[(uint64_t)j * PBu];
+                        atomicAdd(myhist + (rowb[u] + bl) * 32u, 1u);
+                    }
+                }
             }
         }
     } else {
@@ -787,6 +1083,7 @@ struct sqb_nhood {
     // options
     int shuffle_algo = 2;  // 0 serial thread-per-permutation, 1 CTA per permutation, 2 warp per permutation (default)
     int shuffle_q = 4;     // algo 2: PCG64 outputs per lane per batch (window = 64*q raw values)
+    int shuffle_r = 4;     // algo 3: PCG64 outputs per thread per batch (window = 2*r*threads raw values)
     int shuffle_threads = 512;
     int64_t perm_chunk = 0;  // 0 = auto
     int count_algo = 0;
@@ -866,6 +1163,27 @@ static int launch_shuffle_nt(sqb_nhood* h, LT* lab, const uint64_t* states, int6
     return SQB_OK;
 }
 
+template <typename LT, int NT, int R>
+static int launch_shuffle_cta2(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np) {
+    sqb_ctx* c = h->ctx;
+    auto k = nhood_shuffle_cta2_kernel<LT, NT, R>;
+    constexpr size_t RAW = (size_t)2 * R * NT, HS = 2 * RAW;
+    const size_t smem = HS * 8 + RAW * 4 + (RAW / 32) * 4 + (size_t)R * 32 * 4 + 16 + RAW * sizeof(LT) + HS * sizeof(LT);
+    SQB_CHECK(smem <= c->smem_optin, SQB_ERR_UNSUPPORTED, "shuffle_algo 3: %zu bytes of shared memory exceed the device limit", smem);
+    SQB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = h->shuffle_ctas;
+    if (grid <= 0) {
+        int per_sm = 1;
+        SQB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, smem));
+        if (per_sm < 1) per_sm = 1;
+        grid = (int64_t)per_sm * c->sm_count;
+    }
+    if (grid > np) grid = np;
+    k<<<(unsigned)grid, NT, smem, c->stream>>>(lab, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p,
+                                               (float)h->shuffle_wfactor_x100 / 100.0f);
+    return SQB_OK;
+}
+
 template <typename LT>
 static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np) {
     sqb_ctx* c = h->ctx;
@@ -873,6 +1191,18 @@ static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t
     if (h->shuffle_algo == 0) {
         nhood_shuffle_serial_kernel<LT><<<(unsigned)ceil_div64(np, 32), 32, 0, c->stream>>>(
             lab, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p);
+    } else if (h->shuffle_algo == 3) {
+        int rc = SQB_ERR_INVALID;
+        const int nt = h->shuffle_threads, r = h->shuffle_r;
+        if (nt == 512 && r == 4) rc = launch_shuffle_cta2<LT, 512, 4>(h, lab, states, np);
+        else if (nt == 512 && r == 2) rc = launch_shuffle_cta2<LT, 512, 2>(h, lab, states, np);
+        else if (nt == 256 && r == 4) rc = launch_shuffle_cta2<LT, 256, 4>(h, lab, states, np);
+        else if (nt == 256 && r == 8) rc = launch_shuffle_cta2<LT, 256, 8>(h, lab, states, np);
+        else if (nt == 1024 && r == 2) rc = launch_shuffle_cta2<LT, 1024, 2>(h, lab, states, np);
+        else if (nt == 1024 && r == 4) rc = launch_shuffle_cta2<LT, 1024, 4>(h, lab, states, np);
+        else if (nt == 128 && r == 4) rc = launch_shuffle_cta2<LT, 128, 4>(h, lab, states, np);
+        else sqb_set_error("shuffle_algo 3: unsupported (shuffle_threads, shuffle_r) = (%d, %d)", nt, r);
+        SQB_TRY(rc);
     } else if (h->shuffle_algo == 2) {
         const float wf = (float)h->shuffle_wfactor_x100 / 100.0f;
         int64_t ctas = h->shuffle_ctas > 0 ? h->shuffle_ctas : (int64_t)c->sm_count * 8;
@@ -1015,8 +1345,11 @@ int sqb_nhood_destroy(sqb_nhood* h) {
 int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value) {
     SQB_CHECK(h && key, SQB_ERR_INVALID, "sqb_nhood_set_option: null argument");
     if (!strcmp(key, "shuffle_algo")) {
-        SQB_CHECK(value >= 0 && value <= 2, SQB_ERR_INVALID, "shuffle_algo must be 0, 1 or 2");
+        SQB_CHECK(value >= 0 && value <= 3, SQB_ERR_INVALID, "shuffle_algo must be 0, 1, 2 or 3");
         h->shuffle_algo = (int)value;
+    } else if (!strcmp(key, "shuffle_r")) {
+        SQB_CHECK(value == 2 || value == 4 || value == 8, SQB_ERR_INVALID, "shuffle_r must be 2, 4 or 8");
+        h->shuffle_r = (int)value;
     } else if (!strcmp(key, "shuffle_q")) {
         SQB_CHECK(value == 1 || value == 2 || value == 4, SQB_ERR_INVALID, "shuffle_q must be 1, 2 or 4");
         h->shuffle_q = (int)value;
