@@ -21,6 +21,14 @@
 
 typedef unsigned __int128 u128;
 
+// Block barriers (bar.sync / bar.red) are warp-ALIGNED instructions: every lane of a warp must execute them together.
+// After data-dependent branches (hash probing, staging paths) the lanes are not guaranteed to have re-converged
+// (compute-sanitizer synccheck: "Divergent thread(s) in warp" -> cudaErrorIllegalInstruction on sm_100), and the
+// compiler elides a plain __syncwarp() it believes redundant, hence the volatile asm
+// (and ptxas turns a `bar.warp.sync 0xffffffff` it considers redundant into a NOP, so the full mask is passed in
+// at run time, as a kernel argument, which it cannot reason about).
+#define SQB_CONVERGE() asm volatile("bar.warp.sync %0;" ::"r"(full_mask) : "memory")
+
 __constant__ uint64_t c_jump_M[SQB_PCG_JUMP_BITS][2] = SQB_PCG_JUMP_M_INIT;
 __constant__ uint64_t c_jump_C[SQB_PCG_JUMP_BITS][2] = SQB_PCG_JUMP_C_INIT;
 
@@ -176,7 +184,8 @@ template <typename LT, int NT>
 __global__ void __launch_bounds__(NT) nhood_shuffle_cta_kernel(LT* __restrict__ labels, int64_t stride,
                                                                const uint64_t* __restrict__ states, int64_t n_perms,
                                                                int nseg, const int64_t* __restrict__ seg_start,
-                                                               const int64_t* __restrict__ seg_len, float wfactor) {
+                                                               const int64_t* __restrict__ seg_len, float wfactor,
+                                                               uint32_t full_mask) {
     constexpr int RAW = 2 * NT;
     constexpr int HS = 4 * NT;  // hash slots (load factor <= 0.5)
     constexpr int NW = NT / 32;
@@ -339,6 +348,7 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta_kernel(LT* __restrict__ 
                         if (s < S) s_own[s] = vo[q];
                         if (owner[q]) s_hval[slot[q]] = vh[q];
                     }
+                    SQB_CONVERGE();
                     __syncthreads();
                     // conflict-free swaps in parallel
 #pragma unroll
@@ -385,6 +395,7 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta_kernel(LT* __restrict__ 
                             }
                         }
                     }
+                    SQB_CONVERGE();
                     __syncthreads();
                     // write back + reset the tables for the next window
 #pragma unroll
@@ -397,6 +408,7 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta_kernel(LT* __restrict__ 
                         }
                     }
                     if (tid < RAW / 32) s_flag[tid] = 0;
+                    SQB_CONVERGE();
                     __syncthreads();
                 }
                 i_cur -= S;
@@ -623,7 +635,8 @@ template <typename LT, int NT, int R>
 __global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__ labels, int64_t stride,
                                                                 const uint64_t* __restrict__ states, int64_t n_perms,
                                                                 int nseg, const int64_t* __restrict__ seg_start,
-                                                                const int64_t* __restrict__ seg_len, float wfactor) {
+                                                                const int64_t* __restrict__ seg_len, float wfactor,
+                                                                uint32_t full_mask) {
     constexpr int V = 2 * R;          // raw values per thread per batch
     constexpr int RAW = V * NT;       // raw values per batch
     constexpr int HS = 2 * RAW;       // hash slots (load factor <= 0.5), power of two
@@ -646,6 +659,7 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__
     for (int h = tid; h < HS; h += NT) s_tab[h] = SQB_EMPTY64;
     for (int w = tid; w < RAW / 32; w += NT) s_flag[w] = 0;
     for (int w = tid; w < R * 32; w += NT) s_wsum[w] = 0;
+    if (tid < 4) s_misc[tid] = 0;
     u128 Mn, Cn, Mt, Ct;
     pcg_jump_consts((uint64_t)NT, Mn, Cn);
     pcg_jump_consts((uint64_t)tid + 1, Mt, Ct);
@@ -771,6 +785,7 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__
                         }
                     }
                 }
+                SQB_CONVERGE();
                 __syncthreads();
                 const int newpos = phase_ends ? (s_misc[0] + 1) : (pos + K);
                 // ---- B2: conflict-free steps swap directly in global memory; conflicting ones are staged ----
@@ -816,7 +831,13 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__
                         }
                     }
                 }
-                const int any_flag = __syncthreads_or(any_flag_local);
+                // block-wide OR through shared memory + a plain barrier: bar.red (__syncthreads_or) is a warp-aligned
+                // instruction and faults ("divergent thread(s) in warp") when the lanes that took the staging / probing
+                // paths above have not re-converged, which ptxas does not guarantee here
+                if (any_flag_local) s_misc[1] = 1;
+                SQB_CONVERGE();
+                __syncthreads();
+                const int any_flag = s_misc[1];
                 if (any_flag) {
                     // ---- B3: ordered replay of the conflicting steps on the staged values (warp 0, lane 0) ----
                     if (warp == 0) {
@@ -871,6 +892,7 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__
                             }
                         }
                     }
+                    SQB_CONVERGE();
                     __syncthreads();
                     for (int w = tid; w < ((S + 31) >> 5); w += NT) s_flag[w] = 0;
                 }
@@ -884,7 +906,9 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__
                         s_tab[h] = SQB_EMPTY64;
                     }
                 }
+                SQB_CONVERGE();
                 __syncthreads();
+                if (tid == 0) s_misc[1] = 0;  // next writers come after the next window's barriers
                 i_cur -= S;
                 pos = newpos;
             }
@@ -1159,7 +1183,7 @@ static int launch_shuffle_nt(sqb_nhood* h, LT* lab, const uint64_t* states, int6
     }
     if (grid > np) grid = np;
     k<<<(unsigned)grid, NT, smem, c->stream>>>(lab, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p,
-                                            (float)h->shuffle_wfactor_x100 / 100.0f);
+                                            (float)h->shuffle_wfactor_x100 / 100.0f, 0xFFFFFFFFu);
     return SQB_OK;
 }
 
@@ -1180,7 +1204,7 @@ static int launch_shuffle_cta2(sqb_nhood* h, LT* lab, const uint64_t* states, in
     }
     if (grid > np) grid = np;
     k<<<(unsigned)grid, NT, smem, c->stream>>>(lab, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p,
-                                               (float)h->shuffle_wfactor_x100 / 100.0f);
+                                               (float)h->shuffle_wfactor_x100 / 100.0f, 0xFFFFFFFFu);
     return SQB_OK;
 }
 
