@@ -748,6 +748,9 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__
                 // ---- B1: conflict detection (steps are executed by the thread that drew them) ----
                 uint32_t actmask = 0, insmask = 0;
                 bool any_flag_local = false;
+                uint32_t slotv[V];  // hash slot of every key this thread inserted
+#pragma unroll
+                for (int k = 0; k < V; ++k) slotv[k] = 0;
 #pragma unroll
                 for (int k = 0; k < V; ++k) {
                     if ((fmask >> k) & 1u) {
@@ -771,6 +774,7 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__
                                     const unsigned long long prev = atomicCAS(&s_tab[h], SQB_EMPTY64, mine);
                                     if (prev == SQB_EMPTY64) {
                                         insmask |= 1u << k;
+                                        slotv[k] = h;
                                         break;
                                     }
                                     if ((uint32_t)(prev >> 32) == j) {
@@ -789,46 +793,39 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__
                 __syncthreads();
                 const int newpos = phase_ends ? (s_misc[0] + 1) : (pos + K);
                 // ---- B2: conflict-free steps swap directly in global memory; conflicting ones are staged ----
+                // Written branch-free (ternaries / single-statement ifs => predicated loads and stores): compute-sanitizer
+                // synccheck showed lanes arriving at the next block barrier un-converged when this phase contained
+                // real branches around the global loads (cudaErrorIllegalInstruction on sm_100).
+                uint32_t direct = 0, staged = 0;
                 {
                     LT vi[V], vj[V];
-                    uint32_t direct = 0, staged = 0;
 #pragma unroll
                     for (int k = 0; k < V; ++k) {
-                        if ((fmask >> k) & 1u) {
-                            const int ck = cb[k >> 1] + ((k & 1) ? (int)((fmask >> (k - 1)) & 1u) : 0);
-                            if (ck < S) {
-                                const uint32_t j = raw[k] & mask;
-                                const bool flagged = (s_flag[ck >> 5] >> (ck & 31)) & 1u;
-                                if (flagged) {  // includes self swaps that another step targets
-                                    staged |= 1u << k;
-                                    vi[k] = ld_cs<LT>(a + base + (i_cur - ck));
-                                    if ((insmask >> k) & 1u) vj[k] = ld_cg<LT>(a + base + (int64_t)j);
-                                } else if ((actmask >> k) & 1u) {
-                                    direct |= 1u << k;
-                                    vi[k] = ld_cs<LT>(a + base + (i_cur - ck));
-                                    vj[k] = ld_cg<LT>(a + base + (int64_t)j);
-                                }
-                            }
-                        }
+                        const int ck = cb[k >> 1] + ((k & 1) ? (int)((fmask >> (k - 1)) & 1u) : 0);
+                        const bool live = ((fmask >> k) & 1u) && ck < S;
+                        const int cks = live ? ck : 0;
+                        const bool flagged = live && ((s_flag[cks >> 5] >> (cks & 31)) & 1u);
+                        const bool dir = live && !flagged && ((actmask >> k) & 1u);
+                        const bool ins = (insmask >> k) & 1u;
+                        staged |= (flagged ? 1u : 0u) << k;  // includes self swaps that another step targets
+                        direct |= (dir ? 1u : 0u) << k;
+                        const uint32_t j = raw[k] & mask;
+                        const LT* po = a + base + (i_cur - cks);
+                        const LT* pt = a + base + (int64_t)((dir || (flagged && ins)) ? j : 0u);
+                        vi[k] = (dir || flagged) ? ld_cs<LT>(po) : (LT)0;
+                        vj[k] = (dir || (flagged && ins)) ? ld_cg<LT>(pt) : (LT)0;
                     }
                     any_flag_local = staged != 0;
 #pragma unroll
                     for (int k = 0; k < V; ++k) {
-                        if (((direct | staged) >> k) & 1u) {
-                            const int ck = cb[k >> 1] + ((k & 1) ? (int)((fmask >> (k - 1)) & 1u) : 0);
-                            const uint32_t j = raw[k] & mask;
-                            if ((direct >> k) & 1u) {
-                                st_cs<LT>(a + base + (i_cur - ck), vj[k]);  // final position: never read again here
-                                a[base + (int64_t)j] = vi[k];
-                            } else {
-                                s_own[ck] = vi[k];
-                                if ((insmask >> k) & 1u) {
-                                    uint32_t h = (j * 2654435761u) >> HS_SHIFT;
-                                    while ((uint32_t)(s_tab[h] >> 32) != j) h = (h + 1) & (HS - 1);
-                                    s_hval[h] = vj[k];
-                                }
-                            }
-                        }
+                        const int ck = cb[k >> 1] + ((k & 1) ? (int)((fmask >> (k - 1)) & 1u) : 0);
+                        const bool dir = (direct >> k) & 1u, stg = (staged >> k) & 1u, ins = (insmask >> k) & 1u;
+                        const int cks = (dir || stg) ? ck : 0;
+                        const uint32_t j = raw[k] & mask;
+                        if (dir) st_cs<LT>(a + base + (i_cur - cks), vj[k]);  // final position: never read again here
+                        if (dir) a[base + (int64_t)j] = vi[k];
+                        if (stg) s_own[cks] = vi[k];
+                        if (stg && ins) s_hval[slotv[k]] = vj[k];
                     }
                 }
                 // block-wide OR through shared memory + a plain barrier: bar.red (__syncthreads_or) is a warp-aligned
@@ -879,18 +876,12 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__
                     // ---- B4: write the staged values back ----
 #pragma unroll
                     for (int k = 0; k < V; ++k) {
-                        if ((fmask >> k) & 1u) {
-                            const int ck = cb[k >> 1] + ((k & 1) ? (int)((fmask >> (k - 1)) & 1u) : 0);
-                            if (ck < S && ((s_flag[ck >> 5] >> (ck & 31)) & 1u)) {
-                                const uint32_t j = raw[k] & mask;
-                                st_cs<LT>(a + base + (i_cur - ck), s_own[ck]);
-                                if ((insmask >> k) & 1u) {
-                                    uint32_t h = (j * 2654435761u) >> HS_SHIFT;
-                                    while ((uint32_t)(s_tab[h] >> 32) != j) h = (h + 1) & (HS - 1);
-                                    a[base + (int64_t)j] = s_hval[h];
-                                }
-                            }
-                        }
+                        const int ck = cb[k >> 1] + ((k & 1) ? (int)((fmask >> (k - 1)) & 1u) : 0);
+                        const bool stg = (staged >> k) & 1u, ins = (insmask >> k) & 1u;
+                        const int cks = stg ? ck : 0;
+                        const uint32_t j = raw[k] & mask;
+                        if (stg) st_cs<LT>(a + base + (i_cur - cks), s_own[cks]);
+                        if (stg && ins) a[base + (int64_t)j] = s_hval[slotv[k]];
                     }
                     SQB_CONVERGE();
                     __syncthreads();
@@ -898,14 +889,8 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__
                 }
                 // reset the hash table entries this thread inserted
 #pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    if ((insmask >> k) & 1u) {
-                        const uint32_t j = raw[k] & mask;
-                        uint32_t h = (j * 2654435761u) >> HS_SHIFT;
-                        while ((uint32_t)(s_tab[h] >> 32) != j) h = (h + 1) & (HS - 1);
-                        s_tab[h] = SQB_EMPTY64;
-                    }
-                }
+                for (int k = 0; k < V; ++k)
+                    if ((insmask >> k) & 1u) s_tab[slotv[k]] = SQB_EMPTY64;
                 SQB_CONVERGE();
                 __syncthreads();
                 if (tid == 0) s_misc[1] = 0;  // next writers come after the next window's barriers
