@@ -212,6 +212,12 @@ def bench_moran(ctx, rank, ws, steps, warmup, flush):
     _barrier_sync(ws)
     launches = ctx.launches - l0
     ms = _max_over_ranks(tot / steps, ws)
+    ctx.profile(True)
+    ctx.profile_reset()
+    plan.run_async("moran")
+    ctx.sync()
+    kms = {k: ctx.profile_get(k)[0] for k in ("autocorr_prep", "autocorr_main", "autocorr_final")}
+    ctx.profile(False)
     nnz_x = x.nnz
     algo_bytes = 8 * nnz_x + 8 * (hi - lo + 1) + 8 * g.nnz + 4 * (n + 1) + 8 * (hi - lo)
     peak, _ = _peaks()
@@ -221,7 +227,8 @@ def bench_moran(ctx, rank, ws, steps, warmup, flush):
                    "d2h_bytes_per_step": int(8 * (hi - lo)), "seconds": t_e2e, "note": "load (H2D + device CSR transposition) + run + download, pageable scipy buffers"},
            "roofline": {"bound": "hbm", "achieved": algo_bytes / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": algo_bytes / (ms / 1e3) / 1e9 / peak,
                         "algorithmic_bytes_per_step": int(algo_bytes)},
-           "finite_scores": int(np.isfinite(score).sum()), "max_I": float(np.nanmax(score)), "gpu_launches": int(launches), "synth_seconds": t_gen}
+           "finite_scores": int(np.isfinite(score).sum()), "max_I": float(np.nanmax(score)), "gpu_launches": int(launches), "synth_seconds": t_gen,
+           "kernel_ms": kms}
     if rank == 0:
         try:
             from oracle import ref
@@ -298,7 +305,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--perms", type=int, default=CFG2["n_perms"])
     ap.add_argument("--shuffle-threads", type=int, default=0)
-    ap.add_argument("--shuffle-algo", type=int, default=2)
+    ap.add_argument("--shuffle-algo", type=int, default=-1)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 

@@ -100,9 +100,12 @@ int sqb_nhood_permute_download(sqb_nhood* h, uint32_t* out_counts);
  * (original node order), out: (p1-p0) x n uint32.                                                        */
 int sqb_nhood_shuffled_labels(sqb_nhood* h, int64_t p0, int64_t p1, uint32_t* out);
 
-/* Tuning / test options.  key: "shuffle_algo" (0 = one thread per permutation, serial replay; 1 = CTA-parallel
- * replay, default), "shuffle_threads" (256/512/1024), "perm_chunk" (permutations resident at once),
- * "count_algo" (0 auto, 1 shared-memory lane-private histograms, 2 global atomics).                       */
+/* Tuning / test options.  key: "shuffle_algo" (-1 auto [default]; 0 one thread per permutation, serial replay;
+ * 1 CTA per permutation; 2 warp per permutation; 3 CTA per permutation with large windows), "shuffle_threads"
+ * (128/256/512/1024, algos 1 and 3), "shuffle_q" (1/2/4, algo 2), "shuffle_r" (2/4/8, algo 3), "shuffle_ctas"
+ * (persistent grid size, 0 = auto), "shuffle_wfactor_x100" (window = min(i/4, f*sqrt(i)) raw values),
+ * "perm_chunk" (permutations resident at once), "count_algo" (0 auto, 1 shared-memory histograms, 2 global atomics).
+ * All variants produce bit-identical results.                                                              */
 int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value);
 /* algorithmic bytes per permutation, SURVEY.md 8(d): 4*nnz + 4*(n+1) + 8*n + 4*n_cls^2                   */
 int sqb_nhood_bytes_per_perm(sqb_nhood* h, int64_t* bytes);

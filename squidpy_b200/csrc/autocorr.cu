@@ -14,28 +14,34 @@
 #define TILE 32
 
 // ---- CSR by feature -> dense tile ------------------------------------------------------------------
-// one warp per feature of the super-tile: scatter the feature's non-zeros into D[tile][obs][lane] and reduce its
-// sum (for the mean) in a fixed order.
+// one CTA (256 threads) per feature of the super-tile: scatter the feature's non-zeros into D[tile][obs][lane] and
+// reduce its sum (for the mean) in a fixed order (per-thread strided partial, warp shuffle tree, then warp 0).
 template <typename XT>
-__global__ void ac_scatter_kernel(const int64_t* __restrict__ xp, const int32_t* __restrict__ xi,
-                                  const XT* __restrict__ xv, int64_t g0, int64_t n_feat, int64_t n, XT* __restrict__ D,
-                                  double* __restrict__ sums) {
-    const int lane = threadIdx.x & 31;
-    const int64_t wglobal = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+__global__ void __launch_bounds__(256) ac_scatter_kernel(const int64_t* __restrict__ xp, const int32_t* __restrict__ xi,
+                                                         const XT* __restrict__ xv, int64_t g0, int64_t n_feat, int64_t n,
+                                                         XT* __restrict__ D, double* __restrict__ sums) {
+    __shared__ double s_part[8];
+    const int64_t wglobal = blockIdx.x;  // feature index inside the super-tile
     const int64_t g = g0 + wglobal;
     if (g >= n_feat) return;
     const int64_t tile = wglobal / TILE;
     const int t = (int)(wglobal % TILE);
     XT* __restrict__ Dt = D + tile * n * TILE;
     double s = 0.0;
-    for (int64_t e = xp[g] + lane; e < xp[g + 1]; e += 32) {
+    for (int64_t e = xp[g] + threadIdx.x; e < xp[g + 1]; e += 256) {
         const XT v = xv[e];
         Dt[(int64_t)xi[e] * TILE + t] = v;
         s += (double)v;
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if (lane == 0) sums[wglobal] = s;
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; ++w) tot += s_part[w];
+        sums[wglobal] = tot;
+    }
 }
 
 // ---- dense features x obs (row-major) -> dense tile (transpose through shared memory) -------------------
@@ -128,21 +134,50 @@ __global__ void __launch_bounds__(256) ac_main_kernel(const int32_t* __restrict_
             den = fma(zr, zr, den);
         }
     }
-    pnum[(tl * nw + w) * TILE + lane] = num;
-    pden[(tl * nw + w) * TILE + lane] = den;
+    // fixed-order combine of the 8 warps of this CTA -> one partial per (tile, CTA)
+    __shared__ double s_num[8][TILE], s_den[8][TILE];
+    s_num[threadIdx.x >> 5][lane] = num;
+    s_den[threadIdx.x >> 5][lane] = den;
+    __syncthreads();
+    if (threadIdx.x < TILE) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a += s_num[k][lane];
+            b += s_den[k][lane];
+        }
+        pnum[(tl * gridDim.x + blockIdx.x) * TILE + lane] = a;
+        pden[(tl * gridDim.x + blockIdx.x) * TILE + lane] = b;
+    }
 }
 
 template <int MODE>
-__global__ void ac_final_kernel(const double* __restrict__ pnum, const double* __restrict__ pden, int64_t nw, int64_t n,
-                                double s0, int64_t g0, int64_t n_feat, double* __restrict__ out) {
-    const int lane = threadIdx.x;
+__global__ void __launch_bounds__(256) ac_final_kernel(const double* __restrict__ pnum, const double* __restrict__ pden,
+                                                       int64_t nparts, int64_t n, double s0, int64_t g0, int64_t n_feat,
+                                                       double* __restrict__ out) {
+    // 8 warps sum contiguous ranges of the per-CTA partials (lane = feature), then warp 0 combines them in order
+    __shared__ double s_num[8][TILE], s_den[8][TILE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t tl = blockIdx.x;
-    const int64_t g = g0 + tl * TILE + lane;
-    if (g >= n_feat) return;
+    const int64_t chunk = (nparts + 7) / 8;
+    int64_t p0 = warp * chunk, p1 = p0 + chunk;
+    if (p1 > nparts) p1 = nparts;
     double num = 0.0, den = 0.0;
-    for (int64_t w = 0; w < nw; ++w) {
-        num += pnum[(tl * nw + w) * TILE + lane];
-        den += pden[(tl * nw + w) * TILE + lane];
+    for (int64_t w = p0; w < p1; ++w) {
+        num += pnum[(tl * nparts + w) * TILE + lane];
+        den += pden[(tl * nparts + w) * TILE + lane];
+    }
+    s_num[warp][lane] = num;
+    s_den[warp][lane] = den;
+    __syncthreads();
+    const int64_t g = g0 + tl * TILE + lane;
+    if (warp != 0 || g >= n_feat) return;
+    num = 0.0;
+    den = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        num += s_num[k][lane];
+        den += s_den[k][lane];
     }
     double r;
     if (den == 0.0) {
@@ -193,7 +228,7 @@ struct sqb_autocorr {
     DevBuf<uint8_t> d_tile;
     DevBuf<double> d_sums, d_partial, d_pnum, d_pden, d_out;
     DevBuf<int64_t> d_perm;
-    int tiles_per_launch = 2;
+    int tiles_per_launch = 8;  // 256 features per launch: enough CTAs to fill 148 SMs in every phase
     bool ran = false;
 };
 
@@ -203,8 +238,8 @@ template <typename XT>
 static int ac_run_typed(sqb_autocorr* h, int mode, const int64_t* d_perm) {
     sqb_ctx* c = h->ctx;
     const int64_t n = h->n, G = h->n_feat;
-    const int TPL = h->tiles_per_launch;
     const int64_t ntiles = ceil_div64(G, TILE);
+    const int TPL = (int)(ntiles < h->tiles_per_launch ? ntiles : h->tiles_per_launch);
     // warps: contiguous observation ranges, >= 32 observations per warp
     int64_t ctas = (int64_t)c->sm_count * 4;
     int64_t nw = ctas * 8;
@@ -239,9 +274,8 @@ static int ac_run_typed(sqb_autocorr* h, int mode, const int64_t* d_perm) {
         if (h->kind == 3) {
             SQB_CUDA(cudaMemsetAsync(Dbuf, 0, (size_t)nt * n * TILE * sizeof(XT), c->stream));
             SqbLaunchScope scope(c, SQB_K_AUTOCORR_PREP);
-            const int64_t warps = (int64_t)nt * TILE;
-            ac_scatter_kernel<XT><<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, c->stream>>>(
-                h->d_xp.p, h->d_xi.p, X, g0, G, n, Dbuf, h->d_sums.p);
+            ac_scatter_kernel<XT><<<(unsigned)(nt * TILE), 256, 0, c->stream>>>(h->d_xp.p, h->d_xi.p, X, g0, G, n, Dbuf,
+                                                                                  h->d_sums.p);
             SQB_POST_LAUNCH();
         } else {
             if (h->kind == 1) {
@@ -278,9 +312,9 @@ static int ac_run_typed(sqb_autocorr* h, int mode, const int64_t* d_perm) {
         {
             SqbLaunchScope scope(c, SQB_K_AUTOCORR_FINAL);
             if (mode == 0)
-                ac_final_kernel<0><<<nt, 32, 0, c->stream>>>(h->d_pnum.p, h->d_pden.p, nw, n, h->s0, g0, G, h->d_out.p);
+                ac_final_kernel<0><<<nt, 256, 0, c->stream>>>(h->d_pnum.p, h->d_pden.p, ctas, n, h->s0, g0, G, h->d_out.p);
             else
-                ac_final_kernel<1><<<nt, 32, 0, c->stream>>>(h->d_pnum.p, h->d_pden.p, nw, n, h->s0, g0, G, h->d_out.p);
+                ac_final_kernel<1><<<nt, 256, 0, c->stream>>>(h->d_pnum.p, h->d_pden.p, ctas, n, h->s0, g0, G, h->d_out.p);
             SQB_POST_LAUNCH();
         }
     }

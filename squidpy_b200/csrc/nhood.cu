@@ -1090,7 +1090,8 @@ struct sqb_nhood {
     DevBuf<uint32_t> d_tmp_u32;
     std::vector<uint32_t> h_order;
     // options
-    int shuffle_algo = 2;  // 0 serial thread-per-permutation, 1 CTA per permutation, 2 warp per permutation (default)
+    int shuffle_algo = -1;  // -1 auto (1 for few permutations, else 2); 0 serial thread per permutation (cross-check);
+                            // 1 CTA per permutation; 2 warp per permutation; 3 CTA per permutation, large windows
     int shuffle_q = 4;     // algo 2: PCG64 outputs per lane per batch (window = 64*q raw values)
     int shuffle_r = 4;     // algo 3: PCG64 outputs per thread per batch (window = 2*r*threads raw values)
     int shuffle_threads = 512;
@@ -1197,10 +1198,14 @@ template <typename LT>
 static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np) {
     sqb_ctx* c = h->ctx;
     SqbLaunchScope scope(c, SQB_K_NHOOD_SHUFFLE);
-    if (h->shuffle_algo == 0) {
+    // auto: every variant is bound by the per-permutation dependency chain, not by HBM or issue slots (ncu), so with few
+    // permutations the CTA version (one permutation finishes sooner) wins, with many the warp version (3-4x fewer
+    // instructions per step, thousands of permutations in flight) does
+    const int algo = h->shuffle_algo >= 0 ? h->shuffle_algo : (np <= 2 * (int64_t)c->sm_count ? 1 : 2);
+    if (algo == 0) {
         nhood_shuffle_serial_kernel<LT><<<(unsigned)ceil_div64(np, 32), 32, 0, c->stream>>>(
             lab, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p);
-    } else if (h->shuffle_algo == 3) {
+    } else if (algo == 3) {
         int rc = SQB_ERR_INVALID;
         const int nt = h->shuffle_threads, r = h->shuffle_r;
         if (nt == 512 && r == 4) rc = launch_shuffle_cta2<LT, 512, 4>(h, lab, states, np);
@@ -1212,7 +1217,7 @@ static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t
         else if (nt == 128 && r == 4) rc = launch_shuffle_cta2<LT, 128, 4>(h, lab, states, np);
         else sqb_set_error("shuffle_algo 3: unsupported (shuffle_threads, shuffle_r) = (%d, %d)", nt, r);
         SQB_TRY(rc);
-    } else if (h->shuffle_algo == 2) {
+    } else if (algo == 2) {
         const float wf = (float)h->shuffle_wfactor_x100 / 100.0f;
         int64_t ctas = h->shuffle_ctas > 0 ? h->shuffle_ctas : (int64_t)c->sm_count * 8;
         if (ctas > ceil_div64(np, 4)) ctas = ceil_div64(np, 4);
@@ -1354,7 +1359,7 @@ int sqb_nhood_destroy(sqb_nhood* h) {
 int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value) {
     SQB_CHECK(h && key, SQB_ERR_INVALID, "sqb_nhood_set_option: null argument");
     if (!strcmp(key, "shuffle_algo")) {
-        SQB_CHECK(value >= 0 && value <= 3, SQB_ERR_INVALID, "shuffle_algo must be 0, 1, 2 or 3");
+        SQB_CHECK(value >= -1 && value <= 3, SQB_ERR_INVALID, "shuffle_algo must be -1 (auto), 0, 1, 2 or 3");
         h->shuffle_algo = (int)value;
     } else if (!strcmp(key, "shuffle_r")) {
         SQB_CHECK(value == 2 || value == 4 || value == 8, SQB_ERR_INVALID, "shuffle_r must be 2, 4 or 8");
