@@ -65,6 +65,9 @@ int sqb_ctx_destroy(sqb_ctx* c) {
     cudaSetDevice(c->device);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->scratch[0].release();
+    c->scratch[1].release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return SQB_OK;

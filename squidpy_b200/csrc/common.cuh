@@ -54,18 +54,7 @@ enum {
     SQB_K_NCLASS = 16
 };
 
-struct sqb_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    int sm_count = 148;
-    size_t smem_optin = 0;   // max opt-in dynamic shared memory per block
-    int64_t launches = 0;
-    bool profile = false;
-    double k_ms[SQB_K_NCLASS] = {0};
-    int64_t k_n[SQB_K_NCLASS] = {0};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-};
+struct sqb_ctx;
 
 // RAII-less device buffer helper (explicit free; all allocations are synchronous cudaMalloc)
 template <typename T>
@@ -91,6 +80,22 @@ struct DevBuf {
         p = nullptr;
         n = 0;
     }
+};
+
+struct sqb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    size_t smem_optin = 0;   // max opt-in dynamic shared memory per block
+    int64_t launches = 0;
+    bool profile = false;
+    double k_ms[SQB_K_NCLASS] = {0};
+    int64_t k_n[SQB_K_NCLASS] = {0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // Large scratch buffers that live as long as the context (GB-sized cudaMalloc/cudaFree per API call would
+    // otherwise dominate the host-facing latency).  Work on one ctx is stream ordered, so handles can share them.
+    DevBuf<uint8_t> scratch[2];
 };
 
 // Launch accounting.  In profile mode each launch is bracketed by events on the ctx stream and the elapsed

@@ -902,6 +902,289 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2e. TWO-WARP PIPELINE per permutation.  ncu: 2c spends ~9 500 cycles per 192-step window in ONE dependent chain
+//     (PCG64 multiply-adds -> ballots/prefix -> hash inserts -> global loads -> stores) at IPC ~0.12, with HBM and the
+//     issue slots mostly idle.  The first half of that chain (RNG + rejection sampling) depends on nothing but the
+//     generator, so it is split off: the PRODUCER warp turns the PCG64 stream into lists of swap targets (one list
+//     per window) in a shared-memory ring, the CONSUMER warp applies the swaps of one window while the producer is
+//     already several windows ahead.  Hand-off with sequence counters in shared memory (one writer each).
+// ------------------------------------------------------------------------------------------------
+#define PIPE_RAW 256     // raw values per batch (Q = 4 outputs per lane)
+#define PIPE_NSLOT 4     // ring depth
+#define PIPE_HS 1024     // hash slots per team
+#define PIPE_TEAMS 2     // teams (producer + consumer warp) per CTA
+
+struct PipeSlot {
+    int S;         // number of steps; -1 = end of permutation
+    int i_cur;     // step s swaps positions base + i_cur - s and base + j[s]
+    long long base;
+    uint32_t j[PIPE_RAW];
+};
+
+template <typename LT>
+__global__ void __launch_bounds__(PIPE_TEAMS * 64) nhood_shuffle_pipe_kernel(LT* __restrict__ labels, int64_t stride,
+                                                                             const uint64_t* __restrict__ states,
+                                                                             int64_t n_perms, int nseg,
+                                                                             const int64_t* __restrict__ seg_start,
+                                                                             const int64_t* __restrict__ seg_len,
+                                                                             float wfactor) {
+    constexpr int Q = 4, RAW = PIPE_RAW, HS = PIPE_HS, HS_SHIFT = 22;
+    __shared__ PipeSlot s_slot_all[PIPE_TEAMS][PIPE_NSLOT];
+    __shared__ unsigned long long s_tab_all[PIPE_TEAMS][HS];
+    __shared__ uint32_t s_flag_all[PIPE_TEAMS][RAW / 32];
+    __shared__ unsigned s_full_all[PIPE_TEAMS][PIPE_NSLOT], s_empty_all[PIPE_TEAMS][PIPE_NSLOT];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int team = warp >> 1, role = warp & 1;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    PipeSlot* slots = s_slot_all[team];
+    unsigned long long* s_tab = s_tab_all[team];
+    uint32_t* s_flag = s_flag_all[team];
+    volatile unsigned* s_full = s_full_all[team];
+    volatile unsigned* s_empty = s_empty_all[team];
+    if (role == 0) {
+        for (int h = lane; h < HS; h += 32) s_tab[h] = SQB_EMPTY64;
+        if (lane < RAW / 32) s_flag[lane] = 0;
+        if (lane < PIPE_NSLOT) {
+            s_full[lane] = 0;
+            s_empty[lane] = 0;
+        }
+    }
+    __syncthreads();
+
+    const int64_t teams_total = (int64_t)gridDim.x * PIPE_TEAMS;
+    const int64_t team_id = (int64_t)blockIdx.x * PIPE_TEAMS + team;
+    unsigned w = 0;  // window counter of this team (same sequence in both warps)
+
+    if (role == 0) {
+        // ================= PRODUCER: PCG64 stream -> per-window target lists =================
+        u128 M32, C32, Mt, Ct;
+        pcg_jump_consts(32, M32, C32);
+        pcg_jump_consts((uint64_t)lane + 1, Mt, Ct);
+        for (int64_t perm = team_id; perm < n_perms; perm += teams_total) {
+            const uint64_t* st4 = states + perm * 4;
+            const u128 inc = mk128(st4[2], st4[3]);
+            u128 st = Mt * mk128(st4[0], st4[1]) + Ct * inc;
+            const u128 C32_inc = C32 * inc;
+            uint32_t raw[2 * Q];
+#pragma unroll
+            for (int k = 0; k < 2 * Q; ++k) raw[k] = 0;
+            int pos = RAW;
+            for (int seg = 0; seg <= nseg; ++seg) {
+                const bool last = (seg == nseg);
+                const long long base = last ? 0 : seg_start[seg];
+                int i_cur = last ? 0 : (int)(seg_len[seg] - 1);
+                while (last || i_cur >= 1) {
+                    int S = -1, newpos = pos;
+                    uint32_t u[2 * Q];
+                    bool F[2 * Q];
+                    int c[2 * Q];
+#pragma unroll
+                    for (int k = 0; k < 2 * Q; ++k) {
+                        u[k] = 0;
+                        F[k] = false;
+                        c[k] = 0;
+                    }
+                    if (!last) {
+                        if (pos >= RAW) {
+#pragma unroll
+                            for (int q = 0; q < Q; ++q) {
+                                const uint64_t o = pcg_output(st);
+                                st = M32 * st + C32_inc;
+                                raw[2 * q] = (uint32_t)o;
+                                raw[2 * q + 1] = (uint32_t)(o >> 32);
+                            }
+                            pos = 0;
+                        }
+                        const uint32_t mask = 0xFFFFFFFFu >> __clz(i_cur);
+                        const int i_lo = (int)(mask >> 1) + 1;
+                        const int n_ph = i_cur - i_lo + 1;
+                        const int K = sqb_window_size((int64_t)i_cur, RAW - pos, RAW, wfactor);
+                        bool inw[2 * Q];
+#pragma unroll
+                        for (int k = 0; k < 2 * Q; ++k) {
+                            const int r = (k >> 1) * 64 + 2 * lane + (k & 1);
+                            inw[k] = (r >= pos) && (r < pos + K);
+                            u[k] = raw[k] & mask;
+                            F[k] = inw[k] && (u[k] <= (uint32_t)i_cur);
+                        }
+                        int total = 0;
+                        while (true) {
+                            int run = 0;
+#pragma unroll
+                            for (int q = 0; q < Q; ++q) {
+                                const uint32_t blo = __ballot_sync(0xffffffffu, F[2 * q]);
+                                const uint32_t bhi = __ballot_sync(0xffffffffu, F[2 * q + 1]);
+                                c[2 * q] = run + __popc(blo & lt_mask) + __popc(bhi & lt_mask);
+                                c[2 * q + 1] = c[2 * q] + (F[2 * q] ? 1 : 0);
+                                run += __popc(blo) + __popc(bhi);
+                            }
+                            total = run;
+                            bool changed = false;
+#pragma unroll
+                            for (int k = 0; k < 2 * Q; ++k) {
+                                const bool nf = inw[k] && ((int)u[k] <= i_cur - c[k]) && (u[k] <= (uint32_t)i_cur);
+                                changed |= (nf != F[k]);
+                                F[k] = nf;
+                            }
+                            if (!__any_sync(0xffffffffu, changed)) break;
+                        }
+                        if (total >= n_ph) {
+                            S = n_ph;
+                            int myr = -1;
+#pragma unroll
+                            for (int k = 0; k < 2 * Q; ++k)
+                                if (F[k] && c[k] == S - 1) myr = (k >> 1) * 64 + 2 * lane + (k & 1);
+                            const uint32_t who = __ballot_sync(0xffffffffu, myr >= 0);
+                            newpos = __shfl_sync(0xffffffffu, myr, __ffs(who) - 1) + 1;
+                        } else {
+                            S = total;
+                            newpos = pos + K;
+                        }
+                    }
+                    if (last || S > 0) {
+                        // hand the window over: wait for the ring slot, fill it, publish
+                        const int slot = (int)(w % PIPE_NSLOT);
+                        const unsigned gen = w / PIPE_NSLOT;
+                        if (lane == 0)
+                            while (s_empty[slot] != gen) {
+                            }
+                        __syncwarp();
+                        PipeSlot* sl = &slots[slot];
+#pragma unroll
+                        for (int k = 0; k < 2 * Q; ++k)
+                            if (F[k] && c[k] < S) sl->j[c[k]] = u[k];
+                        if (lane == 0) {
+                            sl->S = S;
+                            sl->i_cur = i_cur;
+                            sl->base = base;
+                        }
+                        __threadfence_block();
+                        __syncwarp();
+                        if (lane == 0) s_full[slot] = gen + 1;
+                        ++w;
+                    }
+                    if (last) break;
+                    i_cur -= S;
+                    pos = newpos;
+                }
+            }
+        }
+    } else {
+        // ================= CONSUMER: apply the swaps of one window at a time =================
+        for (int64_t perm = team_id; perm < n_perms; perm += teams_total) {
+            LT* __restrict__ a = labels + perm * stride;
+            while (true) {
+                const int slot = (int)(w % PIPE_NSLOT);
+                const unsigned gen = w / PIPE_NSLOT;
+                if (lane == 0)
+                    while (s_full[slot] != gen + 1) {
+                    }
+                __syncwarp();
+                const PipeSlot* sl = &slots[slot];
+                const int S = sl->S;
+                const int i_cur = sl->i_cur;
+                const long long base = sl->base;
+                if (S > 0) {
+                    const int own_lo = i_cur - S;
+                    uint32_t jv[2 * Q];
+                    uint32_t actm = 0, insm = 0;
+                    int slotv[2 * Q];
+#pragma unroll
+                    for (int t = 0; t < 2 * Q; ++t) {
+                        const int s = lane + 32 * t;
+                        jv[t] = 0;
+                        slotv[t] = 0;
+                        if (s < S) {
+                            const uint32_t j = sl->j[s];
+                            jv[t] = j;
+                            if ((int)j > own_lo) {
+                                const int s2 = i_cur - (int)j;
+                                if (s2 != s) {
+                                    actm |= 1u << t;
+                                    atomicOr(&s_flag[s >> 5], 1u << (s & 31));
+                                    atomicOr(&s_flag[s2 >> 5], 1u << (s2 & 31));
+                                }
+                            } else {
+                                actm |= 1u << t;
+                                uint32_t h = (j * 2654435761u) >> HS_SHIFT;
+                                const unsigned long long mine = ((unsigned long long)j << 32) | (unsigned)s;
+                                while (true) {
+                                    const unsigned long long prev = atomicCAS(&s_tab[h], SQB_EMPTY64, mine);
+                                    if (prev == SQB_EMPTY64) {
+                                        insm |= 1u << t;
+                                        slotv[t] = (int)h;
+                                        break;
+                                    }
+                                    if ((uint32_t)(prev >> 32) == j) {
+                                        const int so = (int)(uint32_t)prev;
+                                        atomicOr(&s_flag[s >> 5], 1u << (s & 31));
+                                        atomicOr(&s_flag[so >> 5], 1u << (so & 31));
+                                        break;
+                                    }
+                                    h = (h + 1) & (HS - 1);
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    // conflict-free swaps straight on global memory: all loads, then all stores (branch-free)
+                    LT vi[2 * Q], vj[2 * Q];
+                    uint32_t dirm = 0;
+#pragma unroll
+                    for (int t = 0; t < 2 * Q; ++t) {
+                        const int s = lane + 32 * t;
+                        const bool act = (actm >> t) & 1u;
+                        const int ss = act ? s : 0;
+                        const bool dir = act && !((s_flag[ss >> 5] >> (ss & 31)) & 1u);
+                        dirm |= (dir ? 1u : 0u) << t;
+                        vi[t] = dir ? ld_cg<LT>(a + base + (i_cur - ss)) : (LT)0;
+                        vj[t] = dir ? ld_cg<LT>(a + base + (long long)jv[t]) : (LT)0;
+                    }
+#pragma unroll
+                    for (int t = 0; t < 2 * Q; ++t) {
+                        const int s = lane + 32 * t;
+                        const bool dir = (dirm >> t) & 1u;
+                        const int ss = dir ? s : 0;
+                        if (dir) a[base + (i_cur - ss)] = vj[t];
+                        if (dir) a[base + (long long)jv[t]] = vi[t];
+                    }
+                    // conflicting swaps in step order (disjoint from the set above), lane 0, on global memory
+                    const uint32_t fw = (lane < RAW / 32) ? s_flag[lane] : 0u;
+                    if (__ballot_sync(0xffffffffu, fw != 0u)) {
+                        if (lane == 0) {
+                            for (int wd = 0; wd < RAW / 32; ++wd) {
+                                uint32_t bits = s_flag[wd];
+                                while (bits) {
+                                    const int b = __ffs(bits) - 1;
+                                    bits &= bits - 1;
+                                    const int s = wd * 32 + b;
+                                    const long long pi = base + (i_cur - s), pj = base + (long long)sl->j[s];
+                                    const LT x = ld_cg<LT>(a + pi), y = ld_cg<LT>(a + pj);
+                                    a[pi] = y;
+                                    a[pj] = x;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (lane < RAW / 32) s_flag[lane] = 0;
+                    }
+#pragma unroll
+                    for (int t = 0; t < 2 * Q; ++t)
+                        if ((insm >> t) & 1u) s_tab[slotv[t]] = SQB_EMPTY64;
+                }
+                // release the slot (also orders this window's global stores before the next window's loads)
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) s_empty[slot] = gen + 1;
+                ++w;
+                if (S < 0) break;  // end of this permutation
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 3. transpose [P][stride] -> [n][PB]  (32 permutations x 256 nodes per CTA), optional row scatter through
 //    `order` (library-grouped position k -> original node id)
 // ------------------------------------------------------------------------------------------------
@@ -1084,8 +1367,7 @@ struct sqb_nhood {
     DevBuf<uint64_t> d_states;  // P x 4
     int64_t n_perms = 0;
     bool uploaded = false, ran = false;
-    DevBuf<uint8_t> d_lab;   // [chunk][stride] LT
-    DevBuf<uint8_t> d_labT;  // [n][PB] LT
+    // label matrices [chunk][stride] and [n][PB] live in ctx->scratch[0..1]
     DevBuf<uint32_t> d_counts;  // [P][C*C]
     DevBuf<uint32_t> d_tmp_u32;
     std::vector<uint32_t> h_order;
@@ -1217,6 +1499,11 @@ static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t
         else if (nt == 128 && r == 4) rc = launch_shuffle_cta2<LT, 128, 4>(h, lab, states, np);
         else sqb_set_error("shuffle_algo 3: unsupported (shuffle_threads, shuffle_r) = (%d, %d)", nt, r);
         SQB_TRY(rc);
+    } else if (algo == 4) {
+        int64_t ctas = h->shuffle_ctas > 0 ? h->shuffle_ctas : (int64_t)c->sm_count * 6;
+        if (ctas > ceil_div64(np, PIPE_TEAMS)) ctas = ceil_div64(np, PIPE_TEAMS);
+        nhood_shuffle_pipe_kernel<LT><<<(unsigned)ctas, PIPE_TEAMS * 64, 0, c->stream>>>(
+            lab, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, (float)h->shuffle_wfactor_x100 / 100.0f);
     } else if (algo == 2) {
         const float wf = (float)h->shuffle_wfactor_x100 / 100.0f;
         int64_t ctas = h->shuffle_ctas > 0 ? h->shuffle_ctas : (int64_t)c->sm_count * 8;
@@ -1268,8 +1555,8 @@ static int64_t auto_chunk(sqb_nhood* h) {
 template <typename LT>
 static int run_chunk(sqb_nhood* h, int64_t p0, int64_t np, bool do_count) {
     sqb_ctx* c = h->ctx;
-    LT* lab = reinterpret_cast<LT*>(h->d_lab.p);
-    LT* labT = reinterpret_cast<LT*>(h->d_labT.p);
+    LT* lab = reinterpret_cast<LT*>(c->scratch[0].p);
+    LT* labT = reinterpret_cast<LT*>(c->scratch[1].p);
     const int64_t vec_per_row = h->stride * (int64_t)sizeof(LT) / 16;
     {
         SqbLaunchScope scope(c, SQB_K_NHOOD_FILL);
@@ -1297,8 +1584,8 @@ static int run_chunk(sqb_nhood* h, int64_t p0, int64_t np, bool do_count) {
 }
 
 static int ensure_buffers(sqb_nhood* h, int64_t chunk) {
-    SQB_TRY(h->d_lab.alloc((size_t)chunk * h->stride * h->lt_bytes));
-    SQB_TRY(h->d_labT.alloc((size_t)h->n * chunk * h->lt_bytes));
+    SQB_TRY(h->ctx->scratch[0].alloc((size_t)chunk * h->stride * h->lt_bytes));
+    SQB_TRY(h->ctx->scratch[1].alloc((size_t)h->n * chunk * h->lt_bytes));
     return SQB_OK;
 }
 
@@ -1348,8 +1635,6 @@ int sqb_nhood_destroy(sqb_nhood* h) {
     h->d_seg_start.release();
     h->d_seg_len.release();
     h->d_states.release();
-    h->d_lab.release();
-    h->d_labT.release();
     h->d_counts.release();
     h->d_tmp_u32.release();
     delete h;
@@ -1359,7 +1644,7 @@ int sqb_nhood_destroy(sqb_nhood* h) {
 int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value) {
     SQB_CHECK(h && key, SQB_ERR_INVALID, "sqb_nhood_set_option: null argument");
     if (!strcmp(key, "shuffle_algo")) {
-        SQB_CHECK(value >= -1 && value <= 3, SQB_ERR_INVALID, "shuffle_algo must be -1 (auto), 0, 1, 2 or 3");
+        SQB_CHECK(value >= -1 && value <= 4, SQB_ERR_INVALID, "shuffle_algo must be -1 (auto), 0, 1, 2, 3 or 4");
         h->shuffle_algo = (int)value;
     } else if (!strcmp(key, "shuffle_r")) {
         SQB_CHECK(value == 2 || value == 4 || value == 8, SQB_ERR_INVALID, "shuffle_r must be 2, 4 or 8");
@@ -1584,7 +1869,7 @@ int sqb_nhood_shuffled_labels(sqb_nhood* h, int64_t p0, int64_t p1, uint32_t* ou
     SQB_CUDA(cudaSetDevice(c->device));
     const size_t row_bytes = (size_t)h->stride * h->lt_bytes;
     int64_t step = auto_chunk(h);
-    const int64_t cap = (int64_t)(h->d_lab.n / row_bytes);
+    const int64_t cap = (int64_t)(c->scratch[0].n / row_bytes);
     if (step > cap) step = cap;
     SQB_CHECK(step >= 1, SQB_ERR_STATE, "sqb_nhood_shuffled_labels: label buffer not allocated");
     std::vector<uint8_t> host(row_bytes);
@@ -1595,7 +1880,7 @@ int sqb_nhood_shuffled_labels(sqb_nhood* h, int64_t p0, int64_t p1, uint32_t* ou
         else
             SQB_TRY(run_chunk<uint16_t>(h, q0, np, false));
         for (int64_t p = 0; p < np; ++p) {
-            SQB_CUDA(cudaMemcpyAsync(host.data(), h->d_lab.p + (size_t)p * row_bytes, row_bytes, cudaMemcpyDeviceToHost,
+            SQB_CUDA(cudaMemcpyAsync(host.data(), c->scratch[0].p + (size_t)p * row_bytes, row_bytes, cudaMemcpyDeviceToHost,
                                      c->stream));
             SQB_CUDA(cudaStreamSynchronize(c->stream));
             uint32_t* row = out + (size_t)(q0 - p0 + p) * h->n;

@@ -28,7 +28,7 @@ for st in $STAGES; do
       timeout 900 python tools/tune_nhood.py 1000 > $OUT/tune_nhood.log 2>&1; echo "tune rc=$?" | tee -a $OUT/summary.txt
       cat $OUT/tune_nhood.log | tail -40 ;;
     ncufull)
-      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"nhood_shuffle_cta2|nhood_count_kernel" -c 2 -f -o $OUT/prof_nhood python bench.py --steps 1 --warmup 0 --perms 592 --skip-cpu --skip-moran --shuffle-algo 3 > $OUT/ncu_full.log 2>&1; echo "ncu-full rc=$?" | tee -a $OUT/summary.txt ;;
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"nhood_shuffle_pipe|nhood_count_kernel" -c 2 -f -o $OUT/prof_nhood python bench.py --steps 1 --warmup 0 --perms 592 --skip-cpu --skip-moran --shuffle-algo 4 > $OUT/ncu_full.log 2>&1; echo "ncu-full rc=$?" | tee -a $OUT/summary.txt ;;
   esac
 done
 cat $OUT/summary.txt

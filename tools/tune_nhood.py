@@ -35,12 +35,10 @@ def main():
     ctx.profile(True)
     variants = [dict(shuffle_algo=1, shuffle_threads=512, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_r=4),
                 dict(shuffle_algo=2, shuffle_threads=512, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_r=4)]
-    for nt, r in ((256, 4), (512, 2), (512, 4), (1024, 2), (256, 8), (1024, 4), (128, 4)):
-        for wf in (400, 800):
-            variants.append(dict(shuffle_algo=3, shuffle_threads=nt, shuffle_r=r, shuffle_ctas=0, shuffle_wfactor_x100=wf, shuffle_q=4))
-    for wf in (200, 600, 1200, 1600):
-        variants.append(dict(shuffle_algo=3, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=wf, shuffle_q=4))
-        variants.append(dict(shuffle_algo=3, shuffle_threads=256, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=wf, shuffle_q=4))
+    for ctas in (0, 74, 148, 222, 296):
+        variants.append(dict(shuffle_algo=4, shuffle_threads=512, shuffle_r=4, shuffle_ctas=ctas, shuffle_wfactor_x100=400, shuffle_q=4))
+    for wf in (100, 200, 800):
+        variants.append(dict(shuffle_algo=4, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=wf, shuffle_q=4))
     for v in variants:
         for k, val in v.items():
             plan.set_option(k, val)
