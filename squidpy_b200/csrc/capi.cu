@@ -1,5 +1,6 @@
 // capi.cu — context management and error plumbing of the C ABI (include/squidpy_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -56,6 +57,16 @@ int sqb_ctx_create(int device, void* stream, sqb_ctx** out) {
     }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+    // The shuffle kernels are bound by RANDOM 1-byte accesses into per-permutation label arrays (ncu: ~1.9 DRAM read
+    // sectors per random load with the default 64-byte L2 fetch granularity).  32-byte granularity halves that; the
+    // streaming kernels of this library read whole sectors anyway.  SQB_L2_FETCH=64|128 restores another value.
+    {
+        size_t gran = 32;
+        const char* env = getenv("SQB_L2_FETCH");
+        if (env && atoi(env) > 0) gran = (size_t)atoi(env);
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
     *out = c;
     return SQB_OK;
 }

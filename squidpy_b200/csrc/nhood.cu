@@ -579,14 +579,14 @@ __global__ void __launch_bounds__(128) nhood_shuffle_warp_kernel(LT* __restrict_
                     for (int k = 0; k < 2 * Q; ++k) {
                         if (act[k]) act[k] = !((s_flag[c[k] >> 5] >> (c[k] & 31)) & 1u);
                         if (act[k]) {
-                            vi[k] = ld_cg<LT>(a + base + (i_cur - c[k]));
+                            vi[k] = ld_cs<LT>(a + base + (i_cur - c[k]));
                             vj[k] = ld_cg<LT>(a + base + (int64_t)u[k]);
                         }
                     }
 #pragma unroll
                     for (int k = 0; k < 2 * Q; ++k) {
                         if (act[k]) {
-                            a[base + (i_cur - c[k])] = vj[k];
+                            st_cs<LT>(a + base + (i_cur - c[k]), vj[k]);  // final: evict first
                             a[base + (int64_t)u[k]] = vi[k];
                         }
                     }
@@ -1047,8 +1047,7 @@ __global__ void __launch_bounds__(PIPE_TEAMS * 64) nhood_shuffle_pipe_kernel(LT*
                         const int slot = (int)(w % PIPE_NSLOT);
                         const unsigned gen = w / PIPE_NSLOT;
                         if (lane == 0)
-                            while (s_empty[slot] != gen) {
-                            }
+                            while (s_empty[slot] != gen) __nanosleep(64);
                         __syncwarp();
                         PipeSlot* sl = &slots[slot];
 #pragma unroll
@@ -1078,8 +1077,7 @@ __global__ void __launch_bounds__(PIPE_TEAMS * 64) nhood_shuffle_pipe_kernel(LT*
                 const int slot = (int)(w % PIPE_NSLOT);
                 const unsigned gen = w / PIPE_NSLOT;
                 if (lane == 0)
-                    while (s_full[slot] != gen + 1) {
-                    }
+                    while (s_full[slot] != gen + 1) __nanosleep(32);
                 __syncwarp();
                 const PipeSlot* sl = &slots[slot];
                 const int S = sl->S;
@@ -1138,7 +1136,7 @@ __global__ void __launch_bounds__(PIPE_TEAMS * 64) nhood_shuffle_pipe_kernel(LT*
                         const int ss = act ? s : 0;
                         const bool dir = act && !((s_flag[ss >> 5] >> (ss & 31)) & 1u);
                         dirm |= (dir ? 1u : 0u) << t;
-                        vi[t] = dir ? ld_cg<LT>(a + base + (i_cur - ss)) : (LT)0;
+                        vi[t] = dir ? ld_cs<LT>(a + base + (i_cur - ss)) : (LT)0;
                         vj[t] = dir ? ld_cg<LT>(a + base + (long long)jv[t]) : (LT)0;
                     }
 #pragma unroll
@@ -1146,7 +1144,7 @@ __global__ void __launch_bounds__(PIPE_TEAMS * 64) nhood_shuffle_pipe_kernel(LT*
                         const int s = lane + 32 * t;
                         const bool dir = (dirm >> t) & 1u;
                         const int ss = dir ? s : 0;
-                        if (dir) a[base + (i_cur - ss)] = vj[t];
+                        if (dir) st_cs<LT>(a + base + (i_cur - ss), vj[t]);  // final: evict first
                         if (dir) a[base + (long long)jv[t]] = vi[t];
                     }
                     // conflicting swaps in step order (disjoint from the set above), lane 0, on global memory

@@ -33,12 +33,13 @@ def main():
     ref_counts = plan.download()
     results = []
     ctx.profile(True)
-    variants = [dict(shuffle_algo=1, shuffle_threads=512, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_r=4),
-                dict(shuffle_algo=2, shuffle_threads=512, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_r=4)]
-    for ctas in (0, 74, 148, 222, 296):
+    variants = []
+    for algo in (1, 2, 4):
+        variants.append(dict(shuffle_algo=algo, shuffle_threads=512, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_r=4))
+    for ctas in (148, 222, 296, 370):
         variants.append(dict(shuffle_algo=4, shuffle_threads=512, shuffle_r=4, shuffle_ctas=ctas, shuffle_wfactor_x100=400, shuffle_q=4))
-    for wf in (100, 200, 800):
-        variants.append(dict(shuffle_algo=4, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=wf, shuffle_q=4))
+    variants.append(dict(shuffle_algo=3, shuffle_threads=512, shuffle_r=2, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4))
+    variants.append(dict(shuffle_algo=3, shuffle_threads=128, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4))
     for v in variants:
         for k, val in v.items():
             plan.set_option(k, val)
