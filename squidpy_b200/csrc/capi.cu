@@ -57,15 +57,14 @@ int sqb_ctx_create(int device, void* stream, sqb_ctx** out) {
     }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
-    // The shuffle kernels are bound by RANDOM 1-byte accesses into per-permutation label arrays (ncu: ~1.9 DRAM read
-    // sectors per random load with the default 64-byte L2 fetch granularity).  32-byte granularity halves that; the
-    // streaming kernels of this library read whole sectors anyway.  SQB_L2_FETCH=64|128 restores another value.
+    // Optional L2 fetch granularity override (SQB_L2_FETCH=32|64|128).  Measured on B200: no effect on the shuffle
+    // kernels (they are bound by random DRAM row activations, not by bytes), so the driver default is kept.
     {
-        size_t gran = 32;
         const char* env = getenv("SQB_L2_FETCH");
-        if (env && atoi(env) > 0) gran = (size_t)atoi(env);
-        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
-        cudaGetLastError();
+        if (env && atoi(env) > 0) {
+            cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(env));
+            cudaGetLastError();
+        }
     }
     *out = c;
     return SQB_OK;
