@@ -45,6 +45,23 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant (shuffle) kernel per launch, from the committed
+    `ncu --set full` capture of this same workload (profiles/r01_prof_nhood_metrics.csv); None if absent."""
+    import csv
+
+    path = os.path.join(ROOT, "profiles", "r01_prof_nhood_metrics.csv")
+    try:
+        rows = {r[0]: r for r in csv.reader(open(path))}
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(rows[k][2]) * scale[rows[k][1]]
+        return {"bytes_per_launch": tot, "kernel": rows["metric"][2], "source": "profiles/r01_prof_nhood_metrics.csv (ncu --set full, P=1000)"}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -378,8 +395,8 @@ def main():
     bpp = plan.bytes_per_perm
     dom = max(kms, key=kms.get)
     step_gbs = bpp * P / (ms_step / 1e3) / 1e9
-    roofline = {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak, "traffic": None,
-                "kernel": "nhood permutation step = fill + shuffle_cta + transpose + count (one launch each per 1000 permutations)",
+    roofline = {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak, "traffic": _ncu_traffic(),
+                "kernel": "nhood permutation step = fill + shuffle + transpose + count (one launch each per 1000 permutations); dominant: nhood_shuffle_*",
                 "algorithmic_bytes_per_perm": int(bpp), "bytes_formula": "4*nnz + 4*(N+1) + 8*N + 4*C^2 (SURVEY.md 8d, reference dtypes)", "peak_source": peak_src,
                 "kernel_ms": kms, "dominant_kernel": dom, "dominant_share": kms[dom] / max(sum(kms.values()), 1e-9)}
 
