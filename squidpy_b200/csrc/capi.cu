@@ -78,6 +78,7 @@ int sqb_ctx_destroy(sqb_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->scratch[0].release();
     c->scratch[1].release();
+    c->scratch[2].release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return SQB_OK;

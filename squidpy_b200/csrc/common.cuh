@@ -95,7 +95,7 @@ struct sqb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // Large scratch buffers that live as long as the context (GB-sized cudaMalloc/cudaFree per API call would
     // otherwise dominate the host-facing latency).  Work on one ctx is stream ordered, so handles can share them.
-    DevBuf<uint8_t> scratch[2];
+    DevBuf<uint8_t> scratch[3];
 };
 
 // Launch accounting.  In profile mode each launch is bracketed by events on the ctx stream and the elapsed

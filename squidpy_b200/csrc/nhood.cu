@@ -28,6 +28,7 @@ typedef unsigned __int128 u128;
 // (and ptxas turns a `bar.warp.sync 0xffffffff` it considers redundant into a NOP, so the full mask is passed in
 // at run time, as a kernel argument, which it cannot reason about).
 #define SQB_CONVERGE() asm volatile("bar.warp.sync %0;" ::"r"(full_mask) : "memory")
+#define SQB_CONVERGE_W() __syncwarp()
 
 __constant__ uint64_t c_jump_M[SQB_PCG_JUMP_BITS][2] = SQB_PCG_JUMP_M_INIT;
 __constant__ uint64_t c_jump_C[SQB_PCG_JUMP_BITS][2] = SQB_PCG_JUMP_C_INIT;
@@ -1183,6 +1184,292 @@ __global__ void __launch_bounds__(PIPE_TEAMS * 64) nhood_shuffle_pipe_kernel(LT*
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2f. TWO-KERNEL replay (algo 5).  ncu showed every fused variant to be bound by random DRAM row activations (1000
+//     live 1 MB label arrays do not fit the 126 MB L2) and, with fewer permutations in flight, by the dependent
+//     instruction chain RNG -> rejection -> swaps.  Splitting the replay removes both:
+//       nhood_jgen_kernel   one warp per permutation, ALL permutations in flight (pure ALU + ballots, no random
+//                           memory traffic): replays PCG64 + masked rejection and streams the Fisher-Yates target
+//                           of every step i to J[perm][i] (coalesced 4-byte stores, read once, evict-first);
+//       nhood_apply_kernel  one CTA per permutation, few permutations in flight (label arrays stay L2 resident):
+//                           takes S consecutive steps per window (no RNG, no prefix sums: the targets are already
+//                           known), detects position sharing (own-range targets, duplicate targets via a
+//                           shared-memory hash table), swaps conflict-free steps straight in global memory and
+//                           replays the few conflicting ones in step order on staged copies.
+// ------------------------------------------------------------------------------------------------
+template <int Q>
+__global__ void __launch_bounds__(128) nhood_jgen_kernel(uint32_t* __restrict__ J, int64_t stride,
+                                                         const uint64_t* __restrict__ states, int64_t n_perms, int nseg,
+                                                         const int64_t* __restrict__ seg_start,
+                                                         const int64_t* __restrict__ seg_len, float wfactor) {
+    constexpr int RAW = 64 * Q;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    u128 M32, C32, Mt, Ct;
+    pcg_jump_consts(32, M32, C32);
+    pcg_jump_consts((uint64_t)lane + 1, Mt, Ct);
+    const int64_t warps_total = (int64_t)gridDim.x * 4;
+    for (int64_t perm = (int64_t)blockIdx.x * 4 + warp; perm < n_perms; perm += warps_total) {
+        uint32_t* __restrict__ Jp = J + perm * stride;
+        const uint64_t* st4 = states + perm * 4;
+        const u128 inc = mk128(st4[2], st4[3]);
+        u128 st = Mt * mk128(st4[0], st4[1]) + Ct * inc;
+        const u128 C32_inc = C32 * inc;
+        uint32_t raw[2 * Q];
+#pragma unroll
+        for (int k = 0; k < 2 * Q; ++k) raw[k] = 0;
+        int pos = RAW;
+        for (int seg = 0; seg < nseg; ++seg) {
+            const int64_t base = seg_start[seg];
+            int i_cur = (int)(seg_len[seg] - 1);
+            while (i_cur >= 1) {
+                if (pos >= RAW) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const uint64_t o = pcg_output(st);
+                        st = M32 * st + C32_inc;
+                        raw[2 * q] = (uint32_t)o;
+                        raw[2 * q + 1] = (uint32_t)(o >> 32);
+                    }
+                    pos = 0;
+                }
+                const uint32_t mask = 0xFFFFFFFFu >> __clz(i_cur);
+                const int i_lo = (int)(mask >> 1) + 1;
+                const int n_ph = i_cur - i_lo + 1;
+                const int K = sqb_window_size((int64_t)i_cur, RAW - pos, RAW, wfactor);
+                uint32_t u[2 * Q];
+                bool inw[2 * Q], F[2 * Q];
+                int c[2 * Q];
+#pragma unroll
+                for (int k = 0; k < 2 * Q; ++k) {
+                    const int r = (k >> 1) * 64 + 2 * lane + (k & 1);
+                    inw[k] = (r >= pos) && (r < pos + K);
+                    u[k] = raw[k] & mask;
+                    F[k] = inw[k] && (u[k] <= (uint32_t)i_cur);
+                    c[k] = 0;
+                }
+                int total = 0;
+                while (true) {
+                    int run = 0;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const uint32_t blo = __ballot_sync(0xffffffffu, F[2 * q]);
+                        const uint32_t bhi = __ballot_sync(0xffffffffu, F[2 * q + 1]);
+                        c[2 * q] = run + __popc(blo & lt_mask) + __popc(bhi & lt_mask);
+                        c[2 * q + 1] = c[2 * q] + (F[2 * q] ? 1 : 0);
+                        run += __popc(blo) + __popc(bhi);
+                    }
+                    total = run;
+                    bool changed = false;
+#pragma unroll
+                    for (int k = 0; k < 2 * Q; ++k) {
+                        const bool nf = inw[k] && ((int)u[k] <= i_cur - c[k]) && (u[k] <= (uint32_t)i_cur);
+                        changed |= (nf != F[k]);
+                        F[k] = nf;
+                    }
+                    if (!__any_sync(0xffffffffu, changed)) break;
+                }
+                int S, newpos;
+                if (total >= n_ph) {
+                    S = n_ph;
+                    int myr = -1;
+#pragma unroll
+                    for (int k = 0; k < 2 * Q; ++k)
+                        if (F[k] && c[k] == S - 1) myr = (k >> 1) * 64 + 2 * lane + (k & 1);
+                    const uint32_t who = __ballot_sync(0xffffffffu, myr >= 0);
+                    newpos = __shfl_sync(0xffffffffu, myr, __ffs(who) - 1) + 1;
+                } else {
+                    S = total;
+                    newpos = pos + K;
+                }
+                // target of step i = i_cur - rank, streamed out (read exactly once by the apply kernel)
+#pragma unroll
+                for (int k = 0; k < 2 * Q; ++k)
+                    if (F[k] && c[k] < S) __stcs(Jp + base + (i_cur - c[k]), u[k]);
+                i_cur -= S;
+                pos = newpos;
+            }
+        }
+    }
+}
+
+template <typename LT, int NT, int SPT>
+__global__ void __launch_bounds__(NT) nhood_apply_kernel(LT* __restrict__ labels, const uint32_t* __restrict__ J,
+                                                         int64_t stride, int64_t n_perms, int nseg,
+                                                         const int64_t* __restrict__ seg_start,
+                                                         const int64_t* __restrict__ seg_len, float wfactor) {
+    constexpr int W = NT * SPT;  // max steps per window
+    constexpr int HS = 2 * W;
+    constexpr int LOG_HS = (HS == 1024 ? 10 : HS == 2048 ? 11 : HS == 4096 ? 12 : HS == 8192 ? 13 : 14);
+    static_assert(HS == (1 << LOG_HS), "HS");
+    constexpr int HS_SHIFT = 32 - LOG_HS;
+    extern __shared__ __align__(16) unsigned char sqb_shuffle_smem[];
+    unsigned long long* s_tab = reinterpret_cast<unsigned long long*>(sqb_shuffle_smem);
+    uint32_t* s_sj = reinterpret_cast<uint32_t*>(s_tab + HS);
+    uint32_t* s_flag = s_sj + W;
+    int* s_misc = reinterpret_cast<int*>(s_flag + W / 32);
+    LT* s_own = reinterpret_cast<LT*>(s_misc + 4);
+    LT* s_hval = s_own + W;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int h = tid; h < HS; h += NT) s_tab[h] = SQB_EMPTY64;
+    for (int w = tid; w < W / 32; w += NT) s_flag[w] = 0;
+    if (tid < 4) s_misc[tid] = 0;
+    __syncthreads();
+
+    for (int64_t perm = blockIdx.x; perm < n_perms; perm += gridDim.x) {
+        LT* __restrict__ a = labels + perm * stride;
+        const uint32_t* __restrict__ Jp = J + perm * stride;
+        for (int seg = 0; seg < nseg; ++seg) {
+            const int64_t base = seg_start[seg];
+            int i_cur = (int)(seg_len[seg] - 1);
+            while (i_cur >= 1) {
+                // window: steps i_cur, i_cur-1, ..., i_cur-S+1 (all >= 1); ~constant expected number of conflicts
+                int S = (int)(wfactor * sqrtf((float)i_cur));
+                S = S < 32 ? 32 : S;
+                S = S > W ? W : S;
+                S = S > i_cur ? i_cur : S;
+                const int own_lo = i_cur - S;
+                uint32_t jv[SPT], slotv[SPT];
+                uint32_t actm = 0, insm = 0;
+                // ---- phase 1: targets (coalesced, streaming), own-range check, hash insert ----
+#pragma unroll
+                for (int k = 0; k < SPT; ++k) {
+                    const int s = tid + k * NT;
+                    const bool live = s < S;
+                    const uint32_t j = live ? __ldcs(Jp + base + (i_cur - (live ? s : 0))) : 0u;
+                    jv[k] = j;
+                    slotv[k] = 0;
+                    if (live) s_sj[s] = j;
+                }
+#pragma unroll
+                for (int k = 0; k < SPT; ++k) {
+                    const int s = tid + k * NT;
+                    if (s < S) {
+                        const uint32_t j = jv[k];
+                        if ((int)j > own_lo) {
+                            const int s2 = i_cur - (int)j;
+                            if (s2 != s) {
+                                actm |= 1u << k;
+                                atomicOr(&s_flag[s >> 5], 1u << (s & 31));
+                                atomicOr(&s_flag[s2 >> 5], 1u << (s2 & 31));
+                            }
+                        } else {
+                            actm |= 1u << k;
+                            uint32_t h = (j * 2654435761u) >> HS_SHIFT;
+                            const unsigned long long mine = ((unsigned long long)j << 32) | (unsigned)s;
+                            while (true) {
+                                const unsigned long long prev = atomicCAS(&s_tab[h], SQB_EMPTY64, mine);
+                                if (prev == SQB_EMPTY64) {
+                                    insm |= 1u << k;
+                                    slotv[k] = h;
+                                    break;
+                                }
+                                if ((uint32_t)(prev >> 32) == j) {
+                                    const int so = (int)(uint32_t)prev;
+                                    atomicOr(&s_flag[s >> 5], 1u << (s & 31));
+                                    atomicOr(&s_flag[so >> 5], 1u << (so & 31));
+                                    break;
+                                }
+                                h = (h + 1) & (HS - 1);
+                            }
+                        }
+                    }
+                }
+                SQB_CONVERGE_W();
+                __syncthreads();
+                // ---- phase 2 (branch-free): conflict-free swaps in global memory, conflicting steps staged ----
+                uint32_t dirm = 0, stgm = 0;
+                {
+                    LT vi[SPT], vj[SPT];
+#pragma unroll
+                    for (int k = 0; k < SPT; ++k) {
+                        const int s = tid + k * NT;
+                        const bool live = s < S;
+                        const int ss = live ? s : 0;
+                        const bool flagged = live && ((s_flag[ss >> 5] >> (ss & 31)) & 1u);
+                        const bool dir = live && !flagged && ((actm >> k) & 1u);
+                        const bool ins = (insm >> k) & 1u;
+                        stgm |= (flagged ? 1u : 0u) << k;
+                        dirm |= (dir ? 1u : 0u) << k;
+                        const bool ldt = dir || (flagged && ins);
+                        vi[k] = (dir || flagged) ? ld_cs<LT>(a + base + (i_cur - ss)) : (LT)0;
+                        vj[k] = ldt ? ld_cg<LT>(a + base + (int64_t)(ldt ? jv[k] : 0u)) : (LT)0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < SPT; ++k) {
+                        const int s = tid + k * NT;
+                        const bool dir = (dirm >> k) & 1u, stg = (stgm >> k) & 1u, ins = (insm >> k) & 1u;
+                        const int ss = (dir || stg) ? s : 0;
+                        if (dir) st_cs<LT>(a + base + (i_cur - ss), vj[k]);
+                        if (dir) a[base + (int64_t)jv[k]] = vi[k];
+                        if (stg) s_own[ss] = vi[k];
+                        if (stg && ins) s_hval[slotv[k]] = vj[k];
+                    }
+                }
+                if (stgm) s_misc[1] = 1;
+                SQB_CONVERGE_W();
+                __syncthreads();
+                const int any_flag = s_misc[1];
+                if (any_flag) {
+                    // ---- phase 3: ordered replay of the conflicting steps on the staged values ----
+                    if (warp == 0) {
+                        const int nwords = (S + 31) >> 5;
+                        for (int wb = 0; wb < nwords; wb += 32) {
+                            const uint32_t myw = (wb + lane < nwords) ? s_flag[wb + lane] : 0u;
+                            uint32_t nz = __ballot_sync(0xffffffffu, myw != 0u);
+                            while (nz) {
+                                const int wl = __ffs(nz) - 1;
+                                nz &= nz - 1;
+                                uint32_t bits = __shfl_sync(0xffffffffu, myw, wl);
+                                if (lane == 0) {
+                                    while (bits) {
+                                        const int b = __ffs(bits) - 1;
+                                        bits &= bits - 1;
+                                        const int s = (wb + wl) * 32 + b;
+                                        const uint32_t j = s_sj[s];
+                                        const LT x = s_own[s];
+                                        if ((int)j > own_lo) {
+                                            const int s2 = i_cur - (int)j;
+                                            if (s2 != s) {
+                                                const LT y = s_own[s2];
+                                                s_own[s] = y;
+                                                s_own[s2] = x;
+                                            }
+                                        } else {
+                                            uint32_t h = (j * 2654435761u) >> HS_SHIFT;
+                                            while ((uint32_t)(s_tab[h] >> 32) != j) h = (h + 1) & (HS - 1);
+                                            const LT y = s_hval[h];
+                                            s_own[s] = y;
+                                            s_hval[h] = x;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int k = 0; k < SPT; ++k) {
+                        const int s = tid + k * NT;
+                        const bool stg = (stgm >> k) & 1u, ins = (insm >> k) & 1u;
+                        const int ss = stg ? s : 0;
+                        if (stg) st_cs<LT>(a + base + (i_cur - ss), s_own[ss]);
+                        if (stg && ins) a[base + (int64_t)jv[k]] = s_hval[slotv[k]];
+                    }
+                    __syncthreads();
+                    for (int w = tid; w < ((S + 31) >> 5); w += NT) s_flag[w] = 0;
+                    if (tid == 0) s_misc[1] = 0;
+                }
+#pragma unroll
+                for (int k = 0; k < SPT; ++k)
+                    if ((insm >> k) & 1u) s_tab[slotv[k]] = SQB_EMPTY64;
+                __syncthreads();
+                i_cur -= S;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 3. transpose [P][stride] -> [n][PB]  (32 permutations x 256 nodes per CTA), optional row scatter through
 //    `order` (library-grouped position k -> original node id)
 // ------------------------------------------------------------------------------------------------
@@ -1474,6 +1761,21 @@ static int launch_shuffle_cta2(sqb_nhood* h, LT* lab, const uint64_t* states, in
     return SQB_OK;
 }
 
+template <typename LT, int NT, int SPT>
+static int launch_apply(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t np, float wf) {
+    sqb_ctx* c = h->ctx;
+    auto k = nhood_apply_kernel<LT, NT, SPT>;
+    constexpr size_t W = (size_t)NT * SPT, HS = 2 * W;
+    const size_t smem = HS * 8 + W * 4 + (W / 32) * 4 + 16 + W * sizeof(LT) + HS * sizeof(LT);
+    SQB_CHECK(smem <= c->smem_optin, SQB_ERR_UNSUPPORTED, "shuffle_algo 5: %zu bytes of shared memory exceed the device limit", smem);
+    SQB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = h->shuffle_ctas;
+    if (grid <= 0) grid = c->sm_count;  // one permutation per SM in flight: the live label arrays stay L2 resident
+    if (grid > np) grid = np;
+    k<<<(unsigned)grid, NT, smem, c->stream>>>(lab, J, h->stride, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, wf);
+    return SQB_OK;
+}
+
 template <typename LT>
 static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np) {
     sqb_ctx* c = h->ctx;
@@ -1496,6 +1798,29 @@ static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t
         else if (nt == 1024 && r == 4) rc = launch_shuffle_cta2<LT, 1024, 4>(h, lab, states, np);
         else if (nt == 128 && r == 4) rc = launch_shuffle_cta2<LT, 128, 4>(h, lab, states, np);
         else sqb_set_error("shuffle_algo 3: unsupported (shuffle_threads, shuffle_r) = (%d, %d)", nt, r);
+        SQB_TRY(rc);
+    } else if (algo == 5) {
+        const float wf = (float)h->shuffle_wfactor_x100 / 100.0f;
+        SQB_TRY(c->scratch[2].alloc((size_t)np * h->stride * sizeof(uint32_t)));
+        uint32_t* J = reinterpret_cast<uint32_t*>(c->scratch[2].p);
+        {
+            int64_t ctas = (int64_t)c->sm_count * 8;
+            if (ctas > ceil_div64(np, 4)) ctas = ceil_div64(np, 4);
+            if (h->shuffle_q == 2)
+                nhood_jgen_kernel<2><<<(unsigned)ctas, 128, 0, c->stream>>>(J, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, 4.0f);
+            else
+                nhood_jgen_kernel<4><<<(unsigned)ctas, 128, 0, c->stream>>>(J, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, 4.0f);
+            c->launches += 1;
+        }
+        int rc = SQB_ERR_INVALID;
+        const int nt = h->shuffle_threads, r = h->shuffle_r;
+        if (nt == 512 && r == 4) rc = launch_apply<LT, 512, 4>(h, lab, J, np, wf);
+        else if (nt == 512 && r == 2) rc = launch_apply<LT, 512, 2>(h, lab, J, np, wf);
+        else if (nt == 1024 && r == 2) rc = launch_apply<LT, 1024, 2>(h, lab, J, np, wf);
+        else if (nt == 1024 && r == 4) rc = launch_apply<LT, 1024, 4>(h, lab, J, np, wf);
+        else if (nt == 256 && r == 4) rc = launch_apply<LT, 256, 4>(h, lab, J, np, wf);
+        else if (nt == 256 && r == 8) rc = launch_apply<LT, 256, 8>(h, lab, J, np, wf);
+        else sqb_set_error("shuffle_algo 5: unsupported (shuffle_threads, shuffle_r) = (%d, %d)", nt, r);
         SQB_TRY(rc);
     } else if (algo == 4) {
         int64_t ctas = h->shuffle_ctas > 0 ? h->shuffle_ctas : (int64_t)c->sm_count * 6;
@@ -1543,7 +1868,7 @@ static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t
 static int64_t auto_chunk(sqb_nhood* h) {
     if (h->perm_chunk > 0) return ((h->perm_chunk + 31) / 32) * 32;
     // keep [chunk][stride] + [n][chunk] under ~8 GB
-    int64_t per_perm = 2 * h->stride * h->lt_bytes;
+    int64_t per_perm = 2 * h->stride * h->lt_bytes + 4 * h->stride;  // label matrices + uint32 target lists (algo 5)
     int64_t ch = (int64_t)8e9 / (per_perm > 0 ? per_perm : 1);
     if (ch < 32) ch = 32;
     if (ch > 16384) ch = 16384;
@@ -1642,7 +1967,7 @@ int sqb_nhood_destroy(sqb_nhood* h) {
 int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value) {
     SQB_CHECK(h && key, SQB_ERR_INVALID, "sqb_nhood_set_option: null argument");
     if (!strcmp(key, "shuffle_algo")) {
-        SQB_CHECK(value >= -1 && value <= 4, SQB_ERR_INVALID, "shuffle_algo must be -1 (auto), 0, 1, 2, 3 or 4");
+        SQB_CHECK(value >= -1 && value <= 5, SQB_ERR_INVALID, "shuffle_algo must be -1 (auto) or 0..5");
         h->shuffle_algo = (int)value;
     } else if (!strcmp(key, "shuffle_r")) {
         SQB_CHECK(value == 2 || value == 4 || value == 8, SQB_ERR_INVALID, "shuffle_r must be 2, 4 or 8");

@@ -61,7 +61,8 @@ def test_create_errors():
 
 
 @pytest.mark.parametrize("algo,threads,q", [(0, 512, 4), (1, 128, 4), (1, 256, 4), (1, 512, 4), (1, 1024, 4), (2, 512, 1), (2, 512, 2), (2, 512, 4),
-                                             (3, 128, 4), (3, 256, 4), (3, 256, 8), (3, 512, 2), (3, 512, 4), (3, 1024, 2), (3, 1024, 4), (4, 512, 4)])
+                                             (3, 128, 4), (3, 256, 4), (3, 256, 8), (3, 512, 2), (3, 512, 4), (3, 1024, 2), (3, 1024, 4), (4, 512, 4),
+                                             (5, 256, 4), (5, 256, 8), (5, 512, 2), (5, 512, 4), (5, 1024, 2), (5, 1024, 4)])
 @pytest.mark.parametrize("n", [2, 3, 5, 33, 100, 1000, 1025, 5041, 70001])
 def test_shuffle_is_numpy_exact(algo, threads, q, n):
     """Shuffled label vectors equal numpy Generator.shuffle of the same spawned generators (oracle = exact replay,
@@ -74,7 +75,7 @@ def test_shuffle_is_numpy_exact(algo, threads, q, n):
     plan = _plan(g, n_cls)
     plan.set_option("shuffle_algo", algo)
     plan.set_option("shuffle_threads", threads)
-    plan.set_option("shuffle_r" if algo == 3 else "shuffle_q", q)
+    plan.set_option("shuffle_r" if algo in (3, 5) else "shuffle_q", q)
     plan.set_base(base)
     P = 7
     st = spawn_states(1234 + n, P)
@@ -83,7 +84,7 @@ def test_shuffle_is_numpy_exact(algo, threads, q, n):
     np.testing.assert_array_equal(got, ref.shuffle_labels(base, st))
 
 
-@pytest.mark.parametrize("algo", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("algo", [0, 1, 2, 3, 4, 5])
 def test_shuffle_library_groups(algo):
     n = 4000
     g = synth.hex_graph(40, 100)
@@ -180,7 +181,7 @@ def test_full_size_1m_spots():
     np.testing.assert_array_equal(got[:6], ref.nhood_perm_counts(g.indptr, g.indices, base, 30, st[:6]))
     assert (got.reshape(P, -1).sum(axis=1, dtype=np.int64) == g.nnz).all()  # every stored entry counted once
     np.testing.assert_array_equal(got, got.transpose(0, 2, 1))  # symmetric graph -> symmetric counts
-    for algo in (1, 3, 4):  # every replay variant at full size, incl. several permutations per CTA / team
+    for algo in (1, 3, 4, 5):  # every replay variant at full size, incl. several permutations per CTA / team
         plan.set_option("shuffle_algo", algo)
         plan.set_option("shuffle_ctas", 16)
         np.testing.assert_array_equal(plan.permute(st), got)

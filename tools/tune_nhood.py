@@ -33,13 +33,14 @@ def main():
     ref_counts = plan.download()
     results = []
     ctx.profile(True)
-    variants = []
-    for algo in (1, 2, 4):
-        variants.append(dict(shuffle_algo=algo, shuffle_threads=512, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_r=4))
-    for ctas in (148, 222, 296, 370):
-        variants.append(dict(shuffle_algo=4, shuffle_threads=512, shuffle_r=4, shuffle_ctas=ctas, shuffle_wfactor_x100=400, shuffle_q=4))
-    variants.append(dict(shuffle_algo=3, shuffle_threads=512, shuffle_r=2, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4))
-    variants.append(dict(shuffle_algo=3, shuffle_threads=128, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4))
+    variants = [dict(shuffle_algo=2, shuffle_threads=512, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_r=4)]
+    for nt, r in ((512, 4), (1024, 2), (1024, 4), (256, 8), (512, 2), (256, 4)):
+        variants.append(dict(shuffle_algo=5, shuffle_threads=nt, shuffle_r=r, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4))
+    for ctas in (74, 111, 222, 296):
+        variants.append(dict(shuffle_algo=5, shuffle_threads=512, shuffle_r=4, shuffle_ctas=ctas, shuffle_wfactor_x100=400, shuffle_q=4))
+    for wf in (200, 300, 600, 800):
+        variants.append(dict(shuffle_algo=5, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=wf, shuffle_q=4))
+    variants.append(dict(shuffle_algo=5, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=2))
     for v in variants:
         for k, val in v.items():
             plan.set_option(k, val)
