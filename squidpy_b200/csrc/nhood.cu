@@ -1296,7 +1296,11 @@ template <typename LT, int NT, int SPT>
 __global__ void __launch_bounds__(NT) nhood_apply_kernel(LT* __restrict__ labels, const uint32_t* __restrict__ J,
                                                          int64_t stride, int64_t n_perms, int nseg,
                                                          const int64_t* __restrict__ seg_start,
-                                                         const int64_t* __restrict__ seg_len, float wfactor) {
+                                                         const int64_t* __restrict__ seg_len, float wfactor, int low_cap) {
+    // low_cap > 0: positions [0, min(low_cap, segment length)) of the current segment live in shared memory for the
+    // whole replay.  Targets are uniform in [0, i], so with 176 KB about half of all random accesses of a 1M-element
+    // shuffle never leave the SM (ncu: the kernel is bound by the ~1.8 cycles/request the LSU needs for uncoalesced
+    // global accesses; shared memory serves a whole warp of random bytes in a few cycles).
     constexpr int W = NT * SPT;  // max steps per window
     constexpr int HS = 2 * W;
     constexpr int LOG_HS = (HS == 1024 ? 10 : HS == 2048 ? 11 : HS == 4096 ? 12 : HS == 8192 ? 13 : 14);
@@ -1309,6 +1313,7 @@ __global__ void __launch_bounds__(NT) nhood_apply_kernel(LT* __restrict__ labels
     int* s_misc = reinterpret_cast<int*>(s_flag + W / 32);
     LT* s_own = reinterpret_cast<LT*>(s_misc + 4);
     LT* s_hval = s_own + W;
+    LT* s_low = s_hval + HS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int h = tid; h < HS; h += NT) s_tab[h] = SQB_EMPTY64;
     for (int w = tid; w < W / 32; w += NT) s_flag[w] = 0;
@@ -1321,6 +1326,9 @@ __global__ void __launch_bounds__(NT) nhood_apply_kernel(LT* __restrict__ labels
         for (int seg = 0; seg < nseg; ++seg) {
             const int64_t base = seg_start[seg];
             int i_cur = (int)(seg_len[seg] - 1);
+            const int low_n = (int)(seg_len[seg] < (int64_t)low_cap ? seg_len[seg] : (int64_t)low_cap);
+            for (int p = tid; p < low_n; p += NT) s_low[p] = a[base + p];
+            __syncthreads();
             while (i_cur >= 1) {
                 // window: steps i_cur, i_cur-1, ..., i_cur-S+1 (all >= 1); ~constant expected number of conflicts
                 int S = (int)(wfactor * sqrtf((float)i_cur));
@@ -1391,16 +1399,27 @@ __global__ void __launch_bounds__(NT) nhood_apply_kernel(LT* __restrict__ labels
                         stgm |= (flagged ? 1u : 0u) << k;
                         dirm |= (dir ? 1u : 0u) << k;
                         const bool ldt = dir || (flagged && ins);
-                        vi[k] = (dir || flagged) ? ld_cs<LT>(a + base + (i_cur - ss)) : (LT)0;
-                        vj[k] = ldt ? ld_cg<LT>(a + base + (int64_t)(ldt ? jv[k] : 0u)) : (LT)0;
+                        const bool ldo = dir || flagged;
+                        const int po = i_cur - ss;              // own position (segment relative)
+                        const int pt = (int)(ldt ? jv[k] : 0u);  // target position
+                        LT xo = (LT)0, xt = (LT)0;
+                        if (ldo && po < low_n) xo = s_low[po];
+                        if (ldo && po >= low_n) xo = ld_cs<LT>(a + base + po);
+                        if (ldt && pt < low_n) xt = s_low[pt];
+                        if (ldt && pt >= low_n) xt = ld_cg<LT>(a + base + pt);
+                        vi[k] = xo;
+                        vj[k] = xt;
                     }
 #pragma unroll
                     for (int k = 0; k < SPT; ++k) {
                         const int s = tid + k * NT;
                         const bool dir = (dirm >> k) & 1u, stg = (stgm >> k) & 1u, ins = (insm >> k) & 1u;
                         const int ss = (dir || stg) ? s : 0;
-                        if (dir) st_cs<LT>(a + base + (i_cur - ss), vj[k]);
-                        if (dir) a[base + (int64_t)jv[k]] = vi[k];
+                        const int po = i_cur - ss, pt = (int)jv[k];
+                        if (dir && po < low_n) s_low[po] = vj[k];
+                        if (dir && po >= low_n) st_cs<LT>(a + base + po, vj[k]);
+                        if (dir && pt < low_n) s_low[pt] = vi[k];
+                        if (dir && pt >= low_n) a[base + pt] = vi[k];
                         if (stg) s_own[ss] = vi[k];
                         if (stg && ins) s_hval[slotv[k]] = vj[k];
                     }
@@ -1452,8 +1471,11 @@ __global__ void __launch_bounds__(NT) nhood_apply_kernel(LT* __restrict__ labels
                         const int s = tid + k * NT;
                         const bool stg = (stgm >> k) & 1u, ins = (insm >> k) & 1u;
                         const int ss = stg ? s : 0;
-                        if (stg) st_cs<LT>(a + base + (i_cur - ss), s_own[ss]);
-                        if (stg && ins) a[base + (int64_t)jv[k]] = s_hval[slotv[k]];
+                        const int po = i_cur - ss, pt = (int)jv[k];
+                        if (stg && po < low_n) s_low[po] = s_own[ss];
+                        if (stg && po >= low_n) st_cs<LT>(a + base + po, s_own[ss]);
+                        if (stg && ins && pt < low_n) s_low[pt] = s_hval[slotv[k]];
+                        if (stg && ins && pt >= low_n) a[base + pt] = s_hval[slotv[k]];
                     }
                     __syncthreads();
                     for (int w = tid; w < ((S + 31) >> 5); w += NT) s_flag[w] = 0;
@@ -1465,6 +1487,9 @@ __global__ void __launch_bounds__(NT) nhood_apply_kernel(LT* __restrict__ labels
                 __syncthreads();
                 i_cur -= S;
             }
+            // segment done: the shared-memory resident low part goes back to global memory
+            for (int p = tid; p < low_n; p += NT) a[base + p] = s_low[p];
+            __syncthreads();
         }
     }
 }
@@ -1660,7 +1685,8 @@ struct sqb_nhood {
     int shuffle_algo = -1;  // -1 auto (1 for few permutations, else 2); 0 serial thread per permutation (cross-check);
                             // 1 CTA per permutation; 2 warp per permutation; 3 CTA per permutation, large windows
     int shuffle_q = 4;     // algo 2: PCG64 outputs per lane per batch (window = 64*q raw values)
-    int shuffle_r = 4;     // algo 3: PCG64 outputs per thread per batch (window = 2*r*threads raw values)
+    int shuffle_r = 4;     // algo 3: PCG64 outputs per thread per batch (window = 2*r*threads raw values); algo 5: steps per thread
+    int64_t shuffle_low = -1;  // algo 5: elements of every label array kept in shared memory (-1 = as much as fits, 0 = off)
     int shuffle_threads = 512;
     int64_t perm_chunk = 0;  // 0 = auto
     int count_algo = 0;
@@ -1766,19 +1792,64 @@ static int launch_apply(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t np, fl
     sqb_ctx* c = h->ctx;
     auto k = nhood_apply_kernel<LT, NT, SPT>;
     constexpr size_t W = (size_t)NT * SPT, HS = 2 * W;
-    const size_t smem = HS * 8 + W * 4 + (W / 32) * 4 + 16 + W * sizeof(LT) + HS * sizeof(LT);
-    SQB_CHECK(smem <= c->smem_optin, SQB_ERR_UNSUPPORTED, "shuffle_algo 5: %zu bytes of shared memory exceed the device limit", smem);
+    const size_t tables = HS * 8 + W * 4 + (W / 32) * 4 + 16 + W * sizeof(LT) + HS * sizeof(LT);
+    SQB_CHECK(tables <= c->smem_optin, SQB_ERR_UNSUPPORTED, "shuffle_algo 5: %zu bytes of shared memory exceed the device limit", tables);
+    // shared-memory resident low part: everything the SM has left (one CTA per SM), unless switched off
+    int64_t low_cap = 0;
+    if (h->shuffle_low != 0) {
+        int64_t avail = ((int64_t)c->smem_optin - 1024 - (int64_t)tables) / (int64_t)sizeof(LT);
+        if (h->shuffle_low > 0 && avail > h->shuffle_low) avail = h->shuffle_low;
+        low_cap = avail > 0 ? (avail / 1024) * 1024 : 0;
+    }
+    const size_t smem = tables + (size_t)low_cap * sizeof(LT);
     SQB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = h->shuffle_ctas;
-    if (grid <= 0) grid = c->sm_count;  // one permutation per SM in flight: the live label arrays stay L2 resident
+    if (grid <= 0) {
+        int per_sm = 1;
+        SQB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, smem));
+        grid = (int64_t)(per_sm < 1 ? 1 : per_sm) * c->sm_count;
+    }
     if (grid > np) grid = np;
-    k<<<(unsigned)grid, NT, smem, c->stream>>>(lab, J, h->stride, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, wf);
+    k<<<(unsigned)grid, NT, smem, c->stream>>>(lab, J, h->stride, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, wf,
+                                               (int)low_cap);
+    return SQB_OK;
+}
+
+template <typename LT>
+static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np) {
+    sqb_ctx* c = h->ctx;
+    const float wf = (float)h->shuffle_wfactor_x100 / 100.0f;
+    SQB_TRY(c->scratch[2].alloc((size_t)np * h->stride * sizeof(uint32_t)));
+    uint32_t* J = reinterpret_cast<uint32_t*>(c->scratch[2].p);
+    {
+        SqbLaunchScope scope(c, SQB_K_MISC);  // J generation is accounted under "misc"
+        int64_t ctas = (int64_t)c->sm_count * 8;
+        if (ctas > ceil_div64(np, 4)) ctas = ceil_div64(np, 4);
+        if (h->shuffle_q == 2)
+            nhood_jgen_kernel<2><<<(unsigned)ctas, 128, 0, c->stream>>>(J, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, 4.0f);
+        else
+            nhood_jgen_kernel<4><<<(unsigned)ctas, 128, 0, c->stream>>>(J, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, 4.0f);
+        SQB_POST_LAUNCH();
+    }
+    SqbLaunchScope scope(c, SQB_K_NHOOD_SHUFFLE);
+    int rc = SQB_ERR_INVALID;
+    const int nt = h->shuffle_threads, r = h->shuffle_r;
+    if (nt == 512 && r == 4) rc = launch_apply<LT, 512, 4>(h, lab, J, np, wf);
+    else if (nt == 512 && r == 2) rc = launch_apply<LT, 512, 2>(h, lab, J, np, wf);
+    else if (nt == 1024 && r == 2) rc = launch_apply<LT, 1024, 2>(h, lab, J, np, wf);
+    else if (nt == 1024 && r == 4) rc = launch_apply<LT, 1024, 4>(h, lab, J, np, wf);
+    else if (nt == 256 && r == 4) rc = launch_apply<LT, 256, 4>(h, lab, J, np, wf);
+    else if (nt == 256 && r == 8) rc = launch_apply<LT, 256, 8>(h, lab, J, np, wf);
+    else sqb_set_error("shuffle_algo 5: unsupported (shuffle_threads, shuffle_r) = (%d, %d)", nt, r);
+    SQB_TRY(rc);
+    SQB_POST_LAUNCH();
     return SQB_OK;
 }
 
 template <typename LT>
 static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np) {
     sqb_ctx* c = h->ctx;
+    if (h->shuffle_algo == 5) return launch_shuffle_two_kernel<LT>(h, lab, states, np);
     SqbLaunchScope scope(c, SQB_K_NHOOD_SHUFFLE);
     // auto: every variant is bound by the per-permutation dependency chain, not by HBM or issue slots (ncu), so with few
     // permutations the CTA version (one permutation finishes sooner) wins, with many the warp version (3-4x fewer
@@ -1798,29 +1869,6 @@ static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t
         else if (nt == 1024 && r == 4) rc = launch_shuffle_cta2<LT, 1024, 4>(h, lab, states, np);
         else if (nt == 128 && r == 4) rc = launch_shuffle_cta2<LT, 128, 4>(h, lab, states, np);
         else sqb_set_error("shuffle_algo 3: unsupported (shuffle_threads, shuffle_r) = (%d, %d)", nt, r);
-        SQB_TRY(rc);
-    } else if (algo == 5) {
-        const float wf = (float)h->shuffle_wfactor_x100 / 100.0f;
-        SQB_TRY(c->scratch[2].alloc((size_t)np * h->stride * sizeof(uint32_t)));
-        uint32_t* J = reinterpret_cast<uint32_t*>(c->scratch[2].p);
-        {
-            int64_t ctas = (int64_t)c->sm_count * 8;
-            if (ctas > ceil_div64(np, 4)) ctas = ceil_div64(np, 4);
-            if (h->shuffle_q == 2)
-                nhood_jgen_kernel<2><<<(unsigned)ctas, 128, 0, c->stream>>>(J, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, 4.0f);
-            else
-                nhood_jgen_kernel<4><<<(unsigned)ctas, 128, 0, c->stream>>>(J, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, 4.0f);
-            c->launches += 1;
-        }
-        int rc = SQB_ERR_INVALID;
-        const int nt = h->shuffle_threads, r = h->shuffle_r;
-        if (nt == 512 && r == 4) rc = launch_apply<LT, 512, 4>(h, lab, J, np, wf);
-        else if (nt == 512 && r == 2) rc = launch_apply<LT, 512, 2>(h, lab, J, np, wf);
-        else if (nt == 1024 && r == 2) rc = launch_apply<LT, 1024, 2>(h, lab, J, np, wf);
-        else if (nt == 1024 && r == 4) rc = launch_apply<LT, 1024, 4>(h, lab, J, np, wf);
-        else if (nt == 256 && r == 4) rc = launch_apply<LT, 256, 4>(h, lab, J, np, wf);
-        else if (nt == 256 && r == 8) rc = launch_apply<LT, 256, 8>(h, lab, J, np, wf);
-        else sqb_set_error("shuffle_algo 5: unsupported (shuffle_threads, shuffle_r) = (%d, %d)", nt, r);
         SQB_TRY(rc);
     } else if (algo == 4) {
         int64_t ctas = h->shuffle_ctas > 0 ? h->shuffle_ctas : (int64_t)c->sm_count * 6;
@@ -1969,6 +2017,9 @@ int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value) {
     if (!strcmp(key, "shuffle_algo")) {
         SQB_CHECK(value >= -1 && value <= 5, SQB_ERR_INVALID, "shuffle_algo must be -1 (auto) or 0..5");
         h->shuffle_algo = (int)value;
+    } else if (!strcmp(key, "shuffle_low")) {
+        SQB_CHECK(value >= -1, SQB_ERR_INVALID, "shuffle_low must be >= -1");
+        h->shuffle_low = value;
     } else if (!strcmp(key, "shuffle_r")) {
         SQB_CHECK(value == 2 || value == 4 || value == 8, SQB_ERR_INVALID, "shuffle_r must be 2, 4 or 8");
         h->shuffle_r = (int)value;

@@ -84,6 +84,25 @@ def test_shuffle_is_numpy_exact(algo, threads, q, n):
     np.testing.assert_array_equal(got, ref.shuffle_labels(base, st))
 
 
+@pytest.mark.parametrize("low", [0, 1024, 50000, -1])
+def test_two_kernel_replay_low_part(low):
+    """algo 5 keeps the first `low` positions of every label array in shared memory: same permutations for any split."""
+    n = 70001
+    g = sp.csr_matrix((np.ones(n - 1, np.float32), (np.arange(n - 1), np.arange(1, n))), shape=(n, n))
+    base = (np.arange(n) % 97).astype(np.uint32)
+    lib = (np.arange(n) % 3).astype(np.int32)
+    plan = _plan(g, 97)
+    plan.set_option("shuffle_algo", 5)
+    plan.set_option("shuffle_low", low)
+    st = spawn_states(77, 5)
+    plan.set_base(base)
+    plan.upload(st)
+    np.testing.assert_array_equal(plan.shuffled_labels(0, 5), ref.shuffle_labels(base, st))
+    plan.set_base(base, lib, 3)
+    plan.upload(st)
+    np.testing.assert_array_equal(plan.shuffled_labels(0, 5), ref.shuffle_labels(base, st, lib, 3))
+
+
 @pytest.mark.parametrize("algo", [0, 1, 2, 3, 4, 5])
 def test_shuffle_library_groups(algo):
     n = 4000

@@ -33,14 +33,14 @@ def main():
     ref_counts = plan.download()
     results = []
     ctx.profile(True)
-    variants = [dict(shuffle_algo=2, shuffle_threads=512, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_r=4)]
-    for nt, r in ((512, 4), (1024, 2), (1024, 4), (256, 8), (512, 2), (256, 4)):
-        variants.append(dict(shuffle_algo=5, shuffle_threads=nt, shuffle_r=r, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4))
-    for ctas in (74, 111, 222, 296):
-        variants.append(dict(shuffle_algo=5, shuffle_threads=512, shuffle_r=4, shuffle_ctas=ctas, shuffle_wfactor_x100=400, shuffle_q=4))
-    for wf in (200, 300, 600, 800):
-        variants.append(dict(shuffle_algo=5, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=wf, shuffle_q=4))
-    variants.append(dict(shuffle_algo=5, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=2))
+    variants = []
+    for nt, r in ((512, 4), (1024, 2), (1024, 4), (512, 2)):
+        for low in (-1, 0):
+            variants.append(dict(shuffle_algo=5, shuffle_threads=nt, shuffle_r=r, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_low=low))
+    for low in (65536, 98304):
+        variants.append(dict(shuffle_algo=5, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_low=low))
+    for wf in (200, 800):
+        variants.append(dict(shuffle_algo=5, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=wf, shuffle_q=4, shuffle_low=-1))
     for v in variants:
         for k, val in v.items():
             plan.set_option(k, val)
@@ -49,7 +49,7 @@ def main():
             ctx.profile_reset()
             plan.run_async()
             ctx.sync()
-            kms = {k: ctx.profile_get(k)[0] for k in ("fill", "shuffle", "transpose", "count")}
+            kms = {k: ctx.profile_get(k)[0] for k in ("fill", "shuffle", "transpose", "count", "misc")}
             if best is None or kms["shuffle"] < best["shuffle"]:
                 best = kms
         ok = bool((plan.download() == ref_counts).all())
