@@ -179,6 +179,20 @@ __device__ __forceinline__ void st_cs(LT* p, LT v) {
     __stcs(p, v);
 }
 
+// Start-up stagger (ns): unit u of U starts u/U * stagger_ns late, so that the persistent CTAs work on different
+// phases of their Fisher-Yates replays.  The live part of a label array is [0, i]; with all permutations in lock step
+// the combined working set swings between P MB and 0, with staggered phases it stays near P/2 MB, which is what
+// lets ~150-250 label arrays stay resident in the 126 MB L2 instead of thrashing DRAM with 32-byte sectors.
+__device__ __forceinline__ void sqb_stagger(uint64_t delay_ns) {
+    if (delay_ns == 0) return;
+    uint64_t t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(4000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    } while (t - t0 < delay_ns);
+}
+
 #define SQB_EMPTY64 0xFFFFFFFFFFFFFFFFULL
 
 template <typename LT, int NT>
@@ -186,7 +200,7 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta_kernel(LT* __restrict__ 
                                                                const uint64_t* __restrict__ states, int64_t n_perms,
                                                                int nseg, const int64_t* __restrict__ seg_start,
                                                                const int64_t* __restrict__ seg_len, float wfactor,
-                                                               uint32_t full_mask) {
+                                                               uint32_t full_mask, uint64_t stagger_ns) {
     constexpr int RAW = 2 * NT;
     constexpr int HS = 4 * NT;  // hash slots (load factor <= 0.5)
     constexpr int NW = NT / 32;
@@ -212,6 +226,7 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta_kernel(LT* __restrict__ 
     pcg_jump_consts((uint64_t)NT, Mn, Cn);
     u128 Mt, Ct;
     pcg_jump_consts((uint64_t)tid + 1, Mt, Ct);
+    sqb_stagger(stagger_ns * blockIdx.x / gridDim.x);
     __syncthreads();
 
     // persistent CTA: permutations blockIdx.x, blockIdx.x + gridDim.x, ...  (the grid size bounds how many label
@@ -432,7 +447,8 @@ template <typename LT, int Q>
 __global__ void __launch_bounds__(128) nhood_shuffle_warp_kernel(LT* __restrict__ labels, int64_t stride,
                                                                  const uint64_t* __restrict__ states, int64_t n_perms,
                                                                  int nseg, const int64_t* __restrict__ seg_start,
-                                                                 const int64_t* __restrict__ seg_len, float wfactor) {
+                                                                 const int64_t* __restrict__ seg_len, float wfactor,
+                                                                 uint64_t stagger_ns) {
     constexpr int RAW = 64 * Q;   // raw 32-bit values per batch
     constexpr int HS = 256 * Q;   // hash slots per warp (load factor <= 0.25)
     constexpr int HS_SHIFT = (Q == 1 ? 24 : Q == 2 ? 23 : 22);
@@ -454,6 +470,8 @@ __global__ void __launch_bounds__(128) nhood_shuffle_warp_kernel(LT* __restrict_
     __syncwarp();
 
     const int64_t warps_total = (int64_t)gridDim.x * 4;
+    sqb_stagger(stagger_ns * (uint64_t)(blockIdx.x * 4 + warp) / (uint64_t)warps_total);
+    __syncwarp();
     for (int64_t perm = (int64_t)blockIdx.x * 4 + warp; perm < n_perms; perm += warps_total) {
         LT* __restrict__ a = labels + perm * stride;
         const uint64_t* st4 = states + perm * 4;
@@ -637,7 +655,7 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__
                                                                 const uint64_t* __restrict__ states, int64_t n_perms,
                                                                 int nseg, const int64_t* __restrict__ seg_start,
                                                                 const int64_t* __restrict__ seg_len, float wfactor,
-                                                                uint32_t full_mask) {
+                                                                uint32_t full_mask, uint64_t stagger_ns) {
     constexpr int V = 2 * R;          // raw values per thread per batch
     constexpr int RAW = V * NT;       // raw values per batch
     constexpr int HS = 2 * RAW;       // hash slots (load factor <= 0.5), power of two
@@ -664,6 +682,7 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__
     u128 Mn, Cn, Mt, Ct;
     pcg_jump_consts((uint64_t)NT, Mn, Cn);
     pcg_jump_consts((uint64_t)tid + 1, Mt, Ct);
+    sqb_stagger(stagger_ns * blockIdx.x / gridDim.x);
     __syncthreads();
 
     for (int64_t perm = blockIdx.x; perm < n_perms; perm += gridDim.x) {
@@ -895,6 +914,293 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__
                 SQB_CONVERGE();
                 __syncthreads();
                 if (tid == 0) s_misc[1] = 0;  // next writers come after the next window's barriers
+                i_cur -= S;
+                pos = newpos;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2g. CTA-per-permutation replay WITHOUT a serial pass ("list" kernel, shuffle_algo 6).
+//     Measured on B200 (tools/micro/rmw_bench.cu): random byte swaps over label arrays that stay inside the 126 MB L2
+//     run at ~55 G swaps/s (18 ms per 1e9 steps), over 1000 arrays (1 GB) at ~20 G swaps/s, because every swap then
+//     costs two random 32-byte DRAM sectors.  So the fast regime is FEW permutations in flight (<= ~150-250 label
+//     arrays, one per CTA) and each of them replayed as fast as possible; 2b/2d in that regime were bound by window
+//     latency: ~10 block barriers, an exposed global round trip and a one-thread ordered replay of the conflicting
+//     steps per window.  This kernel removes those:
+//       * the window's global loads (own range, cooperatively; random targets for every optimistically accepted
+//         value) are issued BEFORE the acceptance fixed point, whose barriers hide their latency;
+//       * acceptance iterations cost one barrier each (double-buffered warp sums, monotonic change stamp);
+//       * conflicts are not serialised.  Every step pushes itself on the list of the position it targets (outside
+//         targets: shared-memory hash table keyed by position; targets inside the window's own range: one list head per
+//         step).  With T(s) = value of step s's top position just before step s
+//                          = T(latest earlier step targeting that top) or its ORIGINAL value,
+//         step s writes a[top_s] = value of position j_s just before step s
+//                                = T(latest earlier step targeting j_s) or the original a[j_s],
+//         and the last step targeting an outside position p writes a[p] = T(that step).  Only original values are
+//         read, all lists are immutable once built, so every step resolves independently (chains are almost always
+//         empty) and windows can be several times larger than with an ordered replay
+//         (tests/emu_shuffle.py::resolve_window_lists is the executable specification).
+//     Barriers per window: (acceptance iterations + 1) + 2.
+// ------------------------------------------------------------------------------------------------
+#define SQB_NONE16 0xFFFFu
+#define SQB_NONE32 0xFFFFFFFFu
+
+template <typename LT>
+__device__ __forceinline__ LT sqb_list_T(const uint32_t* __restrict__ s_ohead, const uint16_t* __restrict__ s_next,
+                                         const LT* __restrict__ s_otop, int x) {
+    // follow "latest earlier step targeting my top" until a step whose top nobody targeted before it
+    while (true) {
+        const uint32_t h = s_ohead[x];
+        if (h == SQB_NONE32) break;
+        int m = (int)h;
+        for (uint32_t e = s_next[h]; e != SQB_NONE16; e = s_next[e]) m = max(m, (int)e);
+        x = m;  // every element of the list of x is < x
+    }
+    return s_otop[x];
+}
+
+__device__ __forceinline__ int sqb_list_latest_before(const uint16_t* __restrict__ s_next, uint32_t head, int s, int* mx) {
+    int best = -1, m = -1;
+    for (uint32_t e = head; e != SQB_NONE16 && e != SQB_NONE32; e = s_next[e]) {
+        const int ei = (int)e;
+        m = max(m, ei);
+        if (ei < s) best = max(best, ei);
+    }
+    *mx = m;
+    return best;
+}
+
+template <typename LT, int NT, int R>
+__global__ void __launch_bounds__(NT) nhood_shuffle_list_kernel(LT* __restrict__ labels, int64_t stride,
+                                                                const uint64_t* __restrict__ states, int64_t n_perms,
+                                                                int nseg, const int64_t* __restrict__ seg_start,
+                                                                const int64_t* __restrict__ seg_len, float wfactor,
+                                                                uint32_t full_mask, uint64_t stagger_ns) {
+    constexpr int V = 2 * R;     // raw values per thread per batch
+    constexpr int RAW = V * NT;  // raw values per batch = max steps per window
+    constexpr int HS = 2 * RAW;  // hash slots (load factor <= 0.5), power of two
+    constexpr int NW = NT / 32;
+    constexpr int LOG_HS = (HS == 1024 ? 10 : HS == 2048 ? 11 : HS == 4096 ? 12 : HS == 8192 ? 13 : HS == 16384 ? 14 : 15);
+    static_assert(HS == (1 << LOG_HS), "HS must be a power of two");
+    static_assert(RAW < 0xFFFF, "step indices are stored in 16 bits");
+    constexpr int HS_SHIFT = 32 - LOG_HS;
+
+    extern __shared__ __align__(16) unsigned char sqb_shuffle_smem[];
+    unsigned long long* s_tab = reinterpret_cast<unsigned long long*>(sqb_shuffle_smem);  // (target << 32) | list head, or EMPTY
+    uint32_t* s_ohead = reinterpret_cast<uint32_t*>(s_tab + HS);                            // [RAW] head of "steps targeting top of u"
+    int* s_wsum = reinterpret_cast<int*>(s_ohead + RAW);                                    // [2][R][32]
+    int* s_misc = s_wsum + 2 * R * 32;                                                      // [0] r*, [1] change stamp
+    uint16_t* s_next = reinterpret_cast<uint16_t*>(s_misc + 4);                             // [RAW] list links
+    LT* s_otop = reinterpret_cast<LT*>(s_next + RAW);                                       // [RAW] original own-range values
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int h = tid; h < HS; h += NT) s_tab[h] = SQB_EMPTY64;
+    for (int w = tid; w < RAW; w += NT) s_ohead[w] = SQB_NONE32;
+    for (int w = tid; w < 2 * R * 32; w += NT) s_wsum[w] = 0;
+    if (tid < 4) s_misc[tid] = 0;
+    u128 Mn, Cn, Mt, Ct;
+    pcg_jump_consts((uint64_t)NT, Mn, Cn);
+    pcg_jump_consts((uint64_t)tid + 1, Mt, Ct);
+    int stamp = 0;  // acceptance iteration counter (uniform across the CTA, monotonic for the whole kernel)
+    sqb_stagger(stagger_ns * blockIdx.x / gridDim.x);
+    __syncthreads();
+
+    for (int64_t perm = blockIdx.x; perm < n_perms; perm += gridDim.x) {
+        LT* __restrict__ a = labels + perm * stride;
+        const uint64_t* st4 = states + perm * 4;
+        const u128 inc = mk128(st4[2], st4[3]);
+        u128 st = Mt * mk128(st4[0], st4[1]) + Ct * inc;  // state of output index `tid`
+        const u128 Cn_inc = Cn * inc;
+        uint32_t raw[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) raw[k] = 0;
+        int pos = RAW;
+
+        for (int seg = 0; seg < nseg; ++seg) {
+            const int64_t base = seg_start[seg];
+            int i_cur = (int)(seg_len[seg] - 1);  // n < 2^31
+            while (i_cur >= 1) {
+                if (pos >= RAW) {
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {  // output q*NT + tid of this batch -> raw 2*(q*NT+tid) + {0,1}
+                        const uint64_t o = pcg_output(st);
+                        st = Mn * st + Cn_inc;
+                        raw[2 * q] = (uint32_t)o;
+                        raw[2 * q + 1] = (uint32_t)(o >> 32);
+                    }
+                    pos = 0;
+                }
+                const uint32_t mask = 0xFFFFFFFFu >> __clz(i_cur);
+                const int i_lo = (int)(mask >> 1) + 1;
+                const int n_ph = i_cur - i_lo + 1;
+                const int K = sqb_window_size((int64_t)i_cur, RAW - pos, RAW, wfactor);
+                uint32_t inmask = 0, fmask = 0;  // bit k: value k inside the window / accepted (optimistic start)
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const int r = (k >> 1) * (2 * NT) + 2 * tid + (k & 1);
+                    const bool in = (r >= pos) && (r < pos + K);
+                    const bool ok = in && ((raw[k] & mask) <= (uint32_t)i_cur);
+                    inmask |= (in ? 1u : 0u) << k;
+                    fmask |= (ok ? 1u : 0u) << k;
+                }
+                // ---- early loads (branch free): own range cooperatively (x = tid + m*NT), targets of all candidates ----
+                LT vt[V], vj[V];
+#pragma unroll
+                for (int m = 0; m < V; ++m) {
+                    const int x = tid + m * NT;
+                    const bool ld = x < K;  // K <= i_cur / 4: never below the segment start
+                    vt[m] = ld ? ld_cs<LT>(a + base + (i_cur - (ld ? x : 0))) : (LT)0;
+                }
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const bool ld = (fmask >> k) & 1u;
+                    vj[k] = ld ? ld_cg<LT>(a + base + (int64_t)(ld ? (raw[k] & mask) : 0u)) : (LT)0;
+                }
+                // ---- acceptance fixed point; c(k) = cb[k>>1] + (k odd ? bit(k-1) : 0); one barrier per iteration ----
+                int cb[R];
+                int total = 0;
+                uint32_t blo[R], bhi[R];
+                int buf = 0;
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    blo[q] = __ballot_sync(0xffffffffu, (fmask >> (2 * q)) & 1u);
+                    bhi[q] = __ballot_sync(0xffffffffu, (fmask >> (2 * q + 1)) & 1u);
+                    if (lane == 0) s_wsum[q * 32 + warp] = __popc(blo[q]) + __popc(bhi[q]);
+                }
+                int last_stamp = -1;  // stamp of the previous iteration of THIS window
+                while (true) {
+                    SQB_CONVERGE();
+                    __syncthreads();
+                    // the previous iteration changed nothing anywhere: fmask and the cb computed from it are final
+                    if (last_stamp >= 0 && s_misc[1] < last_stamp) break;
+                    const int* ws = s_wsum + buf * (R * 32);
+                    int run = 0;
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        const int v = (lane < NW) ? ws[q * 32 + lane] : 0;
+                        int incl = v;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                            if (lane >= d) incl += t;
+                        }
+                        const int woff = __shfl_sync(0xffffffffu, incl - v, warp);
+                        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+                        cb[q] = run + woff + __popc(blo[q] & lt_mask) + __popc(bhi[q] & lt_mask);
+                        run += tot;
+                    }
+                    total = run;
+                    uint32_t nf = 0;
+#pragma unroll
+                    for (int k = 0; k < V; ++k) {
+                        const int ck = cb[k >> 1] + ((k & 1) ? (int)((fmask >> (k - 1)) & 1u) : 0);
+                        const uint32_t uk = raw[k] & mask;
+                        const bool ok = ((inmask >> k) & 1u) && uk <= (uint32_t)i_cur && (int)uk <= i_cur - ck;
+                        nf |= (ok ? 1u : 0u) << k;
+                    }
+                    ++stamp;
+                    last_stamp = stamp;
+                    if (nf != fmask) s_misc[1] = stamp;
+                    fmask = nf;
+                    buf ^= 1;
+                    int* wn = s_wsum + buf * (R * 32);
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        blo[q] = __ballot_sync(0xffffffffu, (fmask >> (2 * q)) & 1u);
+                        bhi[q] = __ballot_sync(0xffffffffu, (fmask >> (2 * q + 1)) & 1u);
+                        if (lane == 0) wn[q * 32 + warp] = __popc(blo[q]) + __popc(bhi[q]);
+                    }
+                }
+                const bool phase_ends = total >= n_ph;
+                const int S = phase_ends ? n_ph : total;
+                const int own_lo = i_cur - S;
+                // ---- B: stage the original own-range values, build the target lists ----
+#pragma unroll
+                for (int m = 0; m < V; ++m) {
+                    const int x = tid + m * NT;
+                    if (x < S) s_otop[x] = vt[m];
+                }
+                uint32_t live = 0, ownm = 0;  // bit k: value k is step ck < S / its target lies in the window's own range
+                uint32_t slotv[V];
+#pragma unroll
+                for (int k = 0; k < V; ++k) slotv[k] = 0;
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const int ck = cb[k >> 1] + ((k & 1) ? (int)((fmask >> (k - 1)) & 1u) : 0);
+                    if (((fmask >> k) & 1u) && ck < S) {
+                        live |= 1u << k;
+                        if (phase_ends && ck == S - 1) s_misc[0] = (k >> 1) * (2 * NT) + 2 * tid + (k & 1);
+                        const uint32_t j = raw[k] & mask;
+                        if ((int)j > own_lo) {
+                            ownm |= 1u << k;
+                            const int u = i_cur - (int)j;  // u >= ck
+                            if (u != ck) {
+                                const uint32_t prev = atomicExch(&s_ohead[u], (uint32_t)ck);
+                                s_next[ck] = (uint16_t)prev;  // NONE32 truncates to NONE16
+                            }
+                        } else {
+                            uint32_t h = (j * 2654435761u) >> HS_SHIFT;
+                            const unsigned long long mine = ((unsigned long long)j << 32) | (unsigned)ck;
+                            uint32_t nxt = SQB_NONE16;
+                            while (true) {
+                                const unsigned long long prev = atomicCAS(&s_tab[h], SQB_EMPTY64, mine);
+                                if (prev == SQB_EMPTY64) break;
+                                if ((uint32_t)(prev >> 32) == j) {  // same target: push in front of the current head
+                                    if (atomicCAS(&s_tab[h], prev, mine) == prev) {
+                                        nxt = (uint32_t)prev & 0xFFFFu;
+                                        break;
+                                    }
+                                    continue;  // head moved, retry this slot
+                                }
+                                h = (h + 1) & (HS - 1);
+                            }
+                            s_next[ck] = (uint16_t)nxt;
+                            slotv[k] = h;
+                        }
+                    }
+                }
+                SQB_CONVERGE();
+                __syncthreads();
+                const int newpos = phase_ends ? (s_misc[0] + 1) : (pos + K);
+                // ---- C: every step resolves what it writes from the (now immutable) lists ----
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    if ((live >> k) & 1u) {
+                        const int ck = cb[k >> 1] + ((k & 1) ? (int)((fmask >> (k - 1)) & 1u) : 0);
+                        const uint32_t j = raw[k] & mask;
+                        LT val;
+                        if ((ownm >> k) & 1u) {
+                            const int u = i_cur - (int)j;
+                            if (u == ck) {
+                                val = sqb_list_T<LT>(s_ohead, s_next, s_otop, ck);
+                            } else {
+                                int mx;
+                                const int p = sqb_list_latest_before(s_next, s_ohead[u], ck, &mx);
+                                val = (p >= 0) ? sqb_list_T<LT>(s_ohead, s_next, s_otop, p) : s_otop[u];
+                            }
+                        } else {
+                            const uint32_t head = (uint32_t)s_tab[slotv[k]] & 0xFFFFu;
+                            int mx;
+                            const int p = sqb_list_latest_before(s_next, head, ck, &mx);
+                            val = (p >= 0) ? sqb_list_T<LT>(s_ohead, s_next, s_otop, p) : vj[k];
+                            if (mx == ck) a[base + (int64_t)j] = sqb_list_T<LT>(s_ohead, s_next, s_otop, ck);
+                        }
+                        st_cs<LT>(a + base + (i_cur - ck), val);  // final position: never read again by this kernel
+                    }
+                }
+                SQB_CONVERGE();
+                __syncthreads();
+                // ---- reset the list heads this thread pushed on (the next window's first barrier orders them) ----
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const bool lv = (live >> k) & 1u, ow = (ownm >> k) & 1u;
+                    const uint32_t j = raw[k] & mask;
+                    if (lv && ow) s_ohead[i_cur - (int)j] = SQB_NONE32;
+                    if (lv && !ow) s_tab[slotv[k]] = SQB_EMPTY64;
+                }
                 i_cur -= S;
                 pos = newpos;
             }
@@ -1296,7 +1602,8 @@ template <typename LT, int NT, int SPT>
 __global__ void __launch_bounds__(NT) nhood_apply_kernel(LT* __restrict__ labels, const uint32_t* __restrict__ J,
                                                          int64_t stride, int64_t n_perms, int nseg,
                                                          const int64_t* __restrict__ seg_start,
-                                                         const int64_t* __restrict__ seg_len, float wfactor, int low_cap) {
+                                                         const int64_t* __restrict__ seg_len, float wfactor, int low_cap,
+                                                         uint64_t stagger_ns) {
     // low_cap > 0: positions [0, min(low_cap, segment length)) of the current segment live in shared memory for the
     // whole replay.  Targets are uniform in [0, i], so with 176 KB about half of all random accesses of a 1M-element
     // shuffle never leave the SM (ncu: the kernel is bound by the ~1.8 cycles/request the LSU needs for uncoalesced
@@ -1318,6 +1625,7 @@ __global__ void __launch_bounds__(NT) nhood_apply_kernel(LT* __restrict__ labels
     for (int h = tid; h < HS; h += NT) s_tab[h] = SQB_EMPTY64;
     for (int w = tid; w < W / 32; w += NT) s_flag[w] = 0;
     if (tid < 4) s_misc[tid] = 0;
+    sqb_stagger(stagger_ns * blockIdx.x / gridDim.x);
     __syncthreads();
 
     for (int64_t perm = blockIdx.x; perm < n_perms; perm += gridDim.x) {
@@ -1490,6 +1798,202 @@ __global__ void __launch_bounds__(NT) nhood_apply_kernel(LT* __restrict__ labels
             // segment done: the shared-memory resident low part goes back to global memory
             for (int p = tid; p < low_n; p += NT) a[base + p] = s_low[p];
             __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2h. TWO-KERNEL replay with list-based conflict resolution (shuffle_algo 7): nhood_jgen_kernel (2f, a warp per
+//     permutation, warp-level synchronisation only) turns the PCG64 streams into the swap targets J[perm][i]; this kernel
+//     applies them, one CTA per permutation, W = NT*SPT Fisher-Yates steps per window.  Step s of a window (top position
+//     i_cur - s) belongs to thread s % NT: the J values, the own range and its write-back are fully coalesced, no ranks,
+//     ballots or acceptance barriers are left in this kernel, and conflicts are resolved exactly as in 2g (per-position
+//     lists, original values only, no ordered pass).  The next window's J values are prefetched into registers.
+//     ncu on the first version (every outside target inserted into the hash table): 43% of all instructions and most
+//     short-scoreboard stalls were the dependent 64-bit CAS probe chains, and the barrier stalls (25%) their imbalance.
+//     Duplicate targets are rare, so they are now FILTERED first: two bits per bucket (bucket = target mod 32W) in shared
+//     memory, "seen" and "seen again", set with one atomicOr per step (independent across the steps of a thread).  After a
+//     barrier a step whose bucket was not seen again is alone on its target: it writes the two values without touching
+//     any list.  Only the steps of multiply-hit buckets (a few percent, false positives included) and the own-range
+//     targets build lists.  Three barriers per window; filter, hash table and own-range heads are double buffered
+//     (window parity) so that their reset needs no barrier of its own.
+// ------------------------------------------------------------------------------------------------
+template <typename LT, int NT, int SPT>
+__global__ void __launch_bounds__(NT) nhood_apply_list_kernel(LT* __restrict__ labels, const uint32_t* __restrict__ J,
+                                                              int64_t stride, int64_t n_perms, int nseg,
+                                                              const int64_t* __restrict__ seg_start,
+                                                              const int64_t* __restrict__ seg_len, uint32_t full_mask,
+                                                              uint64_t stagger_ns) {
+    constexpr int W = NT * SPT;  // steps per window
+    constexpr int HS = W;        // hash slots: only steps of multiply-hit buckets are inserted (<= W distinct keys always fit)
+    constexpr int NWB = 2 * W;   // filter words (16 buckets of 2 bits each)
+    constexpr int LOG_HS = (HS == 512 ? 9 : HS == 1024 ? 10 : HS == 2048 ? 11 : HS == 4096 ? 12 : HS == 8192 ? 13 : 14);
+    static_assert(HS == (1 << LOG_HS), "HS must be a power of two");
+    static_assert(W < 0xFFFF, "step indices are stored in 16 bits");
+    constexpr int HS_SHIFT = 32 - LOG_HS;
+    extern __shared__ __align__(16) unsigned char sqb_shuffle_smem[];
+    unsigned long long* s_tab0 = reinterpret_cast<unsigned long long*>(sqb_shuffle_smem);  // [2][HS] (target << 32) | list head
+    uint32_t* s_bits0 = reinterpret_cast<uint32_t*>(s_tab0 + 2 * HS);                        // [2][NWB] duplicate filter
+    uint32_t* s_ohead0 = s_bits0 + 2 * NWB;                                                  // [2][W] own-range list heads
+    uint16_t* s_next = reinterpret_cast<uint16_t*>(s_ohead0 + 2 * W);                        // [W] list links
+    LT* s_otop = reinterpret_cast<LT*>(s_next + W);                                          // [W] original own-range values
+    const int tid = threadIdx.x;
+    for (int h = tid; h < 2 * HS; h += NT) s_tab0[h] = SQB_EMPTY64;
+    for (int w = tid; w < 2 * NWB; w += NT) s_bits0[w] = 0u;
+    for (int w = tid; w < 2 * W; w += NT) s_ohead0[w] = SQB_NONE32;
+    int par = 0;
+    sqb_stagger(stagger_ns * blockIdx.x / gridDim.x);
+    __syncthreads();
+
+    for (int64_t perm = blockIdx.x; perm < n_perms; perm += gridDim.x) {
+        LT* __restrict__ a = labels + perm * stride;
+        const uint32_t* __restrict__ Jp = J + perm * stride;
+        for (int seg = 0; seg < nseg; ++seg) {
+            const int64_t base = seg_start[seg];
+            int i_cur = (int)(seg_len[seg] - 1);  // n < 2^31
+            uint32_t jn[SPT];                      // targets of the coming window (prefetched)
+            {
+                const int S0 = min(W, i_cur);
+#pragma unroll
+                for (int m = 0; m < SPT; ++m) {
+                    const int s = tid + m * NT;
+                    const bool ac = s < S0;
+                    jn[m] = ac ? __ldcs(Jp + base + (i_cur - (ac ? s : 0))) : 0u;
+                }
+            }
+            while (i_cur >= 1) {
+                const int S = min(W, i_cur);  // steps i_cur, i_cur-1, ..., i_cur-S+1 (>= 1)
+                const int own_lo = i_cur - S;
+                unsigned long long* s_tab = s_tab0 + par * HS;
+                uint32_t* s_bits = s_bits0 + par * NWB;
+                uint32_t* s_ohead = s_ohead0 + par * W;
+                par ^= 1;
+                uint32_t jv[SPT];
+                LT vt[SPT], vj[SPT];
+                uint32_t act = 0, ownm = 0;  // bit m: step tid + m*NT exists / targets the window's own range
+#pragma unroll
+                for (int m = 0; m < SPT; ++m) {
+                    const int s = tid + m * NT;
+                    const bool ac = s < S;
+                    jv[m] = jn[m];
+                    const bool ow = ac && ((int)jv[m] > own_lo);
+                    act |= (ac ? 1u : 0u) << m;
+                    ownm |= (ow ? 1u : 0u) << m;
+                    vt[m] = ac ? ld_cs<LT>(a + base + (i_cur - (ac ? s : 0))) : (LT)0;
+                    vj[m] = (ac && !ow) ? ld_cg<LT>(a + base + (int64_t)((ac && !ow) ? jv[m] : 0u)) : (LT)0;
+                }
+                {  // prefetch the next window's targets (same segment; nothing to fetch after the last window)
+                    const int i_nx = i_cur - S;
+                    const int S_nx = min(W, i_nx);
+#pragma unroll
+                    for (int m = 0; m < SPT; ++m) {
+                        const int s = tid + m * NT;
+                        const bool ac = s < S_nx;
+                        jn[m] = ac ? __ldcs(Jp + base + (i_nx - (ac ? s : 0))) : 0u;
+                    }
+                }
+                // ---- B1: duplicate filter for outside targets, list push for own-range targets ----
+                uint32_t old[SPT];
+#pragma unroll
+                for (int m = 0; m < SPT; ++m) {
+                    const bool out = ((act >> m) & 1u) && !((ownm >> m) & 1u);
+                    const uint32_t j = jv[m];
+                    old[m] = out ? atomicOr(&s_bits[(j >> 4) & (NWB - 1)], 1u << ((j & 15u) * 2u)) : 0u;
+                }
+#pragma unroll
+                for (int m = 0; m < SPT; ++m) {
+                    const int s = tid + m * NT;
+                    const bool out = ((act >> m) & 1u) && !((ownm >> m) & 1u);
+                    const uint32_t j = jv[m];
+                    const uint32_t sh = (j & 15u) * 2u;
+                    if (out && ((old[m] >> sh) & 1u)) atomicOr(&s_bits[(j >> 4) & (NWB - 1)], 2u << sh);  // seen again
+                    if ((ownm >> m) & 1u) {
+                        const int u = i_cur - (int)j;  // u >= s
+                        if (u != s) {
+                            const uint32_t prev = atomicExch(&s_ohead[u], (uint32_t)s);
+                            s_next[s] = (uint16_t)prev;  // NONE32 truncates to NONE16
+                        }
+                    }
+                    if ((act >> m) & 1u) s_otop[s] = vt[m];
+                }
+                SQB_CONVERGE();
+                __syncthreads();
+                // ---- B2: steps of multiply-hit buckets build per-target lists in the hash table ----
+                uint32_t slowm = 0;
+                uint32_t slotv[SPT];
+#pragma unroll
+                for (int m = 0; m < SPT; ++m) slotv[m] = 0;
+#pragma unroll
+                for (int m = 0; m < SPT; ++m) {
+                    const int s = tid + m * NT;
+                    const bool out = ((act >> m) & 1u) && !((ownm >> m) & 1u);
+                    const uint32_t j = jv[m];
+                    const uint32_t wbits = out ? s_bits[(j >> 4) & (NWB - 1)] : 0u;
+                    if ((wbits >> ((j & 15u) * 2u + 1u)) & 1u) {
+                        slowm |= 1u << m;
+                        uint32_t h = (j * 2654435761u) >> HS_SHIFT;
+                        const unsigned long long mine = ((unsigned long long)j << 32) | (unsigned)s;
+                        uint32_t nxt = SQB_NONE16;
+                        while (true) {
+                            const unsigned long long prev = atomicCAS(&s_tab[h], SQB_EMPTY64, mine);
+                            if (prev == SQB_EMPTY64) break;
+                            if ((uint32_t)(prev >> 32) == j) {  // same target: push in front of the current head
+                                if (atomicCAS(&s_tab[h], prev, mine) == prev) {
+                                    nxt = (uint32_t)prev & 0xFFFFu;
+                                    break;
+                                }
+                                continue;
+                            }
+                            h = (h + 1) & (HS - 1);
+                        }
+                        s_next[s] = (uint16_t)nxt;
+                        slotv[m] = h;
+                    }
+                }
+                SQB_CONVERGE();
+                __syncthreads();
+                // ---- C: every step derives what it writes (see 2g) ----
+#pragma unroll
+                for (int m = 0; m < SPT; ++m) {
+                    const int s = tid + m * NT;
+                    if ((act >> m) & 1u) {
+                        const uint32_t j = jv[m];
+                        LT val;
+                        if ((ownm >> m) & 1u) {
+                            const int u = i_cur - (int)j;
+                            if (u == s) {
+                                val = sqb_list_T<LT>(s_ohead, s_next, s_otop, s);
+                            } else {
+                                int mx;
+                                const int p = sqb_list_latest_before(s_next, s_ohead[u], s, &mx);
+                                val = (p >= 0) ? sqb_list_T<LT>(s_ohead, s_next, s_otop, p) : s_otop[u];
+                            }
+                        } else if ((slowm >> m) & 1u) {
+                            const uint32_t head = (uint32_t)s_tab[slotv[m]] & 0xFFFFu;
+                            int mx;
+                            const int p = sqb_list_latest_before(s_next, head, s, &mx);
+                            val = (p >= 0) ? sqb_list_T<LT>(s_ohead, s_next, s_otop, p) : vj[m];
+                            if (mx == s) a[base + (int64_t)j] = sqb_list_T<LT>(s_ohead, s_next, s_otop, s);
+                        } else {  // the only step of this window that touches position j
+                            val = vj[m];
+                            a[base + (int64_t)j] = sqb_list_T<LT>(s_ohead, s_next, s_otop, s);
+                        }
+                        st_cs<LT>(a + base + (i_cur - s), val);  // final position: never read again by this kernel
+                    }
+                }
+                SQB_CONVERGE();
+                __syncthreads();
+                // ---- reset this window's copy of the tables (ordered before its reuse by the next window's barriers) ----
+#pragma unroll
+                for (int m = 0; m < SPT; ++m) {
+                    const bool ac = (act >> m) & 1u, ow = (ownm >> m) & 1u, sl = (slowm >> m) & 1u;
+                    const uint32_t j = jv[m];
+                    if (ac && ow) s_ohead[i_cur - (int)j] = SQB_NONE32;
+                    if (ac && !ow) s_bits[(j >> 4) & (NWB - 1)] = 0u;
+                    if (sl) s_tab[slotv[m]] = SQB_EMPTY64;
+                }
+                i_cur -= S;
+            }
         }
     }
 }
@@ -1686,7 +2190,8 @@ struct sqb_nhood {
                             // 1 CTA per permutation; 2 warp per permutation; 3 CTA per permutation, large windows
     int shuffle_q = 4;     // algo 2: PCG64 outputs per lane per batch (window = 64*q raw values)
     int shuffle_r = 4;     // algo 3: PCG64 outputs per thread per batch (window = 2*r*threads raw values); algo 5: steps per thread
-    int64_t shuffle_low = -1;  // algo 5: elements of every label array kept in shared memory (-1 = as much as fits, 0 = off)
+    int64_t shuffle_low = 0;   // algo 5: elements of every label array kept in shared memory (-1 = as much as fits, 0 = off)
+    int64_t shuffle_stagger_us = 0;  // start-up stagger of the persistent shuffle CTAs / warps (see sqb_stagger)
     int shuffle_threads = 512;
     int64_t perm_chunk = 0;  // 0 = auto
     int count_algo = 0;
@@ -1762,7 +2267,8 @@ static int launch_shuffle_nt(sqb_nhood* h, LT* lab, const uint64_t* states, int6
     }
     if (grid > np) grid = np;
     k<<<(unsigned)grid, NT, smem, c->stream>>>(lab, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p,
-                                            (float)h->shuffle_wfactor_x100 / 100.0f, 0xFFFFFFFFu);
+                                            (float)h->shuffle_wfactor_x100 / 100.0f, 0xFFFFFFFFu,
+                                            (uint64_t)h->shuffle_stagger_us * 1000ull);
     return SQB_OK;
 }
 
@@ -1783,7 +2289,31 @@ static int launch_shuffle_cta2(sqb_nhood* h, LT* lab, const uint64_t* states, in
     }
     if (grid > np) grid = np;
     k<<<(unsigned)grid, NT, smem, c->stream>>>(lab, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p,
-                                               (float)h->shuffle_wfactor_x100 / 100.0f, 0xFFFFFFFFu);
+                                               (float)h->shuffle_wfactor_x100 / 100.0f, 0xFFFFFFFFu,
+                                            (uint64_t)h->shuffle_stagger_us * 1000ull);
+    return SQB_OK;
+}
+
+template <typename LT, int NT, int R>
+static int launch_shuffle_list(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np) {
+    sqb_ctx* c = h->ctx;
+    auto k = nhood_shuffle_list_kernel<LT, NT, R>;
+    constexpr size_t RAW = (size_t)2 * R * NT, HS = 2 * RAW;
+    // [tab u64 x HS][ohead u32 x RAW][wsum int x 2*R*32][misc int x 4][next u16 x RAW][otop LT x RAW]
+    const size_t smem = HS * 8 + RAW * 4 + (size_t)2 * R * 32 * 4 + 16 + RAW * 2 + RAW * sizeof(LT);
+    SQB_CHECK(smem <= c->smem_optin, SQB_ERR_UNSUPPORTED, "shuffle_algo 6: %zu bytes of shared memory exceed the device limit", smem);
+    SQB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = h->shuffle_ctas;
+    if (grid <= 0) {
+        int per_sm = 1;
+        SQB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, smem));
+        if (per_sm < 1) per_sm = 1;
+        grid = (int64_t)per_sm * c->sm_count;
+    }
+    if (grid > np) grid = np;
+    k<<<(unsigned)grid, NT, smem, c->stream>>>(lab, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p,
+                                               (float)h->shuffle_wfactor_x100 / 100.0f, 0xFFFFFFFFu,
+                                               (uint64_t)h->shuffle_stagger_us * 1000ull);
     return SQB_OK;
 }
 
@@ -1811,7 +2341,28 @@ static int launch_apply(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t np, fl
     }
     if (grid > np) grid = np;
     k<<<(unsigned)grid, NT, smem, c->stream>>>(lab, J, h->stride, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, wf,
-                                               (int)low_cap);
+                                               (int)low_cap, (uint64_t)h->shuffle_stagger_us * 1000ull);
+    return SQB_OK;
+}
+
+template <typename LT, int NT, int SPT>
+static int launch_apply_list(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t np) {
+    sqb_ctx* c = h->ctx;
+    auto k = nhood_apply_list_kernel<LT, NT, SPT>;
+    constexpr size_t W = (size_t)NT * SPT, HS = W, NWB = 2 * W;
+    // [tab u64 x 2*HS][bits u32 x 2*NWB][ohead u32 x 2*W][next u16 x W][otop LT x W]
+    const size_t smem = 2 * HS * 8 + 2 * NWB * 4 + 2 * W * 4 + W * 2 + W * sizeof(LT);
+    SQB_CHECK(smem <= c->smem_optin, SQB_ERR_UNSUPPORTED, "shuffle_algo 7: %zu bytes of shared memory exceed the device limit", smem);
+    SQB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = h->shuffle_ctas;
+    if (grid <= 0) {
+        int per_sm = 1;
+        SQB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, smem));
+        grid = (int64_t)(per_sm < 1 ? 1 : per_sm) * c->sm_count;
+    }
+    if (grid > np) grid = np;
+    k<<<(unsigned)grid, NT, smem, c->stream>>>(lab, J, h->stride, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, 0xFFFFFFFFu,
+                                               (uint64_t)h->shuffle_stagger_us * 1000ull);
     return SQB_OK;
 }
 
@@ -1834,6 +2385,20 @@ static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* stat
     SqbLaunchScope scope(c, SQB_K_NHOOD_SHUFFLE);
     int rc = SQB_ERR_INVALID;
     const int nt = h->shuffle_threads, r = h->shuffle_r;
+    if (h->shuffle_algo == 7) {
+        if (nt == 1024 && r == 4) rc = launch_apply_list<LT, 1024, 4>(h, lab, J, np);
+        else if (nt == 1024 && r == 2) rc = launch_apply_list<LT, 1024, 2>(h, lab, J, np);
+        else if (nt == 512 && r == 8) rc = launch_apply_list<LT, 512, 8>(h, lab, J, np);
+        else if (nt == 512 && r == 4) rc = launch_apply_list<LT, 512, 4>(h, lab, J, np);
+        else if (nt == 512 && r == 2) rc = launch_apply_list<LT, 512, 2>(h, lab, J, np);
+        else if (nt == 256 && r == 8) rc = launch_apply_list<LT, 256, 8>(h, lab, J, np);
+        else if (nt == 256 && r == 4) rc = launch_apply_list<LT, 256, 4>(h, lab, J, np);
+        else if (nt == 128 && r == 4) rc = launch_apply_list<LT, 128, 4>(h, lab, J, np);
+        else sqb_set_error("shuffle_algo 7: unsupported (shuffle_threads, shuffle_r) = (%d, %d)", nt, r);
+        SQB_TRY(rc);
+        SQB_POST_LAUNCH();
+        return SQB_OK;
+    }
     if (nt == 512 && r == 4) rc = launch_apply<LT, 512, 4>(h, lab, J, np, wf);
     else if (nt == 512 && r == 2) rc = launch_apply<LT, 512, 2>(h, lab, J, np, wf);
     else if (nt == 1024 && r == 2) rc = launch_apply<LT, 1024, 2>(h, lab, J, np, wf);
@@ -1849,7 +2414,7 @@ static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* stat
 template <typename LT>
 static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np) {
     sqb_ctx* c = h->ctx;
-    if (h->shuffle_algo == 5) return launch_shuffle_two_kernel<LT>(h, lab, states, np);
+    if (h->shuffle_algo == 5 || h->shuffle_algo == 7) return launch_shuffle_two_kernel<LT>(h, lab, states, np);
     SqbLaunchScope scope(c, SQB_K_NHOOD_SHUFFLE);
     // auto: every variant is bound by the per-permutation dependency chain, not by HBM or issue slots (ncu), so with few
     // permutations the CTA version (one permutation finishes sooner) wins, with many the warp version (3-4x fewer
@@ -1858,6 +2423,19 @@ static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t
     if (algo == 0) {
         nhood_shuffle_serial_kernel<LT><<<(unsigned)ceil_div64(np, 32), 32, 0, c->stream>>>(
             lab, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p);
+    } else if (algo == 6) {
+        const int nt = (int)h->shuffle_threads, r = (int)h->shuffle_r;
+        int rc = SQB_ERR_UNSUPPORTED;
+        if (nt == 512 && r == 4) rc = launch_shuffle_list<LT, 512, 4>(h, lab, states, np);
+        else if (nt == 512 && r == 2) rc = launch_shuffle_list<LT, 512, 2>(h, lab, states, np);
+        else if (nt == 512 && r == 8) rc = launch_shuffle_list<LT, 512, 8>(h, lab, states, np);
+        else if (nt == 256 && r == 4) rc = launch_shuffle_list<LT, 256, 4>(h, lab, states, np);
+        else if (nt == 256 && r == 8) rc = launch_shuffle_list<LT, 256, 8>(h, lab, states, np);
+        else if (nt == 1024 && r == 2) rc = launch_shuffle_list<LT, 1024, 2>(h, lab, states, np);
+        else if (nt == 1024 && r == 4) rc = launch_shuffle_list<LT, 1024, 4>(h, lab, states, np);
+        else if (nt == 128 && r == 4) rc = launch_shuffle_list<LT, 128, 4>(h, lab, states, np);
+        else sqb_set_error("shuffle_algo 6: unsupported (shuffle_threads, shuffle_r) = (%d, %d)", nt, r);
+        SQB_TRY(rc);
     } else if (algo == 3) {
         int rc = SQB_ERR_INVALID;
         const int nt = h->shuffle_threads, r = h->shuffle_r;
@@ -1882,15 +2460,18 @@ static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t
         switch (h->shuffle_q) {
             case 1:
                 nhood_shuffle_warp_kernel<LT, 1><<<(unsigned)ctas, 128, 0, c->stream>>>(lab, h->stride, states, np, h->nseg,
-                                                                                       h->d_seg_start.p, h->d_seg_len.p, wf);
+                                                                                       h->d_seg_start.p, h->d_seg_len.p, wf,
+                                                                                       (uint64_t)h->shuffle_stagger_us * 1000ull);
                 break;
             case 2:
                 nhood_shuffle_warp_kernel<LT, 2><<<(unsigned)ctas, 128, 0, c->stream>>>(lab, h->stride, states, np, h->nseg,
-                                                                                       h->d_seg_start.p, h->d_seg_len.p, wf);
+                                                                                       h->d_seg_start.p, h->d_seg_len.p, wf,
+                                                                                       (uint64_t)h->shuffle_stagger_us * 1000ull);
                 break;
             default:
                 nhood_shuffle_warp_kernel<LT, 4><<<(unsigned)ctas, 128, 0, c->stream>>>(lab, h->stride, states, np, h->nseg,
-                                                                                       h->d_seg_start.p, h->d_seg_len.p, wf);
+                                                                                       h->d_seg_start.p, h->d_seg_len.p, wf,
+                                                                                       (uint64_t)h->shuffle_stagger_us * 1000ull);
                 break;
         }
     } else {
@@ -2015,8 +2596,11 @@ int sqb_nhood_destroy(sqb_nhood* h) {
 int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value) {
     SQB_CHECK(h && key, SQB_ERR_INVALID, "sqb_nhood_set_option: null argument");
     if (!strcmp(key, "shuffle_algo")) {
-        SQB_CHECK(value >= -1 && value <= 5, SQB_ERR_INVALID, "shuffle_algo must be -1 (auto) or 0..5");
+        SQB_CHECK(value >= -1 && value <= 7, SQB_ERR_INVALID, "shuffle_algo must be -1 (auto) or 0..7");
         h->shuffle_algo = (int)value;
+    } else if (!strcmp(key, "shuffle_stagger_us")) {
+        SQB_CHECK(value >= 0 && value <= 1000000, SQB_ERR_INVALID, "shuffle_stagger_us must be in [0, 1e6]");
+        h->shuffle_stagger_us = value;
     } else if (!strcmp(key, "shuffle_low")) {
         SQB_CHECK(value >= -1, SQB_ERR_INVALID, "shuffle_low must be >= -1");
         h->shuffle_low = value;

@@ -39,7 +39,62 @@ def window_size(i_cur, raw_left, raw_total):
     return min(k, raw_left)
 
 
-def emu_shuffle(arr, state, inc, segs, NT=8, rng=None, stats=None):
+def resolve_window_lists(a, base, i_cur, sj, rng):
+    """Conflict resolution WITHOUT a serial pass (shuffle_algo 6, nhood_shuffle_list_kernel): applies the window's steps
+    s = 0..S-1 (swap positions i_cur-s and sj[s]) to `a` in place.  Every step pushes itself on the list of the position
+    it targets (arbitrary push order = thread interleaving); afterwards each step derives what it has to write from the
+    lists alone, reading only ORIGINAL values:
+      T(s) = value of the top position i_cur-s just before step s = T(latest earlier step targeting it) or the original;
+      step s writes  a[top_s] = value of position sj[s] just before step s = T(latest earlier step targeting sj[s]) or original;
+      the last step targeting an outside position p writes a[p] = T(that step)."""
+    S = len(sj)
+    own_lo = i_cur - S
+    otop = [a[base + i_cur - s] for s in range(S)]          # staged original tops
+    own_list = [[] for _ in range(S)]                        # steps targeting top position of step u (excluding u itself)
+    tab = {}                                                 # outside target -> list of steps
+    order = list(range(S))
+    rng.shuffle(order)
+    for s in order:
+        j = sj[s]
+        if j > own_lo:
+            u = i_cur - j
+            if u != s:
+                own_list[u].append(s)
+        else:
+            tab.setdefault(j, []).append(s)
+    orig_j = {j: a[base + j] for j in tab}
+
+    def T(x):
+        while own_list[x]:
+            x = max(own_list[x])
+        return otop[x]
+
+    def latest_before(lst, s):
+        c = [e for e in lst if e < s]
+        return max(c) if c else None
+
+    writes = []
+    for s in order:
+        j = sj[s]
+        top = base + i_cur - s
+        if j > own_lo:
+            u = i_cur - j
+            if u == s:
+                writes.append((top, T(s)))
+            else:
+                p = latest_before(own_list[u], s)
+                writes.append((top, T(p) if p is not None else otop[u]))
+        else:
+            lst = tab[j]
+            p = latest_before(lst, s)
+            writes.append((top, T(p) if p is not None else orig_j[j]))
+            if s == max(lst):
+                writes.append((base + j, T(s)))
+    for pos, v in writes:
+        a[pos] = v
+
+
+def emu_shuffle(arr, state, inc, segs, NT=8, rng=None, stats=None, resolve="serial"):
     """arr: list (group-contiguous); segs: list of (start, length).  Returns shuffled list."""
     a = list(arr)
     RAW = 2 * NT
@@ -102,6 +157,11 @@ def emu_shuffle(arr, state, inc, segs, NT=8, rng=None, stats=None):
             for r in win:
                 if F[r] and c[r] < S:
                     sj[c[r]] = u[r]
+            if resolve == "lists":
+                resolve_window_lists(a, base, i_cur, sj, rng)
+                i_cur -= S
+                pos = newpos
+                continue
             # ---- swap phase -------------------------------------------------------------------
             own = [a[base + i_cur - s] for s in range(S)]
             flags = [False] * S

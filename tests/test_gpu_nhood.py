@@ -62,7 +62,9 @@ def test_create_errors():
 
 @pytest.mark.parametrize("algo,threads,q", [(0, 512, 4), (1, 128, 4), (1, 256, 4), (1, 512, 4), (1, 1024, 4), (2, 512, 1), (2, 512, 2), (2, 512, 4),
                                              (3, 128, 4), (3, 256, 4), (3, 256, 8), (3, 512, 2), (3, 512, 4), (3, 1024, 2), (3, 1024, 4), (4, 512, 4),
-                                             (5, 256, 4), (5, 256, 8), (5, 512, 2), (5, 512, 4), (5, 1024, 2), (5, 1024, 4)])
+                                             (5, 256, 4), (5, 256, 8), (5, 512, 2), (5, 512, 4), (5, 1024, 2), (5, 1024, 4),
+                                             (6, 128, 4), (6, 256, 4), (6, 256, 8), (6, 512, 2), (6, 512, 4), (6, 512, 8), (6, 1024, 2), (6, 1024, 4),
+                                             (7, 128, 4), (7, 256, 4), (7, 256, 8), (7, 512, 2), (7, 512, 4), (7, 512, 8), (7, 1024, 2), (7, 1024, 4)])
 @pytest.mark.parametrize("n", [2, 3, 5, 33, 100, 1000, 1025, 5041, 70001])
 def test_shuffle_is_numpy_exact(algo, threads, q, n):
     """Shuffled label vectors equal numpy Generator.shuffle of the same spawned generators (oracle = exact replay,
@@ -75,13 +77,32 @@ def test_shuffle_is_numpy_exact(algo, threads, q, n):
     plan = _plan(g, n_cls)
     plan.set_option("shuffle_algo", algo)
     plan.set_option("shuffle_threads", threads)
-    plan.set_option("shuffle_r" if algo in (3, 5) else "shuffle_q", q)
+    plan.set_option("shuffle_r" if algo in (3, 5, 6, 7) else "shuffle_q", q)
     plan.set_base(base)
     P = 7
     st = spawn_states(1234 + n, P)
     plan.upload(st)
     got = plan.shuffled_labels(0, P)
     np.testing.assert_array_equal(got, ref.shuffle_labels(base, st))
+
+
+@pytest.mark.parametrize("wf", [100, 400, 1600, 6400])
+@pytest.mark.parametrize("threads,r", [(256, 4), (512, 8), (1024, 4)])
+def test_list_replay_window_factor(wf, threads, r):
+    """algo 6 resolves conflicting swaps from per-position lists instead of an ordered pass; large window factors make
+    conflicts (and chains of conflicts) frequent.  Any window size must give numpy's permutation."""
+    n = 30011
+    g = sp.csr_matrix((np.ones(n - 1, np.float32), (np.arange(n - 1), np.arange(1, n))), shape=(n, n))
+    base = (np.arange(n) % 199).astype(np.uint32)
+    plan = _plan(g, 199)
+    plan.set_option("shuffle_algo", 6)
+    plan.set_option("shuffle_threads", threads)
+    plan.set_option("shuffle_r", r)
+    plan.set_option("shuffle_wfactor_x100", wf)
+    plan.set_base(base)
+    st = spawn_states(4321 + wf, 9)
+    plan.upload(st)
+    np.testing.assert_array_equal(plan.shuffled_labels(0, 9), ref.shuffle_labels(base, st))
 
 
 @pytest.mark.parametrize("low", [0, 1024, 50000, -1])
@@ -103,7 +124,7 @@ def test_two_kernel_replay_low_part(low):
     np.testing.assert_array_equal(plan.shuffled_labels(0, 5), ref.shuffle_labels(base, st, lib, 3))
 
 
-@pytest.mark.parametrize("algo", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("algo", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_shuffle_library_groups(algo):
     n = 4000
     g = synth.hex_graph(40, 100)
@@ -200,7 +221,7 @@ def test_full_size_1m_spots():
     np.testing.assert_array_equal(got[:6], ref.nhood_perm_counts(g.indptr, g.indices, base, 30, st[:6]))
     assert (got.reshape(P, -1).sum(axis=1, dtype=np.int64) == g.nnz).all()  # every stored entry counted once
     np.testing.assert_array_equal(got, got.transpose(0, 2, 1))  # symmetric graph -> symmetric counts
-    for algo in (1, 3, 4, 5):  # every replay variant at full size, incl. several permutations per CTA / team
+    for algo in (1, 3, 4, 5, 6, 7):  # every replay variant at full size, incl. several permutations per CTA / team
         plan.set_option("shuffle_algo", algo)
         plan.set_option("shuffle_ctas", 16)
         np.testing.assert_array_equal(plan.permute(st), got)

@@ -44,3 +44,47 @@ def test_emulated_cta_shuffle_segments():
             exp[b : b + m] = ref.shuffle_u32(s6, exp[b : b + m])
         got = emu_shuffle(list(range(n)), state, inc, segs, NT=16, rng=rnd)
         np.testing.assert_array_equal(np.array(got, dtype=np.uint32), exp)
+
+
+def test_list_resolution_equals_serial_swaps():
+    """The serial-pass-free conflict resolution of shuffle_algo 6 (tests/emu_shuffle.resolve_window_lists) against the
+    plain in-order application of the same swaps, on windows far denser in conflicts than the device ever sees."""
+    from tests.emu_shuffle import resolve_window_lists
+
+    rnd = random.Random(11)
+    for trial in range(3000):
+        n = rnd.randrange(2, 80)
+        i_cur = n - 1
+        S = rnd.randrange(1, n)  # up to the whole array in one window
+        mode = trial % 3
+        sj = []
+        for s in range(S):
+            top = i_cur - s
+            if mode == 0:
+                sj.append(rnd.randrange(0, top + 1))
+            elif mode == 1:  # mostly inside the window's own range
+                sj.append(rnd.randrange(max(0, top - 6), top + 1))
+            else:  # few distinct outside targets
+                sj.append(min(top, rnd.randrange(0, 4)))
+        base = rnd.randrange(0, 3)
+        a0 = [rnd.randrange(1000) for _ in range(base + n)]
+        exp = list(a0)
+        for s in range(S):
+            t, j = base + i_cur - s, base + sj[s]
+            exp[t], exp[j] = exp[j], exp[t]
+        got = list(a0)
+        resolve_window_lists(got, base, i_cur, sj, rnd)
+        assert got == exp, (trial, n, S, sj)
+
+
+@pytest.mark.parametrize("nt", [4, 64])
+def test_emulated_list_shuffle_matches_numpy(nt):
+    rnd = random.Random(100 + nt)
+    for n in [2, 3, 5, 17, 64, 129, 1000, 4099]:
+        seed = rnd.randrange(10**6)
+        st, state, inc = _state(seed)
+        gen = np.random.default_rng(np.random.SeedSequence(seed).spawn(1)[0])
+        exp = np.arange(n, dtype=np.uint32)
+        gen.shuffle(exp)
+        got = emu_shuffle(list(range(n)), state, inc, [(0, n)], NT=nt, rng=rnd, resolve="lists")
+        np.testing.assert_array_equal(np.array(got, dtype=np.uint32), exp)

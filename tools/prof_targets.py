@@ -28,3 +28,18 @@ elif target == "ripley":
     sup = np.linspace(0, 7000, 50)
     c = pair_counts([pts[lab == k] for k in range(12)], sup, ctx=ctx)
     print("ripley ok", int(c[:, -1].sum()))
+elif target == "shuffle":
+    # nhood shuffle kernel alone at the headline shape: python tools/prof_targets.py shuffle P key=value ...
+    from squidpy_b200._rng import spawn_states
+    from squidpy_b200.gr import NhoodPlan
+    P = int(sys.argv[2]) if len(sys.argv) > 2 else 296
+    g = synth.hex_graph(1000, 1000)
+    base = synth.categorical_labels(g.shape[0], 30, seed=0).cat.codes.to_numpy().astype(np.uint32)
+    plan = NhoodPlan(g.indptr, g.indices, 30, ctx)
+    for kv in sys.argv[3:]:
+        k, v = kv.split("=")
+        plan.set_option(k, int(v))
+    plan.set_base(base)
+    plan.upload(spawn_states(0, P))
+    plan.run_async(); ctx.sync()
+    print("shuffle ok", int(plan.download().sum()))

@@ -34,13 +34,14 @@ def main():
     results = []
     ctx.profile(True)
     variants = []
-    for nt, r in ((512, 4), (1024, 2), (1024, 4), (512, 2)):
-        for low in (-1, 0):
-            variants.append(dict(shuffle_algo=5, shuffle_threads=nt, shuffle_r=r, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_low=low))
-    for low in (65536, 98304):
-        variants.append(dict(shuffle_algo=5, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_low=low))
-    for wf in (200, 800):
-        variants.append(dict(shuffle_algo=5, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=wf, shuffle_q=4, shuffle_low=-1))
+    base = dict(shuffle_algo=1, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_low=0, shuffle_stagger_us=0)
+    # list kernel (algo 6) reference point, then the two-kernel list replay (algo 7): CTA shape x permutations in flight
+    variants.append({**base, "shuffle_algo": 6, "shuffle_threads": 1024, "shuffle_r": 2, "shuffle_wfactor_x100": 1600})
+    for nt, r in ((1024, 4), (1024, 2), (512, 8), (512, 4), (512, 2), (256, 8), (256, 4)):
+        variants.append({**base, "shuffle_algo": 7, "shuffle_threads": nt, "shuffle_r": r})
+    for nt, r in ((1024, 2), (512, 4)):
+        for ctas in (148, 222, 296):
+            variants.append({**base, "shuffle_algo": 7, "shuffle_threads": nt, "shuffle_r": r, "shuffle_ctas": ctas})
     for v in variants:
         for k, val in v.items():
             plan.set_option(k, val)
