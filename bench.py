@@ -46,18 +46,21 @@ def _peaks():
 
 
 def _ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant (shuffle) kernel per launch, from the committed
-    `ncu --set full` capture of this same workload (profiles/r01_prof_nhood_metrics.csv); None if absent."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (the Fisher-Yates apply kernel) per launch, from
+    the committed `ncu --set full` capture of this same workload (profiles/r01_prof_nhood_metrics.csv); None if absent."""
     import csv
 
     path = os.path.join(ROOT, "profiles", "r01_prof_nhood_metrics.csv")
     try:
         rows = {r[0]: r for r in csv.reader(open(path))}
+        names = rows["metric"][2:]
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        dur = [float(v) for v in rows["gpu__time_duration.sum"][2:]]
+        col = 2 + max(range(len(names)), key=lambda i: dur[i])  # the longest launch of the capture
         tot = 0.0
         for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            tot += float(rows[k][2]) * scale[rows[k][1]]
-        return {"bytes_per_launch": tot, "kernel": rows["metric"][2], "source": "profiles/r01_prof_nhood_metrics.csv (ncu --set full, P=1000)"}
+            tot += float(rows[k][col]) * scale[rows[k][1]]
+        return {"bytes_per_launch": tot, "kernel": names[col - 2], "source": "profiles/r01_prof_nhood_metrics.csv (ncu --set full, P=1000)"}
     except Exception:
         return None
 
@@ -389,14 +392,15 @@ def main():
     ctx.profile_reset()
     plan.run_async()
     ctx.sync()
-    kms = {k: ctx.profile_get(k)[0] for k in ("fill", "shuffle", "transpose", "count")}
+    kms = {k: ctx.profile_get(k)[0] for k in ("fill", "misc", "shuffle", "transpose", "count")}
+    kms["jgen"] = kms.pop("misc")  # swap-target generation (PCG64 replay + rejection sampling), accounted as class "misc"
     ctx.profile(False)
     peak, peak_src = _peaks()
     bpp = plan.bytes_per_perm
     dom = max(kms, key=kms.get)
     step_gbs = bpp * P / (ms_step / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak, "traffic": _ncu_traffic(),
-                "kernel": "nhood permutation step = fill + shuffle + transpose + count (one launch each per 1000 permutations); dominant: nhood_shuffle_*",
+                "kernel": "nhood permutation step = fill + jgen + shuffle (apply) + transpose + count (one launch each per 1000 permutations); dominant: nhood_apply_list_kernel",
                 "algorithmic_bytes_per_perm": int(bpp), "bytes_formula": "4*nnz + 4*(N+1) + 8*N + 4*C^2 (SURVEY.md 8d, reference dtypes)", "peak_source": peak_src,
                 "kernel_ms": kms, "dominant_kernel": dom, "dominant_share": kms[dom] / max(sum(kms.values()), 1e-9)}
 

@@ -57,6 +57,14 @@ int sqb_ctx_create(int device, void* stream, sqb_ctx** out) {
     }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+    {  // keep freed blocks of the stream-ordered allocator in the pool (handles are created and destroyed per API call)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        cudaGetLastError();
+    }
     // Optional L2 fetch granularity override (SQB_L2_FETCH=32|64|128).  Measured on B200: no effect on the shuffle
     // kernels (they are bound by random DRAM row activations, not by bytes), so the driver default is kept.
     {

@@ -1823,7 +1823,11 @@ __global__ void __launch_bounds__(NT) nhood_apply_list_kernel(LT* __restrict__ l
                                                               int64_t stride, int64_t n_perms, int nseg,
                                                               const int64_t* __restrict__ seg_start,
                                                               const int64_t* __restrict__ seg_len, uint32_t full_mask,
-                                                              uint64_t stagger_ns) {
+                                                              uint64_t stagger_ns, int low_cap) {
+    // low_cap > 0: positions [0, min(low_cap, segment length)) of the current segment live in shared memory during the
+    // replay.  The kernel is bound by the SM's rate of UNCOALESCED global requests (one random byte load and one random
+    // byte store per step, ~1.8 cycles each, tools/micro/rmw_bench.cu); targets are uniform in [0, i], so a low part of
+    // L elements takes (L + L ln(n/L)) / n of them (25% for L = n/16) off the LSU/L2 path.
     constexpr int W = NT * SPT;  // steps per window
     constexpr int HS = W;        // hash slots: only steps of multiply-hit buckets are inserted (<= W distinct keys always fit)
     constexpr int NWB = 2 * W;   // filter words (16 buckets of 2 bits each)
@@ -1837,6 +1841,7 @@ __global__ void __launch_bounds__(NT) nhood_apply_list_kernel(LT* __restrict__ l
     uint32_t* s_ohead0 = s_bits0 + 2 * NWB;                                                  // [2][W] own-range list heads
     uint16_t* s_next = reinterpret_cast<uint16_t*>(s_ohead0 + 2 * W);                        // [W] list links
     LT* s_otop = reinterpret_cast<LT*>(s_next + W);                                          // [W] original own-range values
+    LT* s_low = s_otop + W;                                                                  // [low_cap] low part of the segment
     const int tid = threadIdx.x;
     for (int h = tid; h < 2 * HS; h += NT) s_tab0[h] = SQB_EMPTY64;
     for (int w = tid; w < 2 * NWB; w += NT) s_bits0[w] = 0u;
@@ -1851,6 +1856,9 @@ __global__ void __launch_bounds__(NT) nhood_apply_list_kernel(LT* __restrict__ l
         for (int seg = 0; seg < nseg; ++seg) {
             const int64_t base = seg_start[seg];
             int i_cur = (int)(seg_len[seg] - 1);  // n < 2^31
+            const int Lc = min(low_cap, i_cur + 1);
+            for (int x = tid; x < Lc; x += NT) s_low[x] = a[base + x];
+            __syncthreads();
             uint32_t jn[SPT];                      // targets of the coming window (prefetched)
             {
                 const int S0 = min(W, i_cur);
@@ -1879,8 +1887,14 @@ __global__ void __launch_bounds__(NT) nhood_apply_list_kernel(LT* __restrict__ l
                     const bool ow = ac && ((int)jv[m] > own_lo);
                     act |= (ac ? 1u : 0u) << m;
                     ownm |= (ow ? 1u : 0u) << m;
-                    vt[m] = ac ? ld_cs<LT>(a + base + (i_cur - (ac ? s : 0))) : (LT)0;
-                    vj[m] = (ac && !ow) ? ld_cg<LT>(a + base + (int64_t)((ac && !ow) ? jv[m] : 0u)) : (LT)0;
+                    const int xt = i_cur - (ac ? s : 0);
+                    const bool tg = ac && xt >= Lc;  // global / shared-memory copy of the position
+                    vt[m] = tg ? ld_cs<LT>(a + base + (tg ? xt : 0)) : (LT)0;
+                    vt[m] = (ac && !tg) ? s_low[tg ? 0 : xt] : vt[m];
+                    const bool jo = ac && !ow;
+                    const bool jg = jo && (int)jv[m] >= Lc;
+                    vj[m] = jg ? ld_cg<LT>(a + base + (int64_t)(jg ? jv[m] : 0u)) : (LT)0;
+                    vj[m] = (jo && !jg) ? s_low[jg ? 0u : (jo ? jv[m] : 0u)] : vj[m];
                 }
                 {  // prefetch the next window's targets (same segment; nothing to fetch after the last window)
                     const int i_nx = i_cur - S;
@@ -1973,12 +1987,19 @@ __global__ void __launch_bounds__(NT) nhood_apply_list_kernel(LT* __restrict__ l
                             int mx;
                             const int p = sqb_list_latest_before(s_next, head, s, &mx);
                             val = (p >= 0) ? sqb_list_T<LT>(s_ohead, s_next, s_otop, p) : vj[m];
-                            if (mx == s) a[base + (int64_t)j] = sqb_list_T<LT>(s_ohead, s_next, s_otop, s);
+                            if (mx == s) {
+                                const LT tv = sqb_list_T<LT>(s_ohead, s_next, s_otop, s);
+                                if ((int)j < Lc) s_low[j] = tv;
+                                else a[base + (int64_t)j] = tv;
+                            }
                         } else {  // the only step of this window that touches position j
                             val = vj[m];
-                            a[base + (int64_t)j] = sqb_list_T<LT>(s_ohead, s_next, s_otop, s);
+                            const LT tv = sqb_list_T<LT>(s_ohead, s_next, s_otop, s);
+                            if ((int)j < Lc) s_low[j] = tv;
+                            else a[base + (int64_t)j] = tv;
                         }
-                        st_cs<LT>(a + base + (i_cur - s), val);  // final position: never read again by this kernel
+                        if (i_cur - s < Lc) s_low[i_cur - s] = val;
+                        else st_cs<LT>(a + base + (i_cur - s), val);  // final position: never read again by this kernel
                     }
                 }
                 SQB_CONVERGE();
@@ -1994,6 +2015,8 @@ __global__ void __launch_bounds__(NT) nhood_apply_list_kernel(LT* __restrict__ l
                 }
                 i_cur -= S;
             }
+            __syncthreads();
+            for (int x = tid; x < Lc; x += NT) a[base + x] = s_low[x];
         }
     }
 }
@@ -2346,13 +2369,21 @@ static int launch_apply(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t np, fl
 }
 
 template <typename LT, int NT, int SPT>
-static int launch_apply_list(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t np) {
+static int launch_apply_list(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t np, int64_t low) {
     sqb_ctx* c = h->ctx;
     auto k = nhood_apply_list_kernel<LT, NT, SPT>;
     constexpr size_t W = (size_t)NT * SPT, HS = W, NWB = 2 * W;
     // [tab u64 x 2*HS][bits u32 x 2*NWB][ohead u32 x 2*W][next u16 x W][otop LT x W]
-    const size_t smem = 2 * HS * 8 + 2 * NWB * 4 + 2 * W * 4 + W * 2 + W * sizeof(LT);
-    SQB_CHECK(smem <= c->smem_optin, SQB_ERR_UNSUPPORTED, "shuffle_algo 7: %zu bytes of shared memory exceed the device limit", smem);
+    const size_t tables = 2 * HS * 8 + 2 * NWB * 4 + 2 * W * 4 + W * 2 + W * sizeof(LT);
+    SQB_CHECK(tables <= c->smem_optin, SQB_ERR_UNSUPPORTED, "shuffle_algo 7: %zu bytes of shared memory exceed the device limit", tables);
+    // shared-memory resident low part (low: -1 = everything the SM has left, 0 = off, > 0 = at most that many elements)
+    int64_t low_cap = 0;
+    if (low != 0) {
+        int64_t avail = ((int64_t)c->smem_optin - (int64_t)tables) / (int64_t)sizeof(LT);
+        if (low > 0 && avail > low) avail = low;
+        low_cap = avail > 0 ? (avail / 1024) * 1024 : 0;
+    }
+    const size_t smem = tables + (size_t)low_cap * sizeof(LT);
     SQB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = h->shuffle_ctas;
     if (grid <= 0) {
@@ -2362,12 +2393,13 @@ static int launch_apply_list(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t n
     }
     if (grid > np) grid = np;
     k<<<(unsigned)grid, NT, smem, c->stream>>>(lab, J, h->stride, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, 0xFFFFFFFFu,
-                                               (uint64_t)h->shuffle_stagger_us * 1000ull);
+                                               (uint64_t)h->shuffle_stagger_us * 1000ull, (int)low_cap);
     return SQB_OK;
 }
 
 template <typename LT>
-static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np) {
+static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np, int algo, int nt, int r,
+                                     int64_t low) {
     sqb_ctx* c = h->ctx;
     const float wf = (float)h->shuffle_wfactor_x100 / 100.0f;
     SQB_TRY(c->scratch[2].alloc((size_t)np * h->stride * sizeof(uint32_t)));
@@ -2384,16 +2416,15 @@ static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* stat
     }
     SqbLaunchScope scope(c, SQB_K_NHOOD_SHUFFLE);
     int rc = SQB_ERR_INVALID;
-    const int nt = h->shuffle_threads, r = h->shuffle_r;
-    if (h->shuffle_algo == 7) {
-        if (nt == 1024 && r == 4) rc = launch_apply_list<LT, 1024, 4>(h, lab, J, np);
-        else if (nt == 1024 && r == 2) rc = launch_apply_list<LT, 1024, 2>(h, lab, J, np);
-        else if (nt == 512 && r == 8) rc = launch_apply_list<LT, 512, 8>(h, lab, J, np);
-        else if (nt == 512 && r == 4) rc = launch_apply_list<LT, 512, 4>(h, lab, J, np);
-        else if (nt == 512 && r == 2) rc = launch_apply_list<LT, 512, 2>(h, lab, J, np);
-        else if (nt == 256 && r == 8) rc = launch_apply_list<LT, 256, 8>(h, lab, J, np);
-        else if (nt == 256 && r == 4) rc = launch_apply_list<LT, 256, 4>(h, lab, J, np);
-        else if (nt == 128 && r == 4) rc = launch_apply_list<LT, 128, 4>(h, lab, J, np);
+    if (algo == 7) {
+        if (nt == 1024 && r == 4) rc = launch_apply_list<LT, 1024, 4>(h, lab, J, np, low);
+        else if (nt == 1024 && r == 2) rc = launch_apply_list<LT, 1024, 2>(h, lab, J, np, low);
+        else if (nt == 512 && r == 8) rc = launch_apply_list<LT, 512, 8>(h, lab, J, np, low);
+        else if (nt == 512 && r == 4) rc = launch_apply_list<LT, 512, 4>(h, lab, J, np, low);
+        else if (nt == 512 && r == 2) rc = launch_apply_list<LT, 512, 2>(h, lab, J, np, low);
+        else if (nt == 256 && r == 8) rc = launch_apply_list<LT, 256, 8>(h, lab, J, np, low);
+        else if (nt == 256 && r == 4) rc = launch_apply_list<LT, 256, 4>(h, lab, J, np, low);
+        else if (nt == 128 && r == 4) rc = launch_apply_list<LT, 128, 4>(h, lab, J, np, low);
         else sqb_set_error("shuffle_algo 7: unsupported (shuffle_threads, shuffle_r) = (%d, %d)", nt, r);
         SQB_TRY(rc);
         SQB_POST_LAUNCH();
@@ -2414,11 +2445,15 @@ static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* stat
 template <typename LT>
 static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np) {
     sqb_ctx* c = h->ctx;
-    if (h->shuffle_algo == 5 || h->shuffle_algo == 7) return launch_shuffle_two_kernel<LT>(h, lab, states, np);
+    if (h->shuffle_algo == 5 || h->shuffle_algo == 7)
+        return launch_shuffle_two_kernel<LT>(h, lab, states, np, h->shuffle_algo, h->shuffle_threads, h->shuffle_r, h->shuffle_low);
+    // auto (measured on B200, 1000 x 1M: two-kernel list replay 23 ms, warp per permutation 39 ms, CTA per permutation
+    // 42 ms): many permutations of large arrays -> J generation + list apply with the tuned shape (1024 threads, 2048-step
+    // windows, 64 K elements of every array in shared memory); few permutations -> one CTA each (finishes sooner);
+    // many permutations of small arrays (L1/L2 resident) -> one warp each
+    if (h->shuffle_algo < 0 && np > 2 * (int64_t)c->sm_count && h->n >= 65536)
+        return launch_shuffle_two_kernel<LT>(h, lab, states, np, 7, 1024, 2, 65536);
     SqbLaunchScope scope(c, SQB_K_NHOOD_SHUFFLE);
-    // auto: every variant is bound by the per-permutation dependency chain, not by HBM or issue slots (ncu), so with few
-    // permutations the CTA version (one permutation finishes sooner) wins, with many the warp version (3-4x fewer
-    // instructions per step, thousands of permutations in flight) does
     const int algo = h->shuffle_algo >= 0 ? h->shuffle_algo : (np <= 2 * (int64_t)c->sm_count ? 1 : 2);
     if (algo == 0) {
         nhood_shuffle_serial_kernel<LT><<<(unsigned)ceil_div64(np, 32), 32, 0, c->stream>>>(
@@ -2559,6 +2594,16 @@ int sqb_nhood_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const uint32_t* indpt
     SQB_CUDA(cudaSetDevice(ctx->device));
     sqb_nhood* h = new sqb_nhood();
     h->ctx = ctx;
+    // all handle buffers are allocated, used and freed in ctx->stream order
+    h->d_indptr.bind(ctx->stream);
+    h->d_indices.bind(ctx->stream);
+    h->d_base.bind(ctx->stream);
+    h->d_order.bind(ctx->stream);
+    h->d_seg_start.bind(ctx->stream);
+    h->d_seg_len.bind(ctx->stream);
+    h->d_states.bind(ctx->stream);
+    h->d_counts.bind(ctx->stream);
+    h->d_tmp_u32.bind(ctx->stream);
     h->n = n;
     h->nnz = nnz;
     h->n_cls = n_cls;
@@ -2649,6 +2694,8 @@ int sqb_nhood_count(sqb_nhood* h, const uint32_t* labels, uint32_t* out) {
     const int64_t CC = (int64_t)h->n_cls * h->n_cls;
     DevBuf<uint8_t> labT;
     DevBuf<uint32_t> cnt;
+    labT.bind(c->stream);
+    cnt.bind(c->stream);
     int rc = SQB_OK;
     if ((rc = h->d_tmp_u32.alloc(h->n)) != SQB_OK) return rc;
     if ((rc = labT.alloc((size_t)h->n * 32 * h->lt_bytes)) != SQB_OK) return rc;

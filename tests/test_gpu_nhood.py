@@ -105,15 +105,16 @@ def test_list_replay_window_factor(wf, threads, r):
     np.testing.assert_array_equal(plan.shuffled_labels(0, 9), ref.shuffle_labels(base, st))
 
 
+@pytest.mark.parametrize("algo", [5, 7])
 @pytest.mark.parametrize("low", [0, 1024, 50000, -1])
-def test_two_kernel_replay_low_part(low):
-    """algo 5 keeps the first `low` positions of every label array in shared memory: same permutations for any split."""
+def test_two_kernel_replay_low_part(low, algo):
+    """algos 5 and 7 can keep the first `low` positions of every label array in shared memory: same permutations for any split."""
     n = 70001
     g = sp.csr_matrix((np.ones(n - 1, np.float32), (np.arange(n - 1), np.arange(1, n))), shape=(n, n))
     base = (np.arange(n) % 97).astype(np.uint32)
     lib = (np.arange(n) % 3).astype(np.int32)
     plan = _plan(g, 97)
-    plan.set_option("shuffle_algo", 5)
+    plan.set_option("shuffle_algo", algo)
     plan.set_option("shuffle_low", low)
     st = spawn_states(77, 5)
     plan.set_base(base)

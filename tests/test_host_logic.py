@@ -165,3 +165,21 @@ def test_anndata_lite_indexing():
     assert list(ad[:, ad.var["highly_variable"]].var_names) == ["a", "c"]
     with pytest.raises(KeyError):
         ad[:, ["zz"]]
+
+
+@pytest.mark.parametrize("seed", [0, 7, 2**32 - 1, 2**32, 2**70 + 12345, 123456789012345678901234567890, [1, 2, 3], [2**40, 5]])
+def test_spawn_states_vectorised_equals_numpy(seed):
+    """The array implementation of SeedSequence.spawn + PCG64 seeding (squidpy_b200/_rng.py) against numpy objects."""
+    from squidpy_b200._rng import generator_state, spawn_generators, spawn_states
+
+    n = 67
+    exp = np.array([generator_state(g) for g in spawn_generators(seed, n)], dtype=np.uint64)
+    np.testing.assert_array_equal(spawn_states(seed, n), exp)
+    np.testing.assert_array_equal(spawn_states(seed, n, 13, 40), exp[13:40])
+
+
+def test_spawn_states_fresh_entropy():
+    from squidpy_b200._rng import spawn_states
+
+    a, b = spawn_states(None, 4), spawn_states(None, 4)
+    assert a.shape == (4, 6) and not np.array_equal(a, b)  # seed=None draws OS entropy, like the reference

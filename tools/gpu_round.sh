@@ -28,7 +28,7 @@ for st in $STAGES; do
       timeout 900 python tools/tune_nhood.py 1000 > $OUT/tune_nhood.log 2>&1; echo "tune rc=$?" | tee -a $OUT/summary.txt
       cat $OUT/tune_nhood.log | tail -40 ;;
     ncufull)
-      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"nhood_shuffle_warp|nhood_shuffle_cta_kernel|nhood_count_kernel" -c 2 -f -o $OUT/prof_nhood python bench.py --steps 1 --warmup 0 --perms 1000 --skip-cpu --skip-moran > $OUT/ncu_full.log 2>&1; echo "ncu-full nhood rc=$?" | tee -a $OUT/summary.txt
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"nhood_apply_list|nhood_jgen|nhood_shuffle_warp|nhood_count_kernel|nhood_transpose" -c 4 -f -o $OUT/prof_nhood python bench.py --steps 1 --warmup 0 --perms 1000 --skip-cpu --skip-moran > $OUT/ncu_full.log 2>&1; echo "ncu-full nhood rc=$?" | tee -a $OUT/summary.txt
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ac_scatter_kernel|ac_main_kernel" -s 2 -c 2 -f -o $OUT/prof_moran python tools/prof_targets.py moran > $OUT/ncu_moran.log 2>&1; echo "ncu-full moran rc=$?" | tee -a $OUT/summary.txt
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:"pairs_kernel" -c 1 -f -o $OUT/prof_cooc python tools/prof_targets.py cooc > $OUT/ncu_cooc.log 2>&1; echo "ncu-full cooc rc=$?" | tee -a $OUT/summary.txt
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:"pairs_kernel" -c 1 -f -o $OUT/prof_ripley python tools/prof_targets.py ripley > $OUT/ncu_ripley.log 2>&1; echo "ncu-full ripley rc=$?" | tee -a $OUT/summary.txt ;;

@@ -35,13 +35,14 @@ def main():
     ctx.profile(True)
     variants = []
     base = dict(shuffle_algo=1, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_low=0, shuffle_stagger_us=0)
-    # list kernel (algo 6) reference point, then the two-kernel list replay (algo 7): CTA shape x permutations in flight
-    variants.append({**base, "shuffle_algo": 6, "shuffle_threads": 1024, "shuffle_r": 2, "shuffle_wfactor_x100": 1600})
-    for nt, r in ((1024, 4), (1024, 2), (512, 8), (512, 4), (512, 2), (256, 8), (256, 4)):
-        variants.append({**base, "shuffle_algo": 7, "shuffle_threads": nt, "shuffle_r": r})
-    for nt, r in ((1024, 2), (512, 4)):
-        for ctas in (148, 222, 296):
-            variants.append({**base, "shuffle_algo": 7, "shuffle_threads": nt, "shuffle_r": r, "shuffle_ctas": ctas})
+    # two-kernel list replay (algo 7): J generation batch size / window, low part size
+    a7 = {**base, "shuffle_algo": 7, "shuffle_threads": 1024, "shuffle_r": 2, "shuffle_low": 65536}
+    for q in (4, 8, 16):
+        for wf in (400, 1600, 6400):
+            variants.append({**a7, "shuffle_q": q, "shuffle_wfactor_x100": wf})
+    for low in (49152, 81920, 98304):
+        variants.append({**a7, "shuffle_low": low})
+    variants.append({**base, "shuffle_algo": -1})
     for v in variants:
         for k, val in v.items():
             plan.set_option(k, val)
