@@ -1819,7 +1819,7 @@ __global__ void __launch_bounds__(NT) nhood_apply_kernel(LT* __restrict__ labels
 //     (window parity) so that their reset needs no barrier of its own.
 // ------------------------------------------------------------------------------------------------
 template <typename LT, int NT, int SPT>
-__global__ void __launch_bounds__(NT) nhood_apply_list_kernel(LT* __restrict__ labels, const uint32_t* __restrict__ J,
+__global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict__ labels, const uint32_t* __restrict__ J,
                                                               int64_t stride, int64_t n_perms, int nseg,
                                                               const int64_t* __restrict__ seg_start,
                                                               const int64_t* __restrict__ seg_len, uint32_t full_mask,
@@ -1877,8 +1877,11 @@ __global__ void __launch_bounds__(NT) nhood_apply_list_kernel(LT* __restrict__ l
                 uint32_t* s_ohead = s_ohead0 + par * W;
                 par ^= 1;
                 uint32_t jv[SPT];
-                LT vt[SPT], vj[SPT];
+                // original values: the global and the shared-memory (low part) copies are loaded into separate registers
+                // and selected where they are USED, so that nothing waits for the global loads before the list phases
+                LT vtg[SPT], vts[SPT], vjg[SPT], vjs[SPT];
                 uint32_t act = 0, ownm = 0;  // bit m: step tid + m*NT exists / targets the window's own range
+                uint32_t tgm = 0, jgm = 0;   // bit m: top / target of the step lives in global memory (not in the low part)
 #pragma unroll
                 for (int m = 0; m < SPT; ++m) {
                     const int s = tid + m * NT;
@@ -1889,12 +1892,14 @@ __global__ void __launch_bounds__(NT) nhood_apply_list_kernel(LT* __restrict__ l
                     ownm |= (ow ? 1u : 0u) << m;
                     const int xt = i_cur - (ac ? s : 0);
                     const bool tg = ac && xt >= Lc;  // global / shared-memory copy of the position
-                    vt[m] = tg ? ld_cs<LT>(a + base + (tg ? xt : 0)) : (LT)0;
-                    vt[m] = (ac && !tg) ? s_low[tg ? 0 : xt] : vt[m];
+                    vtg[m] = tg ? ld_cs<LT>(a + base + (tg ? xt : 0)) : (LT)0;
+                    vts[m] = (ac && !tg) ? s_low[tg ? 0 : xt] : (LT)0;
                     const bool jo = ac && !ow;
                     const bool jg = jo && (int)jv[m] >= Lc;
-                    vj[m] = jg ? ld_cg<LT>(a + base + (int64_t)(jg ? jv[m] : 0u)) : (LT)0;
-                    vj[m] = (jo && !jg) ? s_low[jg ? 0u : (jo ? jv[m] : 0u)] : vj[m];
+                    vjg[m] = jg ? ld_cg<LT>(a + base + (int64_t)(jg ? jv[m] : 0u)) : (LT)0;
+                    vjs[m] = (jo && !jg) ? s_low[jg ? 0u : (jo ? jv[m] : 0u)] : (LT)0;
+                    tgm |= (tg ? 1u : 0u) << m;
+                    jgm |= (jg ? 1u : 0u) << m;
                 }
                 {  // prefetch the next window's targets (same segment; nothing to fetch after the last window)
                     const int i_nx = i_cur - S;
@@ -1928,7 +1933,7 @@ __global__ void __launch_bounds__(NT) nhood_apply_list_kernel(LT* __restrict__ l
                             s_next[s] = (uint16_t)prev;  // NONE32 truncates to NONE16
                         }
                     }
-                    if ((act >> m) & 1u) s_otop[s] = vt[m];
+                    if ((act >> m) & 1u) s_otop[s] = ((tgm >> m) & 1u) ? vtg[m] : vts[m];
                 }
                 SQB_CONVERGE();
                 __syncthreads();
@@ -1964,13 +1969,30 @@ __global__ void __launch_bounds__(NT) nhood_apply_list_kernel(LT* __restrict__ l
                         slotv[m] = h;
                     }
                 }
-                SQB_CONVERGE();
-                __syncthreads();
-                // ---- C: every step derives what it writes (see 2g) ----
+                // ---- C(fast): a step that is alone on its outside target needs no list of its own: it writes both values
+                //      now (all original values were read before the first barrier; the own-range lists T() walks are
+                //      complete), while the few slow steps are still building theirs ----
 #pragma unroll
                 for (int m = 0; m < SPT; ++m) {
                     const int s = tid + m * NT;
-                    if ((act >> m) & 1u) {
+                    const bool fast = ((act >> m) & 1u) && !((ownm >> m) & 1u) && !((slowm >> m) & 1u);
+                    if (fast) {
+                        const uint32_t j = jv[m];
+                        const LT val = ((jgm >> m) & 1u) ? vjg[m] : vjs[m];
+                        const LT tv = sqb_list_T<LT>(s_ohead, s_next, s_otop, s);
+                        if ((int)j < Lc) s_low[j] = tv;
+                        else a[base + (int64_t)j] = tv;
+                        if (i_cur - s < Lc) s_low[i_cur - s] = val;
+                        else st_cs<LT>(a + base + (i_cur - s), val);  // final position: never read again by this kernel
+                    }
+                }
+                SQB_CONVERGE();
+                __syncthreads();
+                // ---- C(slow): own-range targets and steps of multiply-hit buckets derive what they write (see 2g) ----
+#pragma unroll
+                for (int m = 0; m < SPT; ++m) {
+                    const int s = tid + m * NT;
+                    if (((act >> m) & 1u) && (((ownm | slowm) >> m) & 1u)) {
                         const uint32_t j = jv[m];
                         LT val;
                         if ((ownm >> m) & 1u) {
@@ -1982,21 +2004,16 @@ __global__ void __launch_bounds__(NT) nhood_apply_list_kernel(LT* __restrict__ l
                                 const int p = sqb_list_latest_before(s_next, s_ohead[u], s, &mx);
                                 val = (p >= 0) ? sqb_list_T<LT>(s_ohead, s_next, s_otop, p) : s_otop[u];
                             }
-                        } else if ((slowm >> m) & 1u) {
+                        } else {
                             const uint32_t head = (uint32_t)s_tab[slotv[m]] & 0xFFFFu;
                             int mx;
                             const int p = sqb_list_latest_before(s_next, head, s, &mx);
-                            val = (p >= 0) ? sqb_list_T<LT>(s_ohead, s_next, s_otop, p) : vj[m];
+                            val = (p >= 0) ? sqb_list_T<LT>(s_ohead, s_next, s_otop, p) : (((jgm >> m) & 1u) ? vjg[m] : vjs[m]);
                             if (mx == s) {
                                 const LT tv = sqb_list_T<LT>(s_ohead, s_next, s_otop, s);
                                 if ((int)j < Lc) s_low[j] = tv;
                                 else a[base + (int64_t)j] = tv;
                             }
-                        } else {  // the only step of this window that touches position j
-                            val = vj[m];
-                            const LT tv = sqb_list_T<LT>(s_ohead, s_next, s_otop, s);
-                            if ((int)j < Lc) s_low[j] = tv;
-                            else a[base + (int64_t)j] = tv;
                         }
                         if (i_cur - s < Lc) s_low[i_cur - s] = val;
                         else st_cs<LT>(a + base + (i_cur - s), val);  // final position: never read again by this kernel
