@@ -16,6 +16,8 @@
 //   4. nhood_count         CSR neighbour-pair histogram: lane = permutation, warp walks the CSR once for 32
 //                          permutations; lane-private shared-memory histogram columns (bank = lane, no
 //                          conflicts), one flush per CTA.
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 #include "pcg64_jump.h"
 
@@ -2085,11 +2087,65 @@ __global__ void nhood_u32_to_lt_kernel(const uint32_t* __restrict__ src, LT* __r
 }
 
 // ------------------------------------------------------------------------------------------------
+// 3b. Symmetric graphs (what spatial_neighbors builds for grids and Delaunay graphs): when every stored entry (i -> j) has
+//     exactly one mirror (j -> i) and no row holds a column twice, the count of all stored entries equals, per unordered
+//     pair {i, j}: +1 on (l_i, l_j) and +1 on (l_j, l_i), and +1 on (l_i, l_i) per self loop.  The count kernel then walks
+//     only the entries with j >= i: half the index and label loads for the same atomics.  The check and the upper CSR are
+//     built once per graph on the device; anything else (kNN graphs, duplicates, rows longer than 64) keeps the full CSR.
+// ------------------------------------------------------------------------------------------------
+__global__ void nhood_symcheck_kernel(const uint32_t* __restrict__ indptr, const uint32_t* __restrict__ indices, int64_t n,
+                                      uint32_t* __restrict__ flag, uint32_t* __restrict__ upper_cnt) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) {
+        upper_cnt[n] = 0;
+        return;
+    }
+    const uint32_t b = indptr[i], e = indptr[i + 1];
+    bool bad = (e < b) || (e - b > 64u);
+    uint32_t up = 0;
+    if (!bad) {
+        for (uint32_t k = b; k < e; ++k) {
+            const uint32_t j = indices[k];
+            if ((int64_t)j >= n) {
+                bad = true;
+                break;
+            }
+            up += (j >= (uint32_t)i) ? 1u : 0u;
+            for (uint32_t k2 = k + 1; k2 < e; ++k2) bad |= (indices[k2] == j);
+            if (j != (uint32_t)i) {
+                const uint32_t jb = indptr[j], je = indptr[j + 1];
+                if (je < jb || je - jb > 64u) {
+                    bad = true;
+                } else {
+                    uint32_t c = 0;
+                    for (uint32_t t = jb; t < je; ++t) c += (indices[t] == (uint32_t)i) ? 1u : 0u;
+                    bad |= (c != 1u);
+                }
+            }
+        }
+    }
+    upper_cnt[i] = up;
+    if (bad) atomicOr(flag, 1u);
+}
+
+__global__ void nhood_upper_fill_kernel(const uint32_t* __restrict__ indptr, const uint32_t* __restrict__ indices, int64_t n,
+                                        const uint32_t* __restrict__ uptr, uint32_t* __restrict__ uidx) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w = uptr[i];
+    for (uint32_t k = indptr[i]; k < indptr[i + 1]; ++k) {
+        const uint32_t j = indices[k];
+        if (j >= (uint32_t)i) uidx[w++] = j;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 4. count: hist[(a*C+b)*G + perm_in_group] over the nodes of this CTA's chunk.
 //    G = permutations per CTA; lane = (edge slot = lane / G, perm = lane % G).  With G = 32 every lane owns
 //    its own histogram column (bank == lane): shared-memory atomics never conflict inside a warp.
 // ------------------------------------------------------------------------------------------------
-template <typename LT, int G>
+template <typename LT, int G, bool SYM>
 __global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
                                                            const LT* __restrict__ labT, int PB, int64_t n, int C,
                                                            int64_t nodes_per_cta, int P, uint32_t* __restrict__ counts) {
@@ -2115,6 +2171,7 @@ __global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __res
         uint32_t* __restrict__ myhist = hist + lane;
         for (uint32_t i0 = nb32 + (uint32_t)warp * UN; i0 < ne32; i0 += (uint32_t)nwarps * UN) {
             uint32_t beg[UN], deg[UN], rowb[UN];
+            uint32_t rowa[UN];  // SYM: label of the row itself, for the mirrored increment (b, a)
             uint32_t maxdeg = 0, mindeg = 0xFFFFFFFFu;
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
@@ -2122,10 +2179,12 @@ __global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __res
                 beg[u] = 0;
                 deg[u] = 0;
                 rowb[u] = 0;
+                rowa[u] = 0;
                 if (i < ne32) {
                     beg[u] = indptr[i];
                     deg[u] = indptr[i + 1] - beg[u];
-                    rowb[u] = (uint32_t)col[(uint64_t)i * PBu] * Cu;
+                    rowa[u] = (uint32_t)col[(uint64_t)i * PBu];
+                    rowb[u] = rowa[u] * Cu;
                 }
                 maxdeg = deg[u] > maxdeg ? deg[u] : maxdeg;
                 mindeg = deg[u] < mindeg ? deg[u] : mindeg;
@@ -2141,6 +2200,11 @@ __global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __res
                 for (int u = 0; u < UN; ++u) bl[u] = (uint32_t)col[(uint64_t)j[u] * PBu];
 #pragma unroll
                 for (int u = 0; u < UN; ++u) atomicAdd(myhist + (rowb[u] + bl[u]) * 32u, 1u);
+                if (SYM) {  // mirrored entry of every j > i (j == i, a self loop, is stored once); the test is warp uniform
+#pragma unroll
+                    for (int u = 0; u < UN; ++u)
+                        if (j[u] != i0 + u) atomicAdd(myhist + (bl[u] * Cu + rowa[u]) * 32u, 1u);
+                }
             }
             for (; k < maxdeg; ++k) {
 #pragma unroll
@@ -2149,6 +2213,7 @@ __global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __res
                         const uint32_t j = indices[beg[u] + k];
                         const uint32_t bl = (uint32_t)col[(uint64_t)j * PBu];
                         atomicAdd(myhist + (rowb[u] + bl) * 32u, 1u);
+                        if (SYM && j != i0 + u) atomicAdd(myhist + (bl * Cu + rowa[u]) * 32u, 1u);
                     }
                 }
             }
@@ -2212,6 +2277,9 @@ struct sqb_nhood {
     int n_cls = 0;
     int lt_bytes = 1;  // 1: uint8 labels (n_cls <= 256), 2: uint16
     DevBuf<uint32_t> d_indptr, d_indices;
+    DevBuf<uint32_t> d_uptr, d_uidx;  // entries with j >= i of a symmetric graph (see 3b), else unused
+    bool sym = false;
+    int count_sym = -1;  // -1 auto (use the upper CSR when the graph is symmetric), 0 = always the full CSR
     DevBuf<uint8_t> d_base;   // stride * lt_bytes, library-grouped order
     DevBuf<uint32_t> d_order;  // grouped position -> node id (only with libraries)
     bool has_order = false;
@@ -2273,11 +2341,18 @@ static int launch_count(sqb_nhood* h, const LT* labT, int PB, int P, uint32_t* d
     const int threads = smem > 100 * 1024 ? 1024 : 512;
 #define SQB_COUNT_CASE(GV)                                                                                        \
     case GV: {                                                                                                    \
-        auto k = nhood_count_kernel<LT, GV>;                                                                      \
+        auto k = nhood_count_kernel<LT, GV, false>;                                                               \
         SQB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
         k<<<grid, threads, smem, c->stream>>>(h->d_indptr.p, h->d_indices.p, labT, PB, h->n, C, nodes_per_cta, P, \
                                               d_counts);                                                          \
     } break;
+    if (G == 32 && h->sym && h->count_sym != 0) {  // symmetric graph: walk the entries with j >= i only
+        auto k = nhood_count_kernel<LT, 32, true>;
+        SQB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, threads, smem, c->stream>>>(h->d_uptr.p, h->d_uidx.p, labT, PB, h->n, C, nodes_per_cta, P, d_counts);
+        SQB_POST_LAUNCH();
+        return SQB_OK;
+    }
     switch (G) {
         SQB_COUNT_CASE(32)
         SQB_COUNT_CASE(16)
@@ -2614,6 +2689,8 @@ int sqb_nhood_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const uint32_t* indpt
     // all handle buffers are allocated, used and freed in ctx->stream order
     h->d_indptr.bind(ctx->stream);
     h->d_indices.bind(ctx->stream);
+    h->d_uptr.bind(ctx->stream);
+    h->d_uidx.bind(ctx->stream);
     h->d_base.bind(ctx->stream);
     h->d_order.bind(ctx->stream);
     h->d_seg_start.bind(ctx->stream);
@@ -2634,6 +2711,56 @@ int sqb_nhood_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const uint32_t* indpt
     SQB_CUDA(cudaMemcpyAsync(h->d_indptr.p, indptr, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     if (nnz > 0)
         SQB_CUDA(cudaMemcpyAsync(h->d_indices.p, indices, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    // symmetric structure? then keep the entries with j >= i as a second CSR (3b)
+    if (nnz > 0) {
+        DevBuf<uint32_t> flag, ucnt;
+        DevBuf<uint8_t> tmp;
+        flag.bind(ctx->stream);
+        ucnt.bind(ctx->stream);
+        tmp.bind(ctx->stream);
+        uint32_t hflag = 1;
+        auto cleanup = [&]() {
+            flag.release();
+            ucnt.release();
+            tmp.release();
+        };
+        rc = flag.alloc(1);
+        if (rc == SQB_OK) rc = ucnt.alloc(n + 1);
+        if (rc == SQB_OK) rc = h->d_uptr.alloc(n + 1);
+        size_t tmp_bytes = 0;
+        if (rc == SQB_OK) {
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ucnt.p, h->d_uptr.p, (int)(n + 1), ctx->stream);
+            rc = tmp.alloc(tmp_bytes > 0 ? tmp_bytes : 1);
+        }
+        if (rc != SQB_OK) {
+            cleanup();
+            sqb_nhood_destroy(h);
+            return rc;
+        }
+        cudaMemsetAsync(flag.p, 0, sizeof(uint32_t), ctx->stream);
+        nhood_symcheck_kernel<<<(unsigned)ceil_div64(n + 1, 256), 256, 0, ctx->stream>>>(h->d_indptr.p, h->d_indices.p, n, flag.p, ucnt.p);
+        cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, ucnt.p, h->d_uptr.p, (int)(n + 1), ctx->stream);
+        cudaMemcpyAsync(&hflag, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess && hflag == 0) {
+            uint32_t total = 0;
+            cudaMemcpyAsync(&total, h->d_uptr.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+            e = cudaStreamSynchronize(ctx->stream);
+            if (e == cudaSuccess && (rc = h->d_uidx.alloc(total > 0 ? total : 1)) == SQB_OK) {
+                nhood_upper_fill_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(h->d_indptr.p, h->d_indices.p, n,
+                                                                                              h->d_uptr.p, h->d_uidx.p);
+                e = cudaStreamSynchronize(ctx->stream);
+                h->sym = (e == cudaSuccess);
+            }
+        }
+        cleanup();
+        if (e != cudaSuccess || rc != SQB_OK) {
+            if (e != cudaSuccess) sqb_set_error("sqb_nhood_create: symmetric-graph preparation failed: %s", cudaGetErrorString(e));
+            sqb_nhood_destroy(h);
+            return e != cudaSuccess ? SQB_ERR_CUDA : rc;
+        }
+        if (!h->sym) h->d_uptr.release();
+    }
     SQB_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = h;
     return SQB_OK;
@@ -2644,6 +2771,8 @@ int sqb_nhood_destroy(sqb_nhood* h) {
     cudaSetDevice(h->ctx->device);
     h->d_indptr.release();
     h->d_indices.release();
+    h->d_uptr.release();
+    h->d_uidx.release();
     h->d_base.release();
     h->d_order.release();
     h->d_seg_start.release();
@@ -2660,6 +2789,9 @@ int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value) {
     if (!strcmp(key, "shuffle_algo")) {
         SQB_CHECK(value >= -1 && value <= 7, SQB_ERR_INVALID, "shuffle_algo must be -1 (auto) or 0..7");
         h->shuffle_algo = (int)value;
+    } else if (!strcmp(key, "count_sym")) {
+        SQB_CHECK(value == -1 || value == 0, SQB_ERR_INVALID, "count_sym must be -1 (auto) or 0 (full CSR)");
+        h->count_sym = (int)value;
     } else if (!strcmp(key, "shuffle_stagger_us")) {
         SQB_CHECK(value >= 0 && value <= 1000000, SQB_ERR_INVALID, "shuffle_stagger_us must be in [0, 1e6]");
         h->shuffle_stagger_us = value;

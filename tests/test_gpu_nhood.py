@@ -50,6 +50,51 @@ def test_count_directed_selfloops_empty_rows():
     np.testing.assert_array_equal(_plan(empty, 2).count(np.array([0, 1, 0, 1, 1])), np.zeros((2, 2), np.uint32))
 
 
+@pytest.mark.parametrize("kind", ["hex", "sym_selfloops_unsorted", "knn_directed", "duplicates", "one_missing_mirror", "long_rows"])
+def test_count_symmetric_shortcut(kind):
+    """Symmetric graphs are counted from the entries with j >= i (each unordered pair once, mirrored increment); anything
+    that is not a simple symmetric structure keeps the full CSR.  Both must equal the oracle, observed and permuted."""
+    rng = np.random.default_rng(5)
+    if kind == "hex":
+        g = synth.hex_graph(47, 39)
+    elif kind == "sym_selfloops_unsorted":
+        a = sp.random(2500, 2500, density=0.003, format="csr", random_state=2, dtype=np.float32)
+        g = ((a + a.T) > 0).astype(np.float32) + sp.diags((rng.random(2500) < 0.4).astype(np.float32))
+        g = g.tocsr()
+        g.eliminate_zeros()
+        for i in range(g.shape[0]):  # unsorted column order inside the rows
+            b, e = g.indptr[i], g.indptr[i + 1]
+            g.indices[b:e] = rng.permutation(g.indices[b:e])
+    elif kind == "knn_directed":
+        g = synth.knn_graph(rng.random((3000, 2)), 6)
+    elif kind == "duplicates":
+        base = synth.hex_graph(20, 20).tocoo()
+        row, col = np.concatenate([base.row, base.row[:50]]), np.concatenate([base.col, base.col[:50]])
+        order = np.argsort(row, kind="stable")
+        indptr = np.concatenate([[0], np.cumsum(np.bincount(row, minlength=400))])
+        g = sp.csr_matrix((np.ones(row.size, np.float32), col[order].astype(np.int32), indptr.astype(np.int32)), shape=(400, 400))
+    elif kind == "one_missing_mirror":
+        g = synth.hex_graph(30, 30).tolil()
+        g[17, 18] = 0
+        g = g.tocsr()
+        g.eliminate_zeros()
+    else:  # symmetric, but rows longer than the 64 entries the check accepts
+        a = sp.random(600, 600, density=0.2, format="csr", random_state=3, dtype=np.float32)
+        g = ((a + a.T) > 0).astype(np.float32).tocsr()
+    n = g.shape[0]
+    n_cls = 11
+    lab = rng.integers(0, n_cls, n).astype(np.uint32)
+    exp = ref.nhood_count(g.indptr, g.indices, lab, n_cls)
+    st = spawn_states(3, 40)
+    exp_perm = ref.nhood_perm_counts(g.indptr, g.indices, lab, n_cls, st)
+    for count_sym in (-1, 0):
+        plan = _plan(g, n_cls)
+        plan.set_option("count_sym", count_sym)
+        np.testing.assert_array_equal(plan.count(lab), exp)
+        plan.set_base(lab)
+        np.testing.assert_array_equal(plan.permute(st), exp_perm)
+
+
 def test_create_errors():
     with pytest.raises(ValueError, match="Expected at least `2` clusters, found `1`"):
         NhoodPlan(np.array([0, 1]), np.array([0]), 1)
