@@ -1817,15 +1817,16 @@ __global__ void __launch_bounds__(NT) nhood_apply_kernel(LT* __restrict__ labels
 //     memory, "seen" and "seen again", set with one atomicOr per step (independent across the steps of a thread).  After a
 //     barrier a step whose bucket was not seen again is alone on its target: it writes the two values without touching
 //     any list.  Only the steps of multiply-hit buckets (a few percent, false positives included) and the own-range
-//     targets build lists.  Three barriers per window; filter, hash table and own-range heads are double buffered
-//     (window parity) so that their reset needs no barrier of its own.
+//     targets build lists.  Marking a window needs nothing but its targets, so window w+1 is marked while window w is
+//     resolved: TWO barriers per window (lists complete -> resolve + mark next -> reset); filter, hash table, own-range
+//     heads and links are double buffered (window parity) so that neither the overlap nor the reset needs a barrier.
 // ------------------------------------------------------------------------------------------------
 template <typename LT, int NT, int SPT>
 __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict__ labels, const uint32_t* __restrict__ J,
-                                                              int64_t stride, int64_t n_perms, int nseg,
-                                                              const int64_t* __restrict__ seg_start,
-                                                              const int64_t* __restrict__ seg_len, uint32_t full_mask,
-                                                              uint64_t stagger_ns, int low_cap) {
+                                                                 int64_t stride, int64_t n_perms, int nseg,
+                                                                 const int64_t* __restrict__ seg_start,
+                                                                 const int64_t* __restrict__ seg_len, uint32_t full_mask,
+                                                                 uint64_t stagger_ns, int low_cap) {
     // low_cap > 0: positions [0, min(low_cap, segment length)) of the current segment live in shared memory during the
     // replay.  The kernel is bound by the SM's rate of UNCOALESCED global requests (one random byte load and one random
     // byte store per step, ~1.8 cycles each, tools/micro/rmw_bench.cu); targets are uniform in [0, i], so a low part of
@@ -1838,11 +1839,14 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict_
     static_assert(W < 0xFFFF, "step indices are stored in 16 bits");
     constexpr int HS_SHIFT = 32 - LOG_HS;
     extern __shared__ __align__(16) unsigned char sqb_shuffle_smem[];
+    // Everything a window's lists live in is DOUBLE BUFFERED by window parity: window w+1 is marked (filter bits, own-range
+    // list pushes) while window w is still being resolved, and the entries of window w are reset after its last barrier,
+    // ordered before their reuse by window w+2 through the barriers of window w+1.
     unsigned long long* s_tab0 = reinterpret_cast<unsigned long long*>(sqb_shuffle_smem);  // [2][HS] (target << 32) | list head
     uint32_t* s_bits0 = reinterpret_cast<uint32_t*>(s_tab0 + 2 * HS);                        // [2][NWB] duplicate filter
     uint32_t* s_ohead0 = s_bits0 + 2 * NWB;                                                  // [2][W] own-range list heads
-    uint16_t* s_next = reinterpret_cast<uint16_t*>(s_ohead0 + 2 * W);                        // [W] list links
-    LT* s_otop = reinterpret_cast<LT*>(s_next + W);                                          // [W] original own-range values
+    uint16_t* s_next0 = reinterpret_cast<uint16_t*>(s_ohead0 + 2 * W);                       // [2][W] list links
+    LT* s_otop = reinterpret_cast<LT*>(s_next0 + 2 * W);                                     // [W] original own-range values
     LT* s_low = s_otop + W;                                                                  // [low_cap] low part of the segment
     const int tid = threadIdx.x;
     for (int h = tid; h < 2 * HS; h += NT) s_tab0[h] = SQB_EMPTY64;
@@ -1852,6 +1856,38 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict_
     sqb_stagger(stagger_ns * blockIdx.x / gridDim.x);
     __syncthreads();
 
+    // filter marking + own-range list pushes of one window (targets jm[], S_m steps from top i_m) into the tables of parity q
+    auto mark = [&](const uint32_t (&jm)[SPT], int S_m, int i_m, int q) {
+        uint32_t* bits = s_bits0 + q * NWB;
+        uint32_t* ohead = s_ohead0 + q * W;
+        uint16_t* next = s_next0 + q * W;
+        const int lo_m = i_m - S_m;
+        uint32_t old[SPT];
+#pragma unroll
+        for (int m = 0; m < SPT; ++m) {
+            const int s = tid + m * NT;
+            const bool out = (s < S_m) && !((int)jm[m] > lo_m);
+            const uint32_t j = jm[m];
+            old[m] = out ? atomicOr(&bits[(j >> 4) & (NWB - 1)], 1u << ((j & 15u) * 2u)) : 0u;
+        }
+#pragma unroll
+        for (int m = 0; m < SPT; ++m) {
+            const int s = tid + m * NT;
+            const uint32_t j = jm[m];
+            const bool ac = s < S_m;
+            const bool ow = ac && ((int)j > lo_m);
+            const uint32_t sh = (j & 15u) * 2u;
+            if (ac && !ow && ((old[m] >> sh) & 1u)) atomicOr(&bits[(j >> 4) & (NWB - 1)], 2u << sh);  // seen again
+            if (ow) {
+                const int u = i_m - (int)j;  // u >= s
+                if (u != s) {
+                    const uint32_t prev = atomicExch(&ohead[u], (uint32_t)s);
+                    next[s] = (uint16_t)prev;  // NONE32 truncates to NONE16
+                }
+            }
+        }
+    };
+
     for (int64_t perm = blockIdx.x; perm < n_perms; perm += gridDim.x) {
         LT* __restrict__ a = labels + perm * stride;
         const uint32_t* __restrict__ Jp = J + perm * stride;
@@ -1860,25 +1896,29 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict_
             int i_cur = (int)(seg_len[seg] - 1);  // n < 2^31
             const int Lc = min(low_cap, i_cur + 1);
             for (int x = tid; x < Lc; x += NT) s_low[x] = a[base + x];
-            __syncthreads();
-            uint32_t jn[SPT];                      // targets of the coming window (prefetched)
+            uint32_t jv[SPT], jn[SPT];  // targets of the current and of the next window
             {
                 const int S0 = min(W, i_cur);
+                const int i1 = i_cur - S0;
+                const int S1 = min(W, i1);
 #pragma unroll
                 for (int m = 0; m < SPT; ++m) {
                     const int s = tid + m * NT;
-                    const bool ac = s < S0;
-                    jn[m] = ac ? __ldcs(Jp + base + (i_cur - (ac ? s : 0))) : 0u;
+                    const bool a0 = s < S0, a1 = s < S1;
+                    jv[m] = a0 ? __ldcs(Jp + base + (i_cur - (a0 ? s : 0))) : 0u;
+                    jn[m] = a1 ? __ldcs(Jp + base + (i1 - (a1 ? s : 0))) : 0u;
                 }
+                mark(jv, S0, i_cur, par);
             }
+            SQB_CONVERGE();
+            __syncthreads();
             while (i_cur >= 1) {
                 const int S = min(W, i_cur);  // steps i_cur, i_cur-1, ..., i_cur-S+1 (>= 1)
                 const int own_lo = i_cur - S;
                 unsigned long long* s_tab = s_tab0 + par * HS;
                 uint32_t* s_bits = s_bits0 + par * NWB;
                 uint32_t* s_ohead = s_ohead0 + par * W;
-                par ^= 1;
-                uint32_t jv[SPT];
+                uint16_t* s_next = s_next0 + par * W;
                 // original values: the global and the shared-memory (low part) copies are loaded into separate registers
                 // and selected where they are USED, so that nothing waits for the global loads before the list phases
                 LT vtg[SPT], vts[SPT], vjg[SPT], vjs[SPT];
@@ -1888,7 +1928,6 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict_
                 for (int m = 0; m < SPT; ++m) {
                     const int s = tid + m * NT;
                     const bool ac = s < S;
-                    jv[m] = jn[m];
                     const bool ow = ac && ((int)jv[m] > own_lo);
                     act |= (ac ? 1u : 0u) << m;
                     ownm |= (ow ? 1u : 0u) << m;
@@ -1903,43 +1942,22 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict_
                     tgm |= (tg ? 1u : 0u) << m;
                     jgm |= (jg ? 1u : 0u) << m;
                 }
-                {  // prefetch the next window's targets (same segment; nothing to fetch after the last window)
-                    const int i_nx = i_cur - S;
-                    const int S_nx = min(W, i_nx);
+                // prefetch the targets of the window after the next one (same segment)
+                const int i_nx = i_cur - S;
+                const int S_nx = min(W, i_nx);
+                uint32_t jnn[SPT];
+                {
+                    const int i_n2 = i_nx - max(S_nx, 0);
+                    const int S_n2 = min(W, i_n2);
 #pragma unroll
                     for (int m = 0; m < SPT; ++m) {
                         const int s = tid + m * NT;
-                        const bool ac = s < S_nx;
-                        jn[m] = ac ? __ldcs(Jp + base + (i_nx - (ac ? s : 0))) : 0u;
+                        const bool ac = s < S_n2;
+                        jnn[m] = ac ? __ldcs(Jp + base + (i_n2 - (ac ? s : 0))) : 0u;
                     }
                 }
-                // ---- B1: duplicate filter for outside targets, list push for own-range targets ----
-                uint32_t old[SPT];
-#pragma unroll
-                for (int m = 0; m < SPT; ++m) {
-                    const bool out = ((act >> m) & 1u) && !((ownm >> m) & 1u);
-                    const uint32_t j = jv[m];
-                    old[m] = out ? atomicOr(&s_bits[(j >> 4) & (NWB - 1)], 1u << ((j & 15u) * 2u)) : 0u;
-                }
-#pragma unroll
-                for (int m = 0; m < SPT; ++m) {
-                    const int s = tid + m * NT;
-                    const bool out = ((act >> m) & 1u) && !((ownm >> m) & 1u);
-                    const uint32_t j = jv[m];
-                    const uint32_t sh = (j & 15u) * 2u;
-                    if (out && ((old[m] >> sh) & 1u)) atomicOr(&s_bits[(j >> 4) & (NWB - 1)], 2u << sh);  // seen again
-                    if ((ownm >> m) & 1u) {
-                        const int u = i_cur - (int)j;  // u >= s
-                        if (u != s) {
-                            const uint32_t prev = atomicExch(&s_ohead[u], (uint32_t)s);
-                            s_next[s] = (uint16_t)prev;  // NONE32 truncates to NONE16
-                        }
-                    }
-                    if ((act >> m) & 1u) s_otop[s] = ((tgm >> m) & 1u) ? vtg[m] : vts[m];
-                }
-                SQB_CONVERGE();
-                __syncthreads();
-                // ---- B2: steps of multiply-hit buckets build per-target lists in the hash table ----
+                // ---- B: steps of multiply-hit buckets build per-target lists in the hash table (this window was marked
+                //      during the previous one); stage the original own-range values ----
                 uint32_t slowm = 0;
                 uint32_t slotv[SPT];
 #pragma unroll
@@ -1971,31 +1989,20 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict_
                         slotv[m] = h;
                     }
                 }
-                // ---- C(fast): a step that is alone on its outside target needs no list of its own: it writes both values
-                //      now (all original values were read before the first barrier; the own-range lists T() walks are
-                //      complete), while the few slow steps are still building theirs ----
 #pragma unroll
                 for (int m = 0; m < SPT; ++m) {
                     const int s = tid + m * NT;
-                    const bool fast = ((act >> m) & 1u) && !((ownm >> m) & 1u) && !((slowm >> m) & 1u);
-                    if (fast) {
-                        const uint32_t j = jv[m];
-                        const LT val = ((jgm >> m) & 1u) ? vjg[m] : vjs[m];
-                        const LT tv = sqb_list_T<LT>(s_ohead, s_next, s_otop, s);
-                        if ((int)j < Lc) s_low[j] = tv;
-                        else a[base + (int64_t)j] = tv;
-                        if (i_cur - s < Lc) s_low[i_cur - s] = val;
-                        else st_cs<LT>(a + base + (i_cur - s), val);  // final position: never read again by this kernel
-                    }
+                    if ((act >> m) & 1u) s_otop[s] = ((tgm >> m) & 1u) ? vtg[m] : vts[m];
                 }
                 SQB_CONVERGE();
                 __syncthreads();
-                // ---- C(slow): own-range targets and steps of multiply-hit buckets derive what they write (see 2g) ----
+                // ---- C: every step derives what it writes from the (now immutable) lists, original values only (2g) ----
 #pragma unroll
                 for (int m = 0; m < SPT; ++m) {
                     const int s = tid + m * NT;
-                    if (((act >> m) & 1u) && (((ownm | slowm) >> m) & 1u)) {
+                    if ((act >> m) & 1u) {
                         const uint32_t j = jv[m];
+                        const LT vj = ((jgm >> m) & 1u) ? vjg[m] : vjs[m];
                         LT val;
                         if ((ownm >> m) & 1u) {
                             const int u = i_cur - (int)j;
@@ -2007,11 +2014,16 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict_
                                 val = (p >= 0) ? sqb_list_T<LT>(s_ohead, s_next, s_otop, p) : s_otop[u];
                             }
                         } else {
-                            const uint32_t head = (uint32_t)s_tab[slotv[m]] & 0xFFFFu;
-                            int mx;
-                            const int p = sqb_list_latest_before(s_next, head, s, &mx);
-                            val = (p >= 0) ? sqb_list_T<LT>(s_ohead, s_next, s_otop, p) : (((jgm >> m) & 1u) ? vjg[m] : vjs[m]);
-                            if (mx == s) {
+                            bool last = true;  // the only (or the last) step of this window that touches position j
+                            val = vj;
+                            if ((slowm >> m) & 1u) {
+                                const uint32_t head = (uint32_t)s_tab[slotv[m]] & 0xFFFFu;
+                                int mx;
+                                const int p = sqb_list_latest_before(s_next, head, s, &mx);
+                                if (p >= 0) val = sqb_list_T<LT>(s_ohead, s_next, s_otop, p);
+                                last = (mx == s);
+                            }
+                            if (last) {
                                 const LT tv = sqb_list_T<LT>(s_ohead, s_next, s_otop, s);
                                 if ((int)j < Lc) s_low[j] = tv;
                                 else a[base + (int64_t)j] = tv;
@@ -2021,6 +2033,8 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict_
                         else st_cs<LT>(a + base + (i_cur - s), val);  // final position: never read again by this kernel
                     }
                 }
+                // ---- mark the next window in the other copy of the tables (needs nothing but its targets) ----
+                mark(jn, S_nx, i_nx, par ^ 1);
                 SQB_CONVERGE();
                 __syncthreads();
                 // ---- reset this window's copy of the tables (ordered before its reuse by the next window's barriers) ----
@@ -2032,7 +2046,13 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict_
                     if (ac && !ow) s_bits[(j >> 4) & (NWB - 1)] = 0u;
                     if (sl) s_tab[slotv[m]] = SQB_EMPTY64;
                 }
-                i_cur -= S;
+#pragma unroll
+                for (int m = 0; m < SPT; ++m) {
+                    jv[m] = jn[m];
+                    jn[m] = jnn[m];
+                }
+                i_cur = i_nx;
+                par ^= 1;
             }
             __syncthreads();
             for (int x = tid; x < Lc; x += NT) a[base + x] = s_low[x];
@@ -2465,8 +2485,8 @@ static int launch_apply_list(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t n
     sqb_ctx* c = h->ctx;
     auto k = nhood_apply_list_kernel<LT, NT, SPT>;
     constexpr size_t W = (size_t)NT * SPT, HS = W, NWB = 2 * W;
-    // [tab u64 x 2*HS][bits u32 x 2*NWB][ohead u32 x 2*W][next u16 x W][otop LT x W]
-    const size_t tables = 2 * HS * 8 + 2 * NWB * 4 + 2 * W * 4 + W * 2 + W * sizeof(LT);
+    // [tab u64 x 2*HS][bits u32 x 2*NWB][ohead u32 x 2*W][next u16 x 2*W][otop LT x W]
+    const size_t tables = 2 * HS * 8 + 2 * NWB * 4 + 2 * W * 4 + 2 * W * 2 + W * sizeof(LT);
     SQB_CHECK(tables <= c->smem_optin, SQB_ERR_UNSUPPORTED, "shuffle_algo 7: %zu bytes of shared memory exceed the device limit", tables);
     // shared-memory resident low part (low: -1 = everything the SM has left, 0 = off, > 0 = at most that many elements)
     int64_t low_cap = 0;
