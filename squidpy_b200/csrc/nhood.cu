@@ -3,19 +3,20 @@
 // Replaces the reference's per-permutation CPU loop (src/squidpy/gr/_nhood.py:516-547): for every permutation
 //   shuffled = base.copy(); rng_p.shuffle(shuffled)        (numpy PCG64 Generator.shuffle, replayed bit-exactly)
 //   perms[p] = count(indices, indptr, shuffled)            (_nenrich kernel, _nhood.py:54-141)
-// with four kernels per chunk of permutations, all integer / byte work (HBM + shared-memory bound, no tensor
+// with five kernels per chunk of permutations, all integer / byte work (HBM, L2 and shared-memory bound, no tensor
 // cores):
 //   1. nhood_fill          broadcast the base labels into one row per permutation            [P][stride]
-//   2. nhood_shuffle_cta   ONE CTA PER PERMUTATION replays Generator.shuffle exactly: the PCG64 stream is
-//                          produced in parallel by jump-ahead (one 64-bit output per thread per batch), masked
-//                          rejection sampling is resolved with ballots + a block prefix sum, and the resulting
-//                          batch of Fisher-Yates swaps is applied in parallel after shared-memory conflict
-//                          detection (conflicting swaps are replayed in order by one thread on the staged
-//                          values).  RNG state and all reductions live in registers / shared memory.
+//   2. nhood_jgen          one WARP per permutation replays the PCG64 stream (jump-ahead, one 64-bit output per lane
+//                          and batch) and numpy's masked rejection sampling (ballots + prefix sums) and streams the
+//                          Fisher-Yates target of every step to J[P][stride]
+//      nhood_apply_list    one CTA per permutation applies the swaps in 2048-step windows: 2-bit duplicate filter,
+//                          per-position lists instead of an ordered replay of conflicting swaps, low part of the array in
+//                          shared memory, next window marked while the current one is resolved (sections 2f-2h; 2a-2e
+//                          are the earlier, bit-identical variants kept as options and cross-checks)
 //   3. nhood_transpose     [P][n] -> [n][PB] (permutation-minor) so that one warp lane = one permutation
 //   4. nhood_count         CSR neighbour-pair histogram: lane = permutation, warp walks the CSR once for 32
 //                          permutations; lane-private shared-memory histogram columns (bank = lane, no
-//                          conflicts), one flush per CTA.
+//                          conflicts), one flush per CTA; symmetric graphs are walked over j >= i only (3b).
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
@@ -2561,10 +2562,10 @@ static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t
         return launch_shuffle_two_kernel<LT>(h, lab, states, np, h->shuffle_algo, h->shuffle_threads, h->shuffle_r, h->shuffle_low);
     // auto (measured on B200, 1000 x 1M: two-kernel list replay 23 ms, warp per permutation 39 ms, CTA per permutation
     // 42 ms): many permutations of large arrays -> J generation + list apply with the tuned shape (1024 threads, 2048-step
-    // windows, 64 K elements of every array in shared memory); few permutations -> one CTA each (finishes sooner);
+    // windows, 96 K elements of every array in shared memory); few permutations -> one CTA each (finishes sooner);
     // many permutations of small arrays (L1/L2 resident) -> one warp each
     if (h->shuffle_algo < 0 && np > 2 * (int64_t)c->sm_count && h->n >= 65536)
-        return launch_shuffle_two_kernel<LT>(h, lab, states, np, 7, 1024, 2, 65536);
+        return launch_shuffle_two_kernel<LT>(h, lab, states, np, 7, 1024, 2, 98304);
     SqbLaunchScope scope(c, SQB_K_NHOOD_SHUFFLE);
     const int algo = h->shuffle_algo >= 0 ? h->shuffle_algo : (np <= 2 * (int64_t)c->sm_count ? 1 : 2);
     if (algo == 0) {
