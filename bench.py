@@ -313,6 +313,46 @@ def bench_ripley(ctx):
             "largest_cluster": int(max(len(g) for g in groups))}
 
 
+def bench_nhood_variants(ctx, g, base, n_cls, P, seed):
+    """configs[1] variants of SURVEY 8(d): the same lattice with randomly permuted node order (worst-case gather locality
+    for the count kernel) and with half of the mirrored entries dropped (a directed graph: no symmetric shortcut)."""
+    import scipy.sparse as sp
+
+    from squidpy_b200._rng import spawn_states
+    from squidpy_b200.gr import NhoodPlan
+
+    out = {}
+    rng = np.random.default_rng(1)
+    n = g.shape[0]
+    perm = rng.permutation(n)
+    g_perm = g[perm][:, perm].tocsr()
+    g_perm.sort_indices()
+    coo = g.tocoo()
+    keep = (coo.row < coo.col) | (rng.random(coo.nnz) < 0.5)  # drops ~half of the j < i mirrors
+    g_dir = sp.csr_matrix((coo.data[keep], (coo.row[keep], coo.col[keep])), shape=g.shape)
+    states = spawn_states(seed, P)
+    for name, gg, lab in (("permuted_node_order", g_perm, base[perm]), ("directed_graph", g_dir, base)):
+        plan = NhoodPlan(gg.indptr, gg.indices, n_cls, ctx)
+        plan.set_base(lab)
+        plan.upload(states)
+        plan.run_async()
+        ctx.sync()
+        ctx.profile(True)
+        ctx.profile_reset()
+        plan.run_async()
+        ctx.sync()
+        kms = {k: ctx.profile_get(k)[0] for k in ("fill", "misc", "shuffle", "transpose", "count")}
+        ctx.profile(False)
+        kms["jgen"] = kms.pop("misc")
+        counts = plan.download()
+        assert (counts.reshape(P, -1).sum(axis=1, dtype=np.int64) == gg.nnz).all()
+        tot = sum(kms.values())
+        out[name] = {"nnz": int(gg.nnz), "kernel_ms": kms, "permutations_per_s": P / (tot / 1e3),
+                     "note": "sum of per-kernel CUDA-event times of one step (launches synchronised)"}
+        plan.close()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -427,7 +467,8 @@ def main():
         except Exception as e:  # pragma: no cover
             extras["moran"] = {"error": repr(e)}
     if args.all and rank == 0 and ws == 1:
-        for name, fn in (("co_occurrence", lambda: bench_cooc(ctx, flush)), ("ripley_L", lambda: bench_ripley(ctx))):
+        for name, fn in (("co_occurrence", lambda: bench_cooc(ctx, flush)), ("ripley_L", lambda: bench_ripley(ctx)),
+                         ("nhood_variants", lambda: bench_nhood_variants(ctx, g, base, n_cls, P, CFG2["seed"]))):
             try:
                 extras[name] = fn()
             except Exception as e:  # pragma: no cover

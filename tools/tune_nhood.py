@@ -35,13 +35,12 @@ def main():
     ctx.profile(True)
     variants = []
     base = dict(shuffle_algo=1, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_low=0, shuffle_stagger_us=0)
-    # default (auto) and the two-kernel list replay (algo 7) around its tuned shape
+    # default (auto) and the two-kernel list replay (algo 7): CTA shapes with one / two CTAs per SM
     variants.append({**base, "shuffle_algo": -1})
-    a7 = {**base, "shuffle_algo": 7, "shuffle_threads": 1024, "shuffle_r": 2, "shuffle_low": 65536}
-    for low in (0, 32768, 98304):
-        variants.append({**a7, "shuffle_low": low})
-    for nt, r, low in ((1024, 4, 0), (1024, 4, 32768), (512, 4, 0), (512, 4, 16384), (512, 8, 32768)):
-        variants.append({**a7, "shuffle_threads": nt, "shuffle_r": r, "shuffle_low": low})
+    a7 = {**base, "shuffle_algo": 7, "shuffle_threads": 1024, "shuffle_r": 2, "shuffle_low": 98304}
+    for nt, r, low, ctas in ((512, 2, 0, 0), (512, 2, 32768, 0), (512, 2, 65536, 0), (512, 2, 65536, 148), (512, 2, 131072, 148),
+                             (512, 4, 16384, 0), (512, 4, 98304, 0), (256, 4, 16384, 0), (256, 8, 16384, 0), (1024, 2, 131072, 0)):
+        variants.append({**a7, "shuffle_threads": nt, "shuffle_r": r, "shuffle_low": low, "shuffle_ctas": ctas})
     for v in variants:
         for k, val in v.items():
             plan.set_option(k, val)
