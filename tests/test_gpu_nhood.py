@@ -131,6 +131,31 @@ def test_shuffle_is_numpy_exact(algo, threads, q, n):
     np.testing.assert_array_equal(got, ref.shuffle_labels(base, st))
 
 
+@pytest.mark.parametrize("algo,threads,r", [(1, 512, 4), (2, 512, 4), (3, 512, 4), (5, 512, 4), (6, 512, 4), (6, 1024, 2), (7, 1024, 2), (7, 512, 8), (-1, 512, 4)])
+def test_shuffle_uint16_labels(algo, threads, r):
+    """More than 256 categories: 16-bit label arrays through every replay variant (incl. the shared-memory low part of the
+    default, which then holds half as many elements), with library segments."""
+    n = 90001
+    g = sp.csr_matrix((np.ones(n - 1, np.float32), (np.arange(n - 1), np.arange(1, n))), shape=(n, n))
+    n_cls = 300
+    base = (np.arange(n) * 7 % n_cls).astype(np.uint32)
+    lib = (np.arange(n) % 2).astype(np.int32)
+    plan = _plan(g, n_cls)
+    plan.set_option("shuffle_algo", algo)
+    plan.set_option("shuffle_threads", threads)
+    plan.set_option("shuffle_r" if algo in (3, 5, 6, 7) else "shuffle_q", r)
+    if algo == 7:
+        plan.set_option("shuffle_low", -1)
+    P = 300 if algo == -1 else 5  # auto picks the two-kernel list replay only for more than 2 x SM permutations
+    st = spawn_states(11, P)
+    plan.set_base(base)
+    plan.upload(st)
+    np.testing.assert_array_equal(plan.shuffled_labels(P - 3, P), ref.shuffle_labels(base, st[P - 3 :]))
+    plan.set_base(base, lib, 2)
+    plan.upload(st)
+    np.testing.assert_array_equal(plan.shuffled_labels(0, 2), ref.shuffle_labels(base, st[:2], lib, 2))
+
+
 @pytest.mark.parametrize("wf", [100, 400, 1600, 6400])
 @pytest.mark.parametrize("threads,r", [(256, 4), (512, 8), (1024, 4)])
 def test_list_replay_window_factor(wf, threads, r):
