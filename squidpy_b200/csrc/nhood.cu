@@ -1544,18 +1544,29 @@ __global__ void __launch_bounds__(128) nhood_jgen_kernel(uint32_t* __restrict__ 
                 const uint32_t mask = 0xFFFFFFFFu >> __clz(i_cur);
                 const int i_lo = (int)(mask >> 1) + 1;
                 const int n_ph = i_cur - i_lo + 1;
-                const int K = sqb_window_size((int64_t)i_cur, RAW - pos, RAW, wfactor);
+                // no swaps here, hence no conflicts to bound: the window is the rest of the batch (capped at i/4, which keeps
+                // the acceptance fixed point short at the small-i end); wfactor only matters to the kernels that swap
+                int K = min(i_cur >> 2, RAW);
+                K = min(max(K, 1), RAW - pos);
+                (void)wfactor;
                 uint32_t u[2 * Q];
                 bool inw[2 * Q], F[2 * Q];
                 int c[2 * Q];
 #pragma unroll
                 for (int k = 0; k < 2 * Q; ++k) {
                     const int r = (k >> 1) * 64 + 2 * lane + (k & 1);
-                    inw[k] = (r >= pos) && (r < pos + K);
+                    inw[k] = (uint32_t)(r - pos) < (uint32_t)K;
                     u[k] = raw[k] & mask;
                     F[k] = inw[k] && (u[k] <= (uint32_t)i_cur);
                     c[k] = 0;
                 }
+                // A candidate (u <= i_cur) with u <= i_cur - K is accepted whatever its rank (rank < K).  Without any candidate
+                // above that line in the whole window nothing depends on the ranks: one pass.  (Evaluated on the candidates,
+                // not on the current flags: a value rejected in one round can come back in the next.)
+                bool uncertain = false;
+#pragma unroll
+                for (int k = 0; k < 2 * Q; ++k) uncertain |= F[k] && ((int)u[k] > i_cur - K);
+                const bool any_uncertain = __any_sync(0xffffffffu, uncertain);
                 int total = 0;
                 while (true) {
                     int run = 0;
@@ -1568,6 +1579,7 @@ __global__ void __launch_bounds__(128) nhood_jgen_kernel(uint32_t* __restrict__ 
                         run += __popc(blo) + __popc(bhi);
                     }
                     total = run;
+                    if (!any_uncertain) break;  // the optimistic flags, and the ranks just computed from them, are final
                     bool changed = false;
 #pragma unroll
                     for (int k = 0; k < 2 * Q; ++k) {
@@ -1591,9 +1603,10 @@ __global__ void __launch_bounds__(128) nhood_jgen_kernel(uint32_t* __restrict__ 
                     newpos = pos + K;
                 }
                 // target of step i = i_cur - rank, streamed out (read exactly once by the apply kernel)
+                uint32_t* __restrict__ Jtop = Jp + base + i_cur;
 #pragma unroll
                 for (int k = 0; k < 2 * Q; ++k)
-                    if (F[k] && c[k] < S) __stcs(Jp + base + (i_cur - c[k]), u[k]);
+                    if (F[k] && c[k] < S) __stcs(Jtop - c[k], u[k]);
                 i_cur -= S;
                 pos = newpos;
             }

@@ -156,6 +156,24 @@ def test_shuffle_uint16_labels(algo, threads, r):
     np.testing.assert_array_equal(plan.shuffled_labels(0, 2), ref.shuffle_labels(base, st[:2], lib, 2))
 
 
+@pytest.mark.parametrize("q", [2, 4])
+@pytest.mark.parametrize("n", [9, 257, 1000, 4099, 70001])
+def test_target_generation_batch_sizes(q, n):
+    """Swap-target generation of the two-kernel replays (128 / 256 raw values per batch).  Small arrays are the hard case for
+    its acceptance fixed point: a window covers a quarter of the remaining range, so many candidates depend on their rank."""
+    g = sp.csr_matrix((np.ones(n - 1, np.float32), (np.arange(n - 1), np.arange(1, n))), shape=(n, n))
+    base = (np.arange(n) % 113).astype(np.uint32)
+    st = spawn_states(900 + n, 24)
+    exp = ref.shuffle_labels(base, st)
+    for algo in (5, 7):
+        plan = _plan(g, 113)
+        plan.set_option("shuffle_algo", algo)
+        plan.set_option("shuffle_q", q)
+        plan.set_base(base)
+        plan.upload(st)
+        np.testing.assert_array_equal(plan.shuffled_labels(0, 24), exp)
+
+
 @pytest.mark.parametrize("wf", [100, 400, 1600, 6400])
 @pytest.mark.parametrize("threads,r", [(256, 4), (512, 8), (1024, 4)])
 def test_list_replay_window_factor(wf, threads, r):

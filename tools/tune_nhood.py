@@ -35,12 +35,11 @@ def main():
     ctx.profile(True)
     variants = []
     base = dict(shuffle_algo=1, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_low=0, shuffle_stagger_us=0)
-    # default (auto) and the two-kernel list replay (algo 7): CTA shapes with one / two CTAs per SM
+    # default (auto); J generation with 2 / 4 outputs per lane and batch
     variants.append({**base, "shuffle_algo": -1})
     a7 = {**base, "shuffle_algo": 7, "shuffle_threads": 1024, "shuffle_r": 2, "shuffle_low": 98304}
-    for nt, r, low, ctas in ((512, 2, 0, 0), (512, 2, 32768, 0), (512, 2, 65536, 0), (512, 2, 65536, 148), (512, 2, 131072, 148),
-                             (512, 4, 16384, 0), (512, 4, 98304, 0), (256, 4, 16384, 0), (256, 8, 16384, 0), (1024, 2, 131072, 0)):
-        variants.append({**a7, "shuffle_threads": nt, "shuffle_r": r, "shuffle_low": low, "shuffle_ctas": ctas})
+    variants.append({**a7, "shuffle_q": 2})
+    variants.append({**a7, "shuffle_q": 4})
     for v in variants:
         for k, val in v.items():
             plan.set_option(k, val)
