@@ -95,6 +95,10 @@ int sqb_nhood_permute(sqb_nhood* h, const uint64_t* states, int64_t n_perms, uin
 int sqb_nhood_permute_upload(sqb_nhood* h, const uint64_t* states, int64_t n_perms);
 int sqb_nhood_permute_run_async(sqb_nhood* h);
 int sqb_nhood_permute_download(sqb_nhood* h, uint32_t* out_counts);
+/* Mean and standard deviation over the permutations of every count bin (n_cls x n_cls float64 each), computed on the
+ * device in the operation order of numpy's perms.mean(axis=0) / perms.std(axis=0) on the float64 counts
+ * (_nhood.py:231), i.e. bit-identical to the reference's host computation; saves the download of all counts.          */
+int sqb_nhood_permute_stats(sqb_nhood* h, double* mean_out, double* std_out);
 
 /* Test hook: shuffled label vectors of permutations [p0, p1) of the last upload, recomputed on the device
  * (original node order), out: (p1-p0) x n uint32.                                                        */

@@ -3042,6 +3042,53 @@ int sqb_nhood_permute_download(sqb_nhood* h, uint32_t* out_counts) {
     return SQB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// 5. per-bin mean and standard deviation over the permutations, in the exact operation order of the reference's
+//    `perms.mean(axis=0)` / `perms.std(axis=0)` on the float64 copy of the counts (_nhood.py:231): numpy reduces axis 0 of a
+//    C-contiguous array row by row (sequential adds per output element), std = sqrt(sum((x - mean)^2) / P).  Explicit
+//    round-to-nearest intrinsics: no FMA contraction, so the doubles are bit-identical to numpy's.
+// ------------------------------------------------------------------------------------------------
+__global__ void nhood_stats_kernel(const uint32_t* __restrict__ counts, int64_t P, int CC, double* __restrict__ mean,
+                                   double* __restrict__ stdv) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= CC) return;
+    double s = 0.0;
+    for (int64_t p = 0; p < P; ++p) s = __dadd_rn(s, (double)counts[p * CC + b]);
+    const double m = __ddiv_rn(s, (double)P);
+    double v = 0.0;
+    for (int64_t p = 0; p < P; ++p) {
+        const double x = __dsub_rn((double)counts[p * CC + b], m);
+        v = __dadd_rn(v, __dmul_rn(x, x));
+    }
+    mean[b] = m;
+    stdv[b] = __dsqrt_rn(__ddiv_rn(v, (double)P));
+}
+
+int sqb_nhood_permute_stats(sqb_nhood* h, double* mean_out, double* std_out) {
+    SQB_CHECK(h && mean_out && std_out, SQB_ERR_INVALID, "sqb_nhood_permute_stats: null argument");
+    SQB_CHECK(h->ran, SQB_ERR_STATE, "sqb_nhood_permute_stats: nothing has run");
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    const int CC = h->n_cls * h->n_cls;
+    DevBuf<double> d;
+    d.bind(c->stream);
+    SQB_TRY(d.alloc((size_t)2 * CC));
+    {
+        SqbLaunchScope scope(c, SQB_K_MISC);
+        nhood_stats_kernel<<<(unsigned)ceil_div64(CC, 64), 64, 0, c->stream>>>(h->d_counts.p, h->n_perms, CC, d.p, d.p + CC);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mean_out, d.p, CC * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(std_out, d.p + CC, CC * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    d.release();
+    if (e != cudaSuccess) {
+        sqb_set_error("sqb_nhood_permute_stats: %s", cudaGetErrorString(e));
+        return SQB_ERR_CUDA;
+    }
+    return SQB_OK;
+}
+
 int sqb_nhood_permute(sqb_nhood* h, const uint64_t* states, int64_t n_perms, uint32_t* out_counts) {
     SQB_TRY(sqb_nhood_permute_upload(h, states, n_perms));
     SQB_TRY(sqb_nhood_permute_run_async(h));

@@ -105,6 +105,14 @@ class NhoodPlan:
         check(self._lib.sqb_nhood_permute_download(self._h, out.ctypes.data))
         return out
 
+    def stats(self) -> tuple[np.ndarray, np.ndarray]:
+        """float64 (n_cls, n_cls) mean and standard deviation over the permutations of the last run, bit-identical to
+        ``perms.astype(float64).mean(axis=0)`` / ``.std(axis=0)`` (same operation order, computed on the device)."""
+        mean = np.empty((self.n_cls, self.n_cls), dtype=np.float64)
+        std = np.empty((self.n_cls, self.n_cls), dtype=np.float64)
+        check(self._lib.sqb_nhood_permute_stats(self._h, mean.ctypes.data, std.ctypes.data))
+        return mean, std
+
     def permute(self, states: np.ndarray) -> np.ndarray:
         """uint32 (n_perms, n_cls, n_cls) neighbour-pair counts of every permutation."""
         states = np.ascontiguousarray(states, dtype=np.uint64)
@@ -178,16 +186,25 @@ def nhood_enrichment(
         rank, ws = world()
         lo, hi = shard_range(int(n_perms), rank, ws)
         logg.info("Calculating neighborhood enrichment on cuda:%d (rank %d/%d, permutations %d..%d)", ctx.device, rank, ws, lo, hi)
-        if hi > lo:
+        if ws == 1:
+            # single GPU: mean / std over the permutations on the device, in numpy's operation order (bit-identical to the
+            # host expression below); the per-permutation counts never leave the GPU
             plan.set_base(int_clust, lib_codes, n_libs)
-            perms_local = plan.permute(spawn_states(seed, int(n_perms), lo, hi))
+            plan.upload(spawn_states(seed, int(n_perms), lo, hi))
+            plan.run_async()
+            mean, std = plan.stats()
         else:
-            perms_local = np.empty((0, n_cls, n_cls), dtype=np.uint32)
-        perms = all_gather_rows(perms_local, int(n_perms)).astype(np.float64)
+            if hi > lo:
+                plan.set_base(int_clust, lib_codes, n_libs)
+                perms_local = plan.permute(spawn_states(seed, int(n_perms), lo, hi))
+            else:
+                perms_local = np.empty((0, n_cls, n_cls), dtype=np.uint32)
+            perms = all_gather_rows(perms_local, int(n_perms)).astype(np.float64)
+            mean, std = perms.mean(axis=0), perms.std(axis=0)
     finally:
         plan.close()
     with np.errstate(divide="ignore", invalid="ignore"):
-        zscore = (count - perms.mean(axis=0)) / perms.std(axis=0)  # _nhood.py:231 (no zero-std guard there either)
+        zscore = (count - mean) / std  # _nhood.py:231 (no zero-std guard there either)
 
     if copy:
         return NhoodEnrichmentResult(zscore=zscore, counts=count)

@@ -285,6 +285,25 @@ def test_api_cfg1_visium_grid_golden(golden_cfg1):
     np.testing.assert_array_equal(res.zscore, golden_cfg1["nhood_z"])
 
 
+def test_device_stats_are_numpy_bitwise():
+    """Mean / std over the permutations computed on the device equal numpy's float64 mean/std of the downloaded counts BIT FOR
+    BIT (same operation order, no FMA contraction): the z-scores of the single-GPU path are the reference's."""
+    g = synth.hex_graph(61, 47)
+    n_cls = 12
+    lab = np.random.default_rng(2).integers(0, n_cls, g.shape[0]).astype(np.uint32)
+    for P in (1, 2, 7, 333, 1000):
+        plan = _plan(g, n_cls)
+        plan.set_base(lab)
+        plan.upload(spawn_states(5, P))
+        plan.run_async()
+        mean, std = plan.stats()
+        perms = plan.download().astype(np.float64)
+        assert mean.tobytes() == perms.mean(axis=0).tobytes()
+        assert std.tobytes() == perms.std(axis=0).tobytes()
+    with pytest.raises(sq.SquidpyB200Error, match="nothing has run"):
+        _plan(g, n_cls).stats()
+
+
 def test_api_reproducibility(dummy_adata):
     # reference tests/graph/test_nhood.py:41-59
     a = sq.gr.nhood_enrichment(dummy_adata, "cluster", n_perms=30, seed=42, copy=True)
