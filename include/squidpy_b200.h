@@ -115,7 +115,8 @@ int sqb_nhood_shuffled_labels(sqb_nhood* h, int64_t p0, int64_t p1, uint32_t* ou
  *   "shuffle_ctas"   persistent grid size = permutations in flight (0 = occupancy x SM count),
  *   "shuffle_stagger_us" start-up stagger of the persistent CTAs, "shuffle_wfactor_x100" window = min(i/4, f*sqrt(i)),
  *   "perm_chunk"     permutations resident at once, "count_algo" 0 auto / 1 shared-memory histograms / 2 global atomics,
- *   "count_sym"      -1 auto (count structurally symmetric graphs from the entries with j >= i) / 0 always the full CSR. */
+ *   "count_sym"      -1 auto (count structurally symmetric graphs from the entries with j >= i) / 0 always the full CSR,
+ *   "count_un"       CSR rows a warp walks at once in the symmetric count kernel (4 / 6 [default] / 8 / 12). */
 int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value);
 /* algorithmic bytes per permutation, SURVEY.md 8(d): 4*nnz + 4*(n+1) + 8*n + 4*n_cls^2                   */
 int sqb_nhood_bytes_per_perm(sqb_nhood* h, int64_t* bytes);
