@@ -344,8 +344,8 @@ static int ac_transpose_csr(sqb_autocorr* h, const int64_t* h_xp, const int32_t*
         return rc;
     }
     cudaError_t e = cudaMemcpyAsync(t_xp.p, h_xp, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(t_xi.p, h_xi, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(t_xv.p, h_xv, nnz * sizeof(XT), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && nnz > 0 && sqb_h2d(c, t_xi.p, h_xi, nnz * sizeof(int32_t)) != SQB_OK) e = cudaErrorUnknown;
+    if (e == cudaSuccess && nnz > 0 && sqb_h2d(c, t_xv.p, h_xv, nnz * sizeof(XT)) != SQB_OK) e = cudaErrorUnknown;
     if (e == cudaSuccess) e = cudaMemsetAsync(cnt.p, 0, (n_feat + 1) * sizeof(unsigned long long), c->stream);
     if (e != cudaSuccess) {
         cleanup();
@@ -463,7 +463,7 @@ int sqb_autocorr_load_dense(sqb_autocorr* h, const void* x, int x_dtype, int lay
     const size_t bytes = (size_t)n_features * h->n * xsize(x_dtype);
     // zero-copy tiles read up to 31 elements past the last feature of a row: pad the allocation
     SQB_TRY(h->d_x.alloc(bytes + 64 * 8));
-    SQB_CUDA(cudaMemcpyAsync(h->d_x.p, x, bytes, cudaMemcpyHostToDevice, c->stream));
+    SQB_TRY(sqb_h2d(c, h->d_x.p, x, bytes));
     SQB_CUDA(cudaStreamSynchronize(c->stream));
     h->kind = layout == 0 ? 1 : 2;
     h->x_dtype = x_dtype;
@@ -494,8 +494,8 @@ int sqb_autocorr_load_csr(sqb_autocorr* h, const int64_t* x_indptr, const int32_
         SQB_TRY(h->d_x.alloc((size_t)(nnz > 0 ? nnz : 1) * xsize(x_dtype)));
         SQB_CUDA(cudaMemcpyAsync(h->d_xp.p, x_indptr, (n_features + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
         if (nnz > 0) {
-            SQB_CUDA(cudaMemcpyAsync(h->d_xi.p, x_indices, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-            SQB_CUDA(cudaMemcpyAsync(h->d_x.p, x_data, (size_t)nnz * xsize(x_dtype), cudaMemcpyHostToDevice, c->stream));
+            SQB_TRY(sqb_h2d(c, h->d_xi.p, x_indices, nnz * sizeof(int32_t)));
+            SQB_TRY(sqb_h2d(c, h->d_x.p, x_data, (size_t)nnz * xsize(x_dtype)));
         }
         SQB_CUDA(cudaStreamSynchronize(c->stream));
         h->x_nnz = nnz;

@@ -964,6 +964,12 @@ __device__ __forceinline__ LT sqb_list_T(const uint32_t* __restrict__ s_ohead, c
     return s_otop[x];
 }
 
+template <typename LT>
+__device__ __forceinline__ LT sqb_list_T_own(const uint32_t* __restrict__ s_ohead, const uint16_t* __restrict__ s_next,
+                                             const LT* __restrict__ s_otop, int s, LT own) {
+    return (s_ohead[s] == SQB_NONE32) ? own : sqb_list_T<LT>(s_ohead, s_next, s_otop, s);
+}
+
 __device__ __forceinline__ int sqb_list_latest_before(const uint16_t* __restrict__ s_next, uint32_t head, int s, int* mx) {
     int best = -1, m = -1;
     for (uint32_t e = head; e != SQB_NONE16 && e != SQB_NONE32; e = s_next[e]) {
@@ -1516,8 +1522,9 @@ __global__ void __launch_bounds__(128) nhood_jgen_kernel(uint32_t* __restrict__ 
     u128 M32, C32, Mt, Ct;
     pcg_jump_consts(32, M32, C32);
     pcg_jump_consts((uint64_t)lane + 1, Mt, Ct);
-    const int64_t warps_total = (int64_t)gridDim.x * 4;
-    for (int64_t perm = (int64_t)blockIdx.x * 4 + warp; perm < n_perms; perm += warps_total) {
+    const int wpb = (int)(blockDim.x >> 5);  // warps per block (1, 2 or 4)
+    const int64_t warps_total = (int64_t)gridDim.x * wpb;
+    for (int64_t perm = (int64_t)blockIdx.x * wpb + warp; perm < n_perms; perm += warps_total) {
         uint32_t* __restrict__ Jp = J + perm * stride;
         const uint64_t* st4 = states + perm * 4;
         const u128 inc = mk128(st4[2], st4[3]);
@@ -2038,7 +2045,7 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict_
                                 last = (mx == s);
                             }
                             if (last) {
-                                const LT tv = sqb_list_T<LT>(s_ohead, s_next, s_otop, s);
+                                const LT tv = sqb_list_T_own<LT>(s_ohead, s_next, s_otop, s, ((tgm >> m) & 1u) ? vtg[m] : vts[m]);
                                 if ((int)j < Lc) s_low[j] = tv;
                                 else a[base + (int64_t)j] = tv;
                             }
@@ -2057,8 +2064,12 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict_
                     const bool ac = (act >> m) & 1u, ow = (ownm >> m) & 1u, sl = (slowm >> m) & 1u;
                     const uint32_t j = jv[m];
                     if (ac && ow) s_ohead[i_cur - (int)j] = SQB_NONE32;
-                    if (ac && !ow) s_bits[(j >> 4) & (NWB - 1)] = 0u;
                     if (sl) s_tab[slotv[m]] = SQB_EMPTY64;
+                }
+                {  // the filter copy of this window only holds this window's marks: clear it wholesale (16-byte stores)
+                    uint4* bz = reinterpret_cast<uint4*>(s_bits);
+#pragma unroll
+                    for (int x = tid; x < NWB / 4; x += NT) bz[x] = make_uint4(0u, 0u, 0u, 0u);
                 }
 #pragma unroll
                 for (int m = 0; m < SPT; ++m) {
@@ -2314,6 +2325,7 @@ struct sqb_nhood {
     DevBuf<uint32_t> d_uptr, d_uidx;  // entries with j >= i of a symmetric graph (see 3b), else unused
     bool sym = false;
     int count_sym = -1;  // -1 auto (use the upper CSR when the graph is symmetric), 0 = always the full CSR
+    int jgen_threads = 128;  // block size of the swap-target generation kernel (32 / 64 / 128: 1 / 2 / 4 permutations per block)
     int count_un = 6;    // CSR rows a warp walks at once in the symmetric count kernel (4 / 6 / 8 / 12)
     DevBuf<uint8_t> d_base;   // stride * lt_bytes, library-grouped order
     DevBuf<uint32_t> d_order;  // grouped position -> node id (only with libraries)
@@ -2538,12 +2550,14 @@ static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* stat
     uint32_t* J = reinterpret_cast<uint32_t*>(c->scratch[2].p);
     {
         SqbLaunchScope scope(c, SQB_K_MISC);  // J generation is accounted under "misc"
-        int64_t ctas = (int64_t)c->sm_count * 8;
-        if (ctas > ceil_div64(np, 4)) ctas = ceil_div64(np, 4);
+        // one warp per permutation; small blocks spread the (latency-bound) warps evenly over the SMs
+        const int jt = (int)h->jgen_threads;
+        int64_t ctas = (int64_t)c->sm_count * 8 * (128 / jt);
+        if (ctas > ceil_div64(np, jt / 32)) ctas = ceil_div64(np, jt / 32);
         if (h->shuffle_q == 2)
-            nhood_jgen_kernel<2><<<(unsigned)ctas, 128, 0, c->stream>>>(J, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, 4.0f);
+            nhood_jgen_kernel<2><<<(unsigned)ctas, jt, 0, c->stream>>>(J, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, 4.0f);
         else
-            nhood_jgen_kernel<4><<<(unsigned)ctas, 128, 0, c->stream>>>(J, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, 4.0f);
+            nhood_jgen_kernel<4><<<(unsigned)ctas, jt, 0, c->stream>>>(J, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, 4.0f);
         SQB_POST_LAUNCH();
     }
     SqbLaunchScope scope(c, SQB_K_NHOOD_SHUFFLE);
@@ -2750,7 +2764,7 @@ int sqb_nhood_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const uint32_t* indpt
     }
     SQB_CUDA(cudaMemcpyAsync(h->d_indptr.p, indptr, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     if (nnz > 0)
-        SQB_CUDA(cudaMemcpyAsync(h->d_indices.p, indices, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        SQB_TRY(sqb_h2d(ctx, h->d_indices.p, indices, nnz * sizeof(uint32_t)));
     // symmetric structure? then keep the entries with j >= i as a second CSR (3b)
     if (nnz > 0) {
         DevBuf<uint32_t> flag, ucnt;
@@ -2829,6 +2843,9 @@ int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value) {
     if (!strcmp(key, "shuffle_algo")) {
         SQB_CHECK(value >= -1 && value <= 7, SQB_ERR_INVALID, "shuffle_algo must be -1 (auto) or 0..7");
         h->shuffle_algo = (int)value;
+    } else if (!strcmp(key, "jgen_threads")) {
+        SQB_CHECK(value == 32 || value == 64 || value == 128, SQB_ERR_INVALID, "jgen_threads must be 32, 64 or 128");
+        h->jgen_threads = (int)value;
     } else if (!strcmp(key, "count_un")) {
         SQB_CHECK(value == 4 || value == 6 || value == 8 || value == 12, SQB_ERR_INVALID, "count_un must be 4, 6, 8 or 12");
         h->count_un = (int)value;

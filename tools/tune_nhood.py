@@ -35,9 +35,9 @@ def main():
     ctx.profile(True)
     variants = []
     base = dict(shuffle_algo=1, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_low=0, shuffle_stagger_us=0)
-    # default (auto); rows per warp pass of the symmetric count kernel
-    for un in (8, 4, 6, 12):
-        variants.append({**base, "shuffle_algo": -1, "count_un": un})
+    # default (auto); block size of the swap-target generation kernel
+    for jt in (128, 64, 32):
+        variants.append({**base, "shuffle_algo": -1, "jgen_threads": jt})
     for v in variants:
         for k, val in v.items():
             plan.set_option(k, val)
