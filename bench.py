@@ -304,13 +304,20 @@ def bench_ripley(ctx):
     area = ConvexHull(pts).volume
     support = np.linspace(0, (area / 2) ** 0.5, 50)
     groups = [pts[lab == c] for c in range(12)]
+    import gc
+
     pair_counts([g[:2000] for g in groups], support, ctx=ctx)
-    t0 = time.perf_counter()
-    pair_counts(groups, support, ctx=ctx)
-    dt = time.perf_counter() - t0
+    gc.collect()  # handles of the previous benchmarks (GB-sized device buffers) are not freed inside the timed call
+    ctx.sync()
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        pair_counts(groups, support, ctx=ctx)
+        times.append(time.perf_counter() - t0)
+    dt = min(times)
     pairs = float(sum(len(g) ** 2 for g in groups))
     return {"metric": "Ripley L ordered pairs/s (300k cells, 12 clusters, float64, 50 radii)", "value": pairs / dt, "unit": "ordered pairs/s", "seconds": dt,
-            "largest_cluster": int(max(len(g) for g in groups))}
+            "seconds_all": times, "note": "best of 3 calls through the C ABI with host buffers", "largest_cluster": int(max(len(g) for g in groups))}
 
 
 def bench_nhood_variants(ctx, g, base, n_cls, P, seed):
