@@ -2147,12 +2147,23 @@ __global__ void nhood_symcheck_kernel(const uint32_t* __restrict__ indptr, const
         return;
     }
     const uint32_t b = indptr[i], e = indptr[i + 1];
-    bool bad = (e < b) || (e - b > 64u);
+    if (e < b) {  // indptr not monotone: invalid CSR (flag bit 1), nothing else of this row is looked at
+        upper_cnt[i] = 0;
+        atomicOr(flag, 3u);
+        return;
+    }
+    bool bad = (e - b > 64u);
+    if (bad) {  // long row: no symmetric shortcut, but every column index is still validated
+        bool oob = false;
+        for (uint32_t k = b; k < e; ++k) oob |= ((int64_t)indices[k] >= n);
+        if (oob) atomicOr(flag, 2u);
+    }
     uint32_t up = 0;
     if (!bad) {
         for (uint32_t k = b; k < e; ++k) {
             const uint32_t j = indices[k];
-            if ((int64_t)j >= n) {
+            if ((int64_t)j >= n) {  // column index out of range (also what a negative int32 index looks like): invalid CSR
+                atomicOr(flag, 2u);
                 bad = true;
                 break;
             }
@@ -2796,6 +2807,12 @@ int sqb_nhood_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const uint32_t* indpt
         cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, ucnt.p, h->d_uptr.p, (int)(n + 1), ctx->stream);
         cudaMemcpyAsync(&hflag, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess && (hflag & 2u)) {  // the kernels index the label arrays with these values: refuse
+            cleanup();
+            sqb_nhood_destroy(h);
+            sqb_set_error("sqb_nhood_create: invalid CSR (column index outside [0, %lld) or indptr not monotone)", (long long)n);
+            return SQB_ERR_INVALID;
+        }
         if (e == cudaSuccess && hflag == 0) {
             uint32_t total = 0;
             cudaMemcpyAsync(&total, h->d_uptr.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);

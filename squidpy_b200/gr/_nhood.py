@@ -38,9 +38,9 @@ def _as_u32(a) -> np.ndarray:
     re-interpreted in place — no copy, so page-locked caller buffers stay page-locked for the H2D copy."""
     a = np.asarray(a)
     if a.dtype == np.int32 and a.flags.c_contiguous:
-        if a.size and a.min() < 0:
-            raise ValueError("Negative CSR index.")
-        return a.view(np.uint32)
+        return a.view(np.uint32)  # a negative index becomes >= 2^31 and is rejected by the device-side range check
+    if a.dtype.kind == "i" and a.size and a.min() < 0:
+        raise ValueError("Negative CSR index.")
     return np.ascontiguousarray(a, dtype=np.uint32)
 
 

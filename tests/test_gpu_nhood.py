@@ -103,6 +103,19 @@ def test_create_errors():
         plan.count(np.array([0, 5]))
     with pytest.raises(sq.SquidpyB200Error, match="set_base"):
         plan.upload(spawn_states(0, 2))
+    # the kernels index the label arrays with the CSR columns: out-of-range / negative columns and a non-monotone indptr are
+    # rejected when the graph is created (checked on the device, together with the symmetry test)
+    with pytest.raises(ValueError, match="invalid CSR"):
+        NhoodPlan(np.array([0, 1, 2, 3]), np.array([1, 7, 0]), 2)
+    with pytest.raises(ValueError, match="invalid CSR"):
+        NhoodPlan(np.array([0, 1, 2, 3], dtype=np.int32), np.array([1, -1, 0], dtype=np.int32), 2)
+    with pytest.raises(ValueError, match="invalid CSR"):
+        NhoodPlan(np.array([0, 2, 1, 3]), np.array([1, 2, 0]), 2)
+    long_row = np.concatenate([np.arange(1, 101), [500]]).astype(np.int64)  # > 64 entries: no symmetry test, still validated
+    with pytest.raises(ValueError, match="invalid CSR"):
+        NhoodPlan(np.concatenate([[0], np.full(200, 101)]), long_row, 2)
+    with pytest.raises(ValueError, match="Negative CSR index"):
+        NhoodPlan(np.array([0, 1, 2]), np.array([1, -1], dtype=np.int64), 2)
 
 
 @pytest.mark.parametrize("algo,threads,q", [(0, 512, 4), (1, 128, 4), (1, 256, 4), (1, 512, 4), (1, 1024, 4), (2, 512, 1), (2, 512, 2), (2, 512, 4),
