@@ -3,6 +3,9 @@
 It mirrors the device algorithm phase by phase (RNG batch by jump-ahead, windowed acceptance fixed point,
 hash-based conflict detection, parallel swaps + ordered serial pass) so the *algorithm* can be validated on
 the CPU against numpy's ``Generator.shuffle`` (tests/test_shuffle_emulation.py).  Not used by the product.
+
+Also here: ``resolve_window_lists`` (the serial-pass-free conflict resolution of shuffle_algo 6 / 7) and ``emu_targets``
+(nhood_jgen_kernel: batch-sized windows, one-pass acceptance), each the executable specification of its kernel.
 """
 from __future__ import annotations
 
@@ -212,3 +215,110 @@ def emu_shuffle(arr, state, inc, segs, NT=8, rng=None, stats=None, resolve="seri
             i_cur -= S
             pos = newpos
     return a
+
+
+def emu_targets(state, inc, segs, Q=4, shortcut="candidates", stats=None):
+    """Python emulation of nhood_jgen_kernel (one warp = one generator, 64*Q raw 32-bit values per batch): returns
+    {(segment base, i): j}, the Fisher-Yates target of every step, as the kernel streams them to J.
+
+    The window is the rest of the batch capped at i/4.  `shortcut`:
+      "candidates"  one pass when no CANDIDATE (u <= i_cur) lies above i_cur - K (what the kernel does);
+      "flags"       the same test on the CURRENT flags inside the loop — the first, wrong version of the shortcut (a value
+                    rejected in one round can come back in the next), kept so that the test proves it can tell them apart;
+      None          always iterate to the fixed point."""
+    RAW = 64 * Q
+    lanes = 32
+    Mn, Cn = _jump_consts(lanes)
+    st = []
+    for t in range(lanes):
+        Mt, Ct = _jump_consts(t + 1)
+        st.append((Mt * state + Ct * inc) & M128)
+    raw = [0] * RAW
+    pos = RAW
+    out = {}
+
+    def gen():
+        nonlocal pos
+        for q in range(Q):
+            for t in range(lanes):
+                o = _out(st[t])
+                raw[q * 64 + 2 * t] = o & 0xFFFFFFFF
+                raw[q * 64 + 2 * t + 1] = o >> 32
+                st[t] = (Mn * st[t] + Cn * inc) & M128
+        pos = 0
+
+    for (base, m) in segs:
+        i_cur = m - 1
+        while i_cur >= 1:
+            if pos >= RAW:
+                gen()
+            mask = (1 << i_cur.bit_length()) - 1
+            i_lo = (mask >> 1) + 1
+            n_ph = i_cur - i_lo + 1
+            K = min(i_cur >> 2, RAW)
+            K = min(max(K, 1), RAW - pos)
+            win = list(range(pos, pos + K))
+            u = {r: raw[r] & mask for r in win}
+            F = {r: u[r] <= i_cur for r in win}  # optimistic start: every candidate accepted
+            any_unc = any(F[r] and u[r] > i_cur - K for r in win)
+            c = {}
+            rounds = 0
+            while True:
+                rounds += 1
+                run = 0
+                for r in win:
+                    c[r] = run
+                    run += 1 if F[r] else 0
+                total = run
+                if shortcut == "candidates" and not any_unc:
+                    break
+                if shortcut == "flags" and not any(F[r] and u[r] > i_cur - K for r in win):
+                    break
+                F2 = {r: (u[r] <= i_cur) and (u[r] <= i_cur - c[r]) for r in win}
+                if F2 == F:
+                    break
+                F = F2
+            if stats is not None:
+                stats["windows"] = stats.get("windows", 0) + 1
+                stats["rounds"] = stats.get("rounds", 0) + rounds
+                stats["one_pass"] = stats.get("one_pass", 0) + (1 if rounds == 1 else 0)
+            if total >= n_ph:
+                S = n_ph
+                rstar = next(r for r in win if F[r] and c[r] == S - 1)
+                newpos = rstar + 1
+            else:
+                S = total
+                newpos = pos + K
+            for r in win:
+                if F[r] and c[r] < S:
+                    out[(base, i_cur - c[r])] = u[r]
+            i_cur -= S
+            pos = newpos
+    return out
+
+
+def serial_targets(state, inc, segs):
+    """numpy's Generator.shuffle target sequence by plain serial replay: PCG64 next32 (low half first) + masked rejection."""
+    s = state
+    buf = None
+    out = {}
+
+    def next32():
+        nonlocal s, buf
+        if buf is not None:
+            v, buf = buf, None
+            return v
+        s = (s * A + inc) & M128
+        o = _out(s)
+        buf = o >> 32
+        return o & 0xFFFFFFFF
+
+    for (base, m) in segs:
+        for i in range(m - 1, 0, -1):
+            mask = (1 << i.bit_length()) - 1
+            while True:
+                v = next32() & mask
+                if v <= i:
+                    break
+            out[(base, i)] = v
+    return out

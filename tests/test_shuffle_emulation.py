@@ -88,3 +88,50 @@ def test_emulated_list_shuffle_matches_numpy(nt):
         gen.shuffle(exp)
         got = emu_shuffle(list(range(n)), state, inc, [(0, n)], NT=nt, rng=rnd, resolve="lists")
         np.testing.assert_array_equal(np.array(got, dtype=np.uint32), exp)
+
+
+def _numpy_shuffle_from_targets(n, targets, base=0):
+    a = np.arange(n, dtype=np.uint32)
+    for i in range(n - 1, 0, -1):
+        j = targets[(base, i)]
+        a[i], a[j] = a[j], a[i]
+    return a
+
+
+@pytest.mark.parametrize("q", [2, 4])
+def test_emulated_target_generation(q):
+    """nhood_jgen_kernel's algorithm (tests/emu_shuffle.emu_targets): batch-sized windows and the one-pass acceptance when no
+    candidate depends on its rank give numpy's swap targets — including small arrays, where most windows do need the fixed point."""
+    from tests.emu_shuffle import emu_targets, serial_targets
+
+    rnd = random.Random(40 + q)
+    for n in [2, 3, 9, 33, 100, 257, 1000, 1025, 4099, 20011]:
+        seed = rnd.randrange(10**6)
+        st, state, inc = _state(seed)
+        exp_t = serial_targets(state, inc, [(0, n)])
+        gen = np.random.default_rng(np.random.SeedSequence(seed).spawn(1)[0])
+        exp = np.arange(n, dtype=np.uint32)
+        gen.shuffle(exp)
+        np.testing.assert_array_equal(_numpy_shuffle_from_targets(n, exp_t), exp)  # the serial replay IS numpy's shuffle
+        stats = {}
+        got_t = emu_targets(state, inc, [(0, n)], Q=q, stats=stats)
+        assert got_t == exp_t, (n, q)
+        assert emu_targets(state, inc, [(0, n)], Q=q, shortcut=None) == exp_t
+        if n >= 20011:
+            assert stats["one_pass"] > 0  # the shortcut is actually taken on large arrays
+
+
+def test_emulated_target_generation_segments_and_wrong_shortcut():
+    from tests.emu_shuffle import emu_targets, serial_targets
+
+    rnd = random.Random(9)
+    st, state, inc = _state(77)
+    segs = [(0, 700), (700, 1), (701, 2300), (3001, 40)]
+    assert emu_targets(state, inc, segs, Q=4) == serial_targets(state, inc, segs)
+    # the first version of the shortcut tested the current flags instead of the candidates: wrong on small arrays
+    wrong = 0
+    for trial in range(40):
+        st, state, inc = _state(rnd.randrange(10**6))
+        n = rnd.choice([300, 1000, 1500])
+        wrong += emu_targets(state, inc, [(0, n)], Q=4, shortcut="flags") != serial_targets(state, inc, [(0, n)])
+    assert wrong > 0
