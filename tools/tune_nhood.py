@@ -35,9 +35,18 @@ def main():
     ctx.profile(True)
     variants = []
     base = dict(shuffle_algo=1, shuffle_threads=512, shuffle_r=4, shuffle_ctas=0, shuffle_wfactor_x100=400, shuffle_q=4, shuffle_low=0, shuffle_stagger_us=0)
-    # default (auto); block size of the swap-target generation kernel
-    for jt in (128, 64, 32):
-        variants.append({**base, "shuffle_algo": -1, "jgen_threads": jt})
+    # the default (auto) next to every replay variant at its best measured shape (edit this list for a focused sweep;
+    # profiles/r01_tune_nhood.json holds the last run)
+    variants.append({**base, "shuffle_algo": -1})
+    a7 = {**base, "shuffle_algo": 7, "shuffle_threads": 1024, "shuffle_r": 2, "shuffle_low": 98304}
+    for low in (0, 65536):
+        variants.append({**a7, "shuffle_low": low})
+    variants.append({**a7, "shuffle_r": 4, "shuffle_low": 0})
+    variants.append({**base, "shuffle_algo": 6, "shuffle_threads": 1024, "shuffle_r": 2, "shuffle_wfactor_x100": 1600})
+    variants.append({**base, "shuffle_algo": 5, "shuffle_threads": 512, "shuffle_r": 2})
+    variants.append({**base, "shuffle_algo": 2})
+    variants.append({**base, "shuffle_algo": 1, "shuffle_threads": 1024, "shuffle_ctas": 148})
+    variants.append({**base, "shuffle_algo": -1, "count_sym": 0})
     for v in variants:
         for k, val in v.items():
             plan.set_option(k, val)
