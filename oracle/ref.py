@@ -251,3 +251,36 @@ def multipletests_fdr_bh(pvals):
     out = np.empty(n)
     out[order] = corrected
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# interaction_matrix: src/squidpy/gr/_nhood.py:349-429  (SURVEY 8f item 2 — oracle prepared ahead of the kernel)
+# ---------------------------------------------------------------------------------------------------
+def interaction_matrix(graph, codes, n_cats: int, weights: bool = False, normalized: bool = False) -> np.ndarray:
+    """``interaction_matrix`` restated with numpy (:383-404 + ``_interaction_matrix`` :412-429).
+
+    ``graph``: scipy CSR (N x N); ``codes``: int category codes with -1 for NaN labels (pandas convention) — observations
+    with NaN labels are removed from rows AND columns (:388-395).  output[a, b] = sum over stored entries (i -> j) of the
+    restricted graph with code(i)=a, code(j)=b of the entry's value (``weights=True``) or of 1 (``weights=False``);
+    dtype int64 for bool/integer graphs else float64 (:398); ``normalized`` divides every row by its sum (:403-404).
+    The reference accumulates in CSR order; ``np.add.at`` does the same, so float sums are bit-identical."""
+    import pandas as pd
+    import scipy.sparse as sp
+
+    g = sp.csr_matrix(graph)
+    codes = np.asarray(codes)
+    mask = codes >= 0
+    if not mask.any():
+        raise RuntimeError("After removing NaNs, none remain.")
+    if not mask.all():
+        g = g[mask, :][:, mask]
+        codes = codes[mask]
+    dtype = np.int64 if (pd.api.types.is_bool_dtype(g.dtype) or pd.api.types.is_integer_dtype(g.dtype)) else np.float64
+    out = np.zeros((n_cats, n_cats), dtype=dtype)
+    rows = np.repeat(codes, np.diff(g.indptr))
+    cols = codes[g.indices]
+    vals = g.data.astype(dtype) if weights else np.ones(g.data.size, dtype=dtype)
+    np.add.at(out, (rows, cols), vals)
+    if normalized:
+        out = out / out.sum(axis=1).reshape((-1, 1))
+    return out

@@ -62,3 +62,34 @@ def test_pair_counts_vs_sklearn():
     P = rr.random((2500, 2)) * 100
     sup = np.linspace(0, 70, 50)
     np.testing.assert_array_equal(ref.pair_counts(P, sup), KDTree(P).two_point_correlation(P, sup, dualtree=True))
+
+
+def test_interaction_matrix_oracle_kat_and_reference():
+    """Oracle restatement of interaction_matrix (next row of SURVEY 8f): the reference's own known answers
+    (tests/graph/test_nhood.py:153-173, fixture tests/conftest.py:177-194) and its numba kernel on random graphs."""
+    import scipy.sparse as sp
+
+    g = sp.csr_matrix(np.array([[0, 1, 1, 0, 0], [0, 0, 0, 0, 1], [1, 2, 0, 0, 0], [0, 1, 0, 0, 1], [0, 0, 1, 2, 0]]))
+    codes = np.array([0, 0, 0, 1, 1])
+    np.testing.assert_array_equal(ref.interaction_matrix(g, codes, 2, weights=True), [[5, 1], [2, 3]])
+    np.testing.assert_array_equal(ref.interaction_matrix(g, codes, 2, weights=False), [[4, 1], [2, 2]])
+    nan_codes = np.array([-1, 0, 0, 1, 1])
+    np.testing.assert_array_equal(ref.interaction_matrix(g, nan_codes, 2, weights=True), [[2, 1], [2, 3]])
+    np.testing.assert_array_equal(ref.interaction_matrix(g, nan_codes, 2, weights=False), [[1, 1], [2, 2]])
+    assert ref.interaction_matrix(g, codes, 2).dtype == np.int64
+    np.testing.assert_allclose(ref.interaction_matrix(g, codes, 2, normalized=True).sum(1), 1.0)
+
+    if not _refload.available():
+        pytest.skip("reference sources not present (GPU box)")
+    kern = _refload.load()["nh"]._interaction_matrix
+    rng = np.random.default_rng(0)
+    for n, dens, k in ((200, 0.05, 5), (1500, 0.004, 12)):
+        a = sp.random(n, n, density=dens, format="csr", random_state=int(rng.integers(1 << 30)), dtype=np.float32)
+        codes = rng.integers(0, k, n)
+        for weights in (False, True):
+            data = a.data if weights else np.broadcast_to(1, shape=len(a.data))
+            exp = np.zeros((k, k), dtype=float)
+            kern(np.ascontiguousarray(data), a.indices, a.indptr, codes, exp)
+            got = ref.interaction_matrix(a, codes, k, weights=weights)
+            assert got.dtype == np.float64
+            np.testing.assert_array_equal(got, exp)  # same accumulation order: bit-identical float sums
