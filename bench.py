@@ -249,7 +249,7 @@ def bench_moran(ctx, rank, ws, steps, warmup, flush):
                         "algorithmic_bytes_per_step": int(algo_bytes)},
            "finite_scores": int(np.isfinite(score).sum()), "max_I": float(np.nanmax(score)), "gpu_launches": int(launches), "synth_seconds": t_gen,
            "kernel_ms": kms}
-    if rank == 0:
+    if rank == 0 and ws == 1:  # CPU baseline at N = 1 only
         try:
             from oracle import ref
 
@@ -483,7 +483,7 @@ def main():
 
     if rank == 0:
         cpu = None
-        if not args.skip_cpu:
+        if not args.skip_cpu and ws == 1:  # the CPU baseline is timed on rank 0 at N = 1 only
             try:
                 cpu = cpu_reference_nhood(g, base, n_cls, CFG2["seed"])
             except Exception as e:  # pragma: no cover
