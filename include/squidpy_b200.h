@@ -16,6 +16,7 @@
  *   sqb_nhood_permute*         <- _nhood_enrichment_helper(...)               src/squidpy/gr/_nhood.py:516-547
  *                                 (+ rng.shuffle / _shuffle_group             src/squidpy/gr/_utils.py:185-213,
  *                                    spawn_generators                         src/squidpy/_utils.py:240-241)
+ *   sqb_interaction_matrix     <- _interaction_matrix(data, indices, indptr, cats, out) src/squidpy/gr/_nhood.py:401,412-429
  *   sqb_autocorr_*             <- scanpy.metrics.morans_i / gearys_c call     src/squidpy/gr/_ppatterns.py:216,267-272
  *   sqb_cooc_counts            <- _occur_count(x, y, thresholds, labs, n,k,l) src/squidpy/gr/_ppatterns.py:283-310
  *   sqb_pair_counts_f64        <- KDTree.two_point_correlation(points, r)     src/squidpy/gr/_ripley.py:218-223
@@ -120,6 +121,16 @@ int sqb_nhood_shuffled_labels(sqb_nhood* h, int64_t p0, int64_t p1, uint32_t* ou
 int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value);
 /* algorithmic bytes per permutation, SURVEY.md 8(d): 4*nnz + 4*(n+1) + 8*n + 4*n_cls^2                   */
 int sqb_nhood_bytes_per_perm(sqb_nhood* h, int64_t* bytes);
+
+/* ---- interaction_matrix ------------------------------------------------------------------------------
+ * Replaces _interaction_matrix(data, indices, indptr, cats, output) (src/squidpy/gr/_nhood.py:401,412-429) and the NaN
+ * masking of interaction_matrix (:386-395).  codes[i] in [0, n_cls) or < 0 for an observation without label: stored
+ * entries with an unlabelled end point are skipped (== restricting the graph to the labelled observations).
+ * data == NULL (weights=False): out_counts[a*n_cls+b] = number of stored entries (i->j) with code(i)=a, code(j)=b (int64).
+ * data != NULL (weights=True, data_dtype 0 = f32, 1 = f64): out_weighted[a*n_cls+b] = float64 sum of their values.       */
+int sqb_interaction_matrix(sqb_ctx* ctx, int64_t n, int64_t nnz, const uint32_t* indptr, const uint32_t* indices,
+                           const void* data, int data_dtype, const int32_t* codes, int n_cls, double* out_weighted,
+                           int64_t* out_counts);
 
 /* ---- spatial_autocorr (Moran's I / Geary's C) -------------------------------------------------------
  * W = obsp[connectivity_key] (after optional float32 row normalisation on the host) as CSR; w_dtype 0 = f32,

@@ -211,3 +211,62 @@ def nhood_enrichment(
     _save_data(adata, attr="uns", key=Key.uns.nhood_enrichment(cluster_key), data={"zscore": zscore, "count": count},
                time_start=start)
     return None
+
+
+def interaction_matrix(
+    adata: Any,
+    cluster_key: str,
+    connectivity_key: str | None = None,
+    normalized: bool = False,
+    copy: bool = False,
+    weights: bool = False,
+    *,
+    table_key: str | None = None,
+    device: int | None = None,
+) -> np.ndarray | None:
+    """Compute the interaction matrix of the clusters (reference ``gr/_nhood.py:349-409``): entry (a, b) sums the stored
+    entries (i -> j) of ``obsp[connectivity_key]`` with cluster(i) = a and cluster(j) = b, their values if ``weights`` else
+    ones; observations with a NaN label are dropped from rows and columns; ``normalized`` divides every row by its sum.
+    dtype as in the reference (:398): int64 for bool / integer graphs, float64 otherwise.
+
+    Returns the matrix if ``copy=True``, otherwise writes ``adata.uns[f'{cluster_key}_interactions']``."""
+    import pandas as pd
+
+    adata = extract_adata_if_sdata(adata, table_key=table_key)
+    connectivity_key = Key.obsp.spatial_conn(connectivity_key)
+    assert_categorical_obs(adata, cluster_key)
+    assert_connectivity_key(adata, connectivity_key)
+
+    cats = adata.obs[cluster_key]
+    codes = np.ascontiguousarray(cats.array.codes, dtype=np.int32)  # -1 == NaN label
+    if not (codes >= 0).any():
+        raise RuntimeError(f"After removing NaNs in `adata.obs[{cluster_key!r}]`, none remain.")  # _nhood.py:391-392
+    g = as_csr(adata.obsp[connectivity_key])
+    n_cats = len(cats.cat.categories)
+    int_graph = bool(pd.api.types.is_bool_dtype(g.dtype) or pd.api.types.is_integer_dtype(g.dtype))
+
+    ctx = default_context(device)
+    lib = load()
+    indptr, indices = _as_u32(g.indptr), _as_u32(g.indices)
+    if weights:
+        data = g.data
+        if data.dtype not in (np.float32, np.float64):
+            data = data.astype(np.float64)  # integer / bool weights are summed exactly in float64 (< 2^53)
+        data = np.ascontiguousarray(data)
+        out = np.zeros((n_cats, n_cats), dtype=np.float64)
+        check(lib.sqb_interaction_matrix(ctx.handle, g.shape[0], indices.size, indptr.ctypes.data, indices.ctypes.data,
+                                         data.ctypes.data, 0 if data.dtype == np.float32 else 1, codes.ctypes.data, n_cats,
+                                         out.ctypes.data, None))
+        output = np.rint(out).astype(np.int64) if int_graph else out
+    else:
+        cnt = np.zeros((n_cats, n_cats), dtype=np.int64)
+        check(lib.sqb_interaction_matrix(ctx.handle, g.shape[0], indices.size, indptr.ctypes.data, indices.ctypes.data,
+                                         None, 0, codes.ctypes.data, n_cats, None, cnt.ctypes.data))
+        output = cnt if int_graph else cnt.astype(np.float64)
+    if normalized:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            output = output / output.sum(axis=1).reshape((-1, 1))  # _nhood.py:403-404
+    if copy:
+        return output
+    _save_data(adata, attr="uns", key=Key.uns.interaction_matrix(cluster_key), data=output)
+    return None
