@@ -100,6 +100,12 @@ int sqb_nhood_permute_download(sqb_nhood* h, uint32_t* out_counts);
  * device in the operation order of numpy's perms.mean(axis=0) / perms.std(axis=0) on the float64 counts
  * (_nhood.py:231), i.e. bit-identical to the reference's host computation; saves the download of all counts.          */
 int sqb_nhood_permute_stats(sqb_nhood* h, double* mean_out, double* std_out);
+/* The same statistics when the permutations are sharded over several GPUs (contiguous shards in rank order):
+ * sums: exact integer per-bin sums of this handle's permutations (all-reduce them, mean = sum / P_total);
+ * var_chain: acc_out = acc_in continued with numpy's sequential sum((x - mean)^2) over this handle's permutations; rank r
+ * passes acc_out to rank r+1, std = sqrt(acc_last / P_total): bit-identical to perms.std(axis=0) on the gathered counts.  */
+int sqb_nhood_permute_sums(sqb_nhood* h, int64_t* sums_out);
+int sqb_nhood_permute_var_chain(sqb_nhood* h, const double* mean, const double* acc_in, double* acc_out);
 
 /* Test hook: shuffled label vectors of permutations [p0, p1) of the last upload, recomputed on the device
  * (original node order), out: (p1-p0) x n uint32.                                                        */

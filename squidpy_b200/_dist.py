@@ -70,3 +70,37 @@ def all_reduce_sum(local: np.ndarray) -> np.ndarray:
     t = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.cpu().numpy()
+
+
+def sequential_stats(sums_local: np.ndarray, var_step, n_total: int) -> tuple[np.ndarray, np.ndarray]:
+    """Per-bin mean and standard deviation over the rows of all ranks (rank r holds the contiguous block
+    ``shard_range(n_total, r, world)``), bit-identical to ``full.mean(axis=0)`` / ``full.std(axis=0)`` of the float64
+    concatenation, without gathering the rows:
+
+    * the rows are non-negative integer counts, so every partial sum is an exact float64 integer (< 2^53): the int64
+      all-reduce of the per-rank sums IS numpy's sequential sum, ``mean = sum / n_total``;
+    * ``sum((x - mean)**2)`` is order dependent: ``var_step(mean, acc_in) -> acc_out`` continues numpy's sequential
+      accumulation over this rank's rows, the running value travels rank 0 -> 1 -> ... -> last (one small message per hop)
+      and the final value is broadcast."""
+    rank, ws = world()
+    total = all_reduce_sum(np.ascontiguousarray(sums_local, dtype=np.int64))
+    mean = total.astype(np.float64) / n_total
+    acc = np.zeros_like(mean)
+    if ws == 1:
+        acc = var_step(mean, acc)
+    else:
+        import torch
+        import torch.distributed as dist
+
+        dev = _device_for_backend()
+        if rank > 0:
+            t = torch.empty(acc.shape, dtype=torch.float64, device=dev)
+            dist.recv(t, src=rank - 1)
+            acc = t.cpu().numpy()
+        acc = var_step(mean, acc)
+        t = torch.from_numpy(np.ascontiguousarray(acc)).to(dev)
+        if rank < ws - 1:
+            dist.send(t, dst=rank + 1)
+        dist.broadcast(t, src=ws - 1)
+        acc = t.cpu().numpy()
+    return mean, np.sqrt(acc / n_total)

@@ -57,6 +57,8 @@ _SIGNATURES: dict[str, tuple] = {
     "sqb_nhood_permute_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sqb_interaction_matrix": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                           C.c_int, C.c_void_p, C.c_void_p]),
+    "sqb_nhood_permute_sums": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sqb_nhood_permute_var_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sqb_nhood_shuffled_labels": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "sqb_nhood_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "sqb_nhood_bytes_per_perm": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),

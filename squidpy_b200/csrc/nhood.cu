@@ -3132,6 +3132,81 @@ int sqb_nhood_permute_stats(sqb_nhood* h, double* mean_out, double* std_out) {
     return SQB_OK;
 }
 
+// Multi-GPU form of the same statistics: the permutations are sharded contiguously over the ranks, so
+//   * the per-bin SUMS are integers (< 2^53): exact in any order, all-reduced as int64 by the caller;
+//   * the variance accumulation sum((x - mean)^2) is order dependent: every rank continues numpy's sequential accumulation
+//     from the running value of the rank before it (one [C*C] float64 message per hop).
+__global__ void nhood_sums_kernel(const uint32_t* __restrict__ counts, int64_t P, int CC, unsigned long long* __restrict__ sums) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= CC) return;
+    unsigned long long s = 0ull;
+    for (int64_t p = 0; p < P; ++p) s += counts[p * CC + b];
+    sums[b] = s;
+}
+
+__global__ void nhood_var_chain_kernel(const uint32_t* __restrict__ counts, int64_t P, int CC, const double* __restrict__ mean,
+                                       const double* __restrict__ acc_in, double* __restrict__ acc_out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= CC) return;
+    const double m = mean[b];
+    double v = acc_in[b];
+    for (int64_t p = 0; p < P; ++p) {
+        const double x = __dsub_rn((double)counts[p * CC + b], m);
+        v = __dadd_rn(v, __dmul_rn(x, x));
+    }
+    acc_out[b] = v;
+}
+
+int sqb_nhood_permute_sums(sqb_nhood* h, int64_t* sums_out) {
+    SQB_CHECK(h && sums_out, SQB_ERR_INVALID, "sqb_nhood_permute_sums: null argument");
+    SQB_CHECK(h->ran, SQB_ERR_STATE, "sqb_nhood_permute_sums: nothing has run");
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    const int CC = h->n_cls * h->n_cls;
+    DevBuf<unsigned long long> d;
+    d.bind(c->stream);
+    SQB_TRY(d.alloc(CC));
+    {
+        SqbLaunchScope scope(c, SQB_K_MISC);
+        nhood_sums_kernel<<<(unsigned)ceil_div64(CC, 64), 64, 0, c->stream>>>(h->d_counts.p, h->n_perms, CC, d.p);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sums_out, d.p, CC * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    d.release();
+    if (e != cudaSuccess) {
+        sqb_set_error("sqb_nhood_permute_sums: %s", cudaGetErrorString(e));
+        return SQB_ERR_CUDA;
+    }
+    return SQB_OK;
+}
+
+int sqb_nhood_permute_var_chain(sqb_nhood* h, const double* mean, const double* acc_in, double* acc_out) {
+    SQB_CHECK(h && mean && acc_in && acc_out, SQB_ERR_INVALID, "sqb_nhood_permute_var_chain: null argument");
+    SQB_CHECK(h->ran, SQB_ERR_STATE, "sqb_nhood_permute_var_chain: nothing has run");
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    const int CC = h->n_cls * h->n_cls;
+    DevBuf<double> d;
+    d.bind(c->stream);
+    SQB_TRY(d.alloc((size_t)3 * CC));
+    cudaError_t e = cudaMemcpyAsync(d.p, mean, CC * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d.p + CC, acc_in, CC * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        SqbLaunchScope scope(c, SQB_K_MISC);
+        nhood_var_chain_kernel<<<(unsigned)ceil_div64(CC, 64), 64, 0, c->stream>>>(h->d_counts.p, h->n_perms, CC, d.p, d.p + CC, d.p + 2 * CC);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(acc_out, d.p + 2 * CC, CC * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    d.release();
+    if (e != cudaSuccess) {
+        sqb_set_error("sqb_nhood_permute_var_chain: %s", cudaGetErrorString(e));
+        return SQB_ERR_CUDA;
+    }
+    return SQB_OK;
+}
+
 int sqb_nhood_permute(sqb_nhood* h, const uint64_t* states, int64_t n_perms, uint32_t* out_counts) {
     SQB_TRY(sqb_nhood_permute_upload(h, states, n_perms));
     SQB_TRY(sqb_nhood_permute_run_async(h));

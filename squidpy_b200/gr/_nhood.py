@@ -17,7 +17,7 @@ from typing import Any, NamedTuple
 import numpy as np
 
 from .._constants import Key
-from .._dist import all_gather_rows, shard_range, world
+from .._dist import sequential_stats, shard_range, world
 from .._lib import Context, check, default_context, load
 from .._rng import spawn_states
 from .._validators import assert_categorical_obs, assert_connectivity_key, assert_positive, extract_adata_if_sdata
@@ -113,6 +113,20 @@ class NhoodPlan:
         check(self._lib.sqb_nhood_permute_stats(self._h, mean.ctypes.data, std.ctypes.data))
         return mean, std
 
+    def sums(self) -> np.ndarray:
+        """int64 (n_cls, n_cls) exact per-bin sums over this plan's permutations (multi-GPU statistics, see ``_dist``)."""
+        out = np.empty((self.n_cls, self.n_cls), dtype=np.int64)
+        check(self._lib.sqb_nhood_permute_sums(self._h, out.ctypes.data))
+        return out
+
+    def var_chain(self, mean: np.ndarray, acc_in: np.ndarray) -> np.ndarray:
+        """Continue numpy's sequential ``sum((x - mean)**2)`` over this plan's permutations from ``acc_in``."""
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        acc_in = np.ascontiguousarray(acc_in, dtype=np.float64)
+        out = np.empty((self.n_cls, self.n_cls), dtype=np.float64)
+        check(self._lib.sqb_nhood_permute_var_chain(self._h, mean.ctypes.data, acc_in.ctypes.data, out.ctypes.data))
+        return out
+
     def permute(self, states: np.ndarray) -> np.ndarray:
         """uint32 (n_perms, n_cls, n_cls) neighbour-pair counts of every permutation."""
         states = np.ascontiguousarray(states, dtype=np.uint64)
@@ -194,13 +208,16 @@ def nhood_enrichment(
             plan.run_async()
             mean, std = plan.stats()
         else:
+            # several GPUs: exact integer sums all-reduced, the order-dependent variance accumulation chained through the
+            # ranks in permutation order (bit-identical to mean/std of the gathered counts; nothing but [C, C] tensors moves)
             if hi > lo:
                 plan.set_base(int_clust, lib_codes, n_libs)
-                perms_local = plan.permute(spawn_states(seed, int(n_perms), lo, hi))
-            else:
-                perms_local = np.empty((0, n_cls, n_cls), dtype=np.uint32)
-            perms = all_gather_rows(perms_local, int(n_perms)).astype(np.float64)
-            mean, std = perms.mean(axis=0), perms.std(axis=0)
+                plan.upload(spawn_states(seed, int(n_perms), lo, hi))
+                plan.run_async()
+                sums_local, step = plan.sums(), plan.var_chain
+            else:  # more ranks than permutations
+                sums_local, step = np.zeros((n_cls, n_cls), dtype=np.int64), (lambda mean, acc: acc)
+            mean, std = sequential_stats(sums_local, step, int(n_perms))
     finally:
         plan.close()
     with np.errstate(divide="ignore", invalid="ignore"):

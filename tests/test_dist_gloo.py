@@ -32,6 +32,20 @@ WORKER = textwrap.dedent(
     full = all_gather_rows(local, P)
     exp = ref.nhood_perm_counts(g.indptr, g.indices, lab, 4, spawn_states(5, P))
     assert full.shape == exp.shape and (full == exp).all(), "gathered permutation counts differ"
+    # multi-GPU z-score statistics without gathering the counts: exact integer sums + variance accumulation chained through the
+    # ranks; numpy stands in for the two device kernels (sqb_nhood_permute_sums / _var_chain, same operation order)
+    from squidpy_b200._dist import sequential_stats
+    def var_step(mean, acc):
+        x = local.astype(np.float64)
+        for p in range(x.shape[0]):
+            d = x[p] - mean
+            acc = acc + d * d
+        return acc
+    lo, hi = shard_range(P, rank, ws)
+    mean, std = sequential_stats(local.sum(axis=0, dtype=np.int64), var_step, P)
+    ef = exp.astype(np.float64)
+    assert mean.tobytes() == ef.mean(axis=0).tobytes(), "chained mean differs from numpy's"
+    assert std.tobytes() == ef.std(axis=0).tobytes(), "chained std differs from numpy's"
     # float64 feature scores (spatial_autocorr sharding)
     sc = np.arange(7, dtype=np.float64) * 1.5
     lo, hi = shard_range(7, rank, ws)

@@ -317,6 +317,31 @@ def test_device_stats_are_numpy_bitwise():
         _plan(g, n_cls).stats()
 
 
+def test_device_chained_stats_are_numpy_bitwise():
+    """The multi-GPU form of the statistics (exact integer sums + variance accumulation continued from a running value):
+    two plans holding consecutive shards of the permutations reproduce numpy's mean/std of all of them bit for bit."""
+    g = synth.hex_graph(41, 37)
+    n_cls = 9
+    lab = np.random.default_rng(4).integers(0, n_cls, g.shape[0]).astype(np.uint32)
+    P, cut = 301, 120
+    st = spawn_states(8, P)
+    plans, counts = [], []
+    for lo, hi in ((0, cut), (cut, P)):
+        plan = _plan(g, n_cls)
+        plan.set_base(lab)
+        plan.upload(st[lo:hi])
+        plan.run_async()
+        plans.append(plan)
+        counts.append(plan.download())
+    full = np.concatenate(counts).astype(np.float64)
+    total = plans[0].sums() + plans[1].sums()
+    np.testing.assert_array_equal(total, np.concatenate(counts).sum(axis=0, dtype=np.int64))
+    mean = total.astype(np.float64) / P
+    assert mean.tobytes() == full.mean(axis=0).tobytes()
+    acc = plans[1].var_chain(mean, plans[0].var_chain(mean, np.zeros_like(mean)))
+    assert np.sqrt(acc / P).tobytes() == full.std(axis=0).tobytes()
+
+
 def test_api_reproducibility(dummy_adata):
     # reference tests/graph/test_nhood.py:41-59
     a = sq.gr.nhood_enrichment(dummy_adata, "cluster", n_perms=30, seed=42, copy=True)
