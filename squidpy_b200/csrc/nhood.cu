@@ -1519,8 +1519,11 @@ __global__ void __launch_bounds__(128) nhood_jgen_kernel(uint32_t* __restrict__ 
     constexpr int RAW = 64 * Q;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    u128 M32, C32, Mt, Ct;
+    // Q independent LCG chains per lane (output q*32 + lane of every batch has its own state, advanced by 32*Q per batch)
+    // instead of one chain stepped Q times: the 128-bit multiply-adds of a batch no longer depend on each other
+    u128 M32, C32, MQ, CQ, Mt, Ct;
     pcg_jump_consts(32, M32, C32);
+    pcg_jump_consts((uint64_t)32 * Q, MQ, CQ);
     pcg_jump_consts((uint64_t)lane + 1, Mt, Ct);
     const int wpb = (int)(blockDim.x >> 5);  // warps per block (1, 2 or 4)
     const int64_t warps_total = (int64_t)gridDim.x * wpb;
@@ -1528,8 +1531,12 @@ __global__ void __launch_bounds__(128) nhood_jgen_kernel(uint32_t* __restrict__ 
         uint32_t* __restrict__ Jp = J + perm * stride;
         const uint64_t* st4 = states + perm * 4;
         const u128 inc = mk128(st4[2], st4[3]);
-        u128 st = Mt * mk128(st4[0], st4[1]) + Ct * inc;
+        u128 st[Q];
+        st[0] = Mt * mk128(st4[0], st4[1]) + Ct * inc;
         const u128 C32_inc = C32 * inc;
+        const u128 CQ_inc = CQ * inc;
+#pragma unroll
+        for (int q = 1; q < Q; ++q) st[q] = M32 * st[q - 1] + C32_inc;
         uint32_t raw[2 * Q];
 #pragma unroll
         for (int k = 0; k < 2 * Q; ++k) raw[k] = 0;
@@ -1541,8 +1548,8 @@ __global__ void __launch_bounds__(128) nhood_jgen_kernel(uint32_t* __restrict__ 
                 if (pos >= RAW) {
 #pragma unroll
                     for (int q = 0; q < Q; ++q) {
-                        const uint64_t o = pcg_output(st);
-                        st = M32 * st + C32_inc;
+                        const uint64_t o = pcg_output(st[q]);
+                        st[q] = MQ * st[q] + CQ_inc;
                         raw[2 * q] = (uint32_t)o;
                         raw[2 * q + 1] = (uint32_t)(o >> 32);
                     }
@@ -2567,6 +2574,8 @@ static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* stat
         if (ctas > ceil_div64(np, jt / 32)) ctas = ceil_div64(np, jt / 32);
         if (h->shuffle_q == 2)
             nhood_jgen_kernel<2><<<(unsigned)ctas, jt, 0, c->stream>>>(J, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, 4.0f);
+        else if (h->shuffle_q == 8)
+            nhood_jgen_kernel<8><<<(unsigned)ctas, jt, 0, c->stream>>>(J, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, 4.0f);
         else
             nhood_jgen_kernel<4><<<(unsigned)ctas, jt, 0, c->stream>>>(J, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, 4.0f);
         SQB_POST_LAUNCH();
@@ -2879,7 +2888,7 @@ int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value) {
         SQB_CHECK(value == 2 || value == 4 || value == 8, SQB_ERR_INVALID, "shuffle_r must be 2, 4 or 8");
         h->shuffle_r = (int)value;
     } else if (!strcmp(key, "shuffle_q")) {
-        SQB_CHECK(value == 1 || value == 2 || value == 4, SQB_ERR_INVALID, "shuffle_q must be 1, 2 or 4");
+        SQB_CHECK(value == 1 || value == 2 || value == 4 || value == 8, SQB_ERR_INVALID, "shuffle_q must be 1, 2, 4 or 8 (8: algos 5, 7 only)");
         h->shuffle_q = (int)value;
     } else if (!strcmp(key, "shuffle_threads")) {
         SQB_CHECK(value == 128 || value == 256 || value == 512 || value == 1024, SQB_ERR_INVALID,

@@ -169,7 +169,7 @@ def test_shuffle_uint16_labels(algo, threads, r):
     np.testing.assert_array_equal(plan.shuffled_labels(0, 2), ref.shuffle_labels(base, st[:2], lib, 2))
 
 
-@pytest.mark.parametrize("q", [2, 4])
+@pytest.mark.parametrize("q", [2, 4, 8])
 @pytest.mark.parametrize("n", [9, 257, 1000, 4099, 70001])
 def test_target_generation_batch_sizes(q, n):
     """Swap-target generation of the two-kernel replays (128 / 256 raw values per batch).  Small arrays are the hard case for
