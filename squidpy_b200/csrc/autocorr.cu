@@ -4,46 +4,39 @@
 // per permutation, :267-272).  Arithmetic follows scanpy's published kernels, float64 throughout:
 //     I = N/S0 * sum_i z_i * sum_j w_ij z_j / sum_i z_i^2,   z = x - mean(x)
 //     C = (N-1) * sum_ij w_ij (x_i - x_j)^2 / (2 * S0 * sum_i (x_i - mean)^2)
-// Layout: features are processed in tiles of 32 (one warp lane per feature).  A tile is a dense [N][32]
-// slab in HBM/L2 (feature-minor), so that the SpMM-style main kernel reads one coalesced 128-byte (f32) row
-// per observation and gathers the neighbour rows through L1/L2.  W is streamed once per tile; X once per
-// call.  Reductions are fixed-order (per-warp partials over contiguous observation ranges, then a
-// sequential combine), so results are bit-reproducible run to run.
+//
+// SPARSE X (AnnData's native CSR, the path BASELINE configs[2] is quoted on) — work proportional to the non-zeros:
+//   The feature matrix is kept as CSR *by feature* with observation indices ascending inside a feature and every
+//   segment padded to a multiple of 4 entries (16-byte vector loads).  One CTA walks one feature at a time:
+//     1. the feature's stored observations S are marked in a shared-memory bitmap; word w of the bitmap also holds the
+//        rank of its first stored observation (entries are sorted, so the rank is the entry's position): a lookup
+//        "is j stored, and what is x_j" is ONE 8-byte shared-memory read, + popc + one cached read of the value;
+//     2. for every stored observation i the row of W is fetched (packed 64/128-byte rows, 8/16 lanes per row, one
+//        slot each) and  acc_i = sum_j w_ij z_j  is formed with z_j = x_j - m for stored j and -m otherwise;
+//     3. the rows of W that belong to unstored observations are never touched; their contribution follows from the
+//        column sums c_j = sum_i w_ij:   sum_{i not in S} (Wz)_i = c'z - sum_{i in S} (Wz)_i,
+//           z'Wz   = A - m * (D - m*(S0 - E) - B)        A = sum_S z_i acc_i, B = sum_S acc_i,
+//                                                         D = sum_S c_j z_j,   E = sum_S c_j
+//           sum z^2 = sum_S z_i^2 + (N - |S|) m^2
+//        (every term is formed from centred values, so nothing of order m^2*N is subtracted from something of the same
+//        size except S0 - E, which is exact when nothing is stored and ~0 when everything is);  Geary likewise:
+//           sum_ij w_ij (x_i-x_j)^2 = sum_{i in S} sum_j w_ij [(x_i-x_j)^2 - [j in S] x_j^2] + sum_{j in S} c_j x_j^2.
+//   A row permutation of W (g[idx, :], the permutation variant) changes neither c nor S0; D, E, sum z^2, m and the
+//   Geary column term are kept per feature from the unpermuted pass.
+//   Reductions are fixed-order (entry -> lane assignment, shuffle tree, sequential combine over warps) and one CTA
+//   owns a feature whatever the grid size: results are bit-reproducible run to run and GPU to GPU.
+// DENSE X keeps the tile formulation of round 1: features in tiles of 32 (lane = feature), a dense [N][32] slab per
+//   tile, W streamed once per tile.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 
 #define TILE 32
 
-// ---- CSR by feature -> dense tile ------------------------------------------------------------------
-// one CTA (256 threads) per feature of the super-tile: scatter the feature's non-zeros into D[tile][obs][lane] and
-// reduce its sum (for the mean) in a fixed order (per-thread strided partial, warp shuffle tree, then warp 0).
-template <typename XT>
-__global__ void __launch_bounds__(256) ac_scatter_kernel(const int64_t* __restrict__ xp, const int32_t* __restrict__ xi,
-                                                         const XT* __restrict__ xv, int64_t g0, int64_t n_feat, int64_t n,
-                                                         XT* __restrict__ D, double* __restrict__ sums) {
-    __shared__ double s_part[8];
-    const int64_t wglobal = blockIdx.x;  // feature index inside the super-tile
-    const int64_t g = g0 + wglobal;
-    if (g >= n_feat) return;
-    const int64_t tile = wglobal / TILE;
-    const int t = (int)(wglobal % TILE);
-    XT* __restrict__ Dt = D + tile * n * TILE;
-    double s = 0.0;
-    for (int64_t e = xp[g] + threadIdx.x; e < xp[g + 1]; e += 256) {
-        const XT v = xv[e];
-        Dt[(int64_t)xi[e] * TILE + t] = v;
-        s += (double)v;
-    }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double tot = 0.0;
-        for (int w = 0; w < 8; ++w) tot += s_part[w];
-        sums[wglobal] = tot;
-    }
-}
-
+// =====================================================================================================
+// dense path (features x obs or obs x features, row-major)
+// =====================================================================================================
 // ---- dense features x obs (row-major) -> dense tile (transpose through shared memory) -------------------
 template <typename XT>
 __global__ void ac_transpose_kernel(const XT* __restrict__ x, int64_t g0, int64_t n_feat, int64_t n, XT* __restrict__ D) {
@@ -90,7 +83,7 @@ __global__ void ac_colsum_final_kernel(const double* __restrict__ partial, int64
     sums[tl * TILE + lane] = s;
 }
 
-// ---- main SpMM-style kernel ------------------------------------------------------------------------------
+// ---- dense SpMM-style kernel -----------------------------------------------------------------------------
 // MODE 0: Moran (num = sum_r z_r * sum_e w_e z_{j_e}), MODE 1: Geary (num = sum_r sum_e w_e (x_r - x_{j_e})^2).
 // den = sum_r z_r^2 in both modes.  lane = feature; warp = contiguous observation range.
 template <typename XT, int MODE>
@@ -102,7 +95,6 @@ __global__ void __launch_bounds__(256) ac_main_kernel(const int32_t* __restrict_
                                                       int64_t n_feat) {
     const int lane = threadIdx.x & 31;
     const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t tl = blockIdx.y;
     const bool valid = g0 + tl * TILE + lane < n_feat;
     const XT* __restrict__ Dt = D + tl * tile_stride + lane;
@@ -190,24 +182,535 @@ __global__ void __launch_bounds__(256) ac_final_kernel(const double* __restrict_
     out[g] = r;
 }
 
-// ---- CSR by observation -> CSR by feature (device transposition; counting sort by column) ----------------
-__global__ void ac_colcount_kernel(const int32_t* __restrict__ xi, int64_t nnz, unsigned long long* __restrict__ cnt) {
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x)
-        atomicAdd(&cnt[xi[e]], 1ULL);
+// =====================================================================================================
+// sparse path
+// =====================================================================================================
+#define AC_T 256          // threads per CTA of the per-feature kernels
+#define AC_NW (AC_T / 32)
+
+enum { AC_ERR_INDEX = 1, AC_ERR_DUP = 2, AC_ERR_INDPTR = 4, AC_ERR_PERM = 8 };
+
+// ---- input validation / transposition (load time) ----------------------------------------------------
+// indptr must start at 0, be non-decreasing and end at nnz
+__global__ void ac_check_indptr_kernel(const int64_t* __restrict__ ptr, int64_t rows, int64_t nnz, int* __restrict__ err) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t a = ptr[r], b = ptr[r + 1];
+        if (a > b || a < 0 || b > nnz || (r == 0 && a != 0)) atomicOr(err, AC_ERR_INDPTR);
+    }
 }
 
+// per-column entry counts of a CSR-by-observation matrix; out-of-range column -> error flag.
+// Shared-memory histogram per CTA when n_feat fits (hist_smem), else global atomics.
+__global__ void ac_colcount_kernel(const int32_t* __restrict__ xi, int64_t nnz, int64_t n_feat, int hist_smem,
+                                   unsigned int* __restrict__ cnt, int* __restrict__ err) {
+    extern __shared__ unsigned int s_hist[];
+    if (hist_smem)
+        for (int64_t c = threadIdx.x; c < n_feat; c += blockDim.x) s_hist[c] = 0;
+    __syncthreads();
+    const int64_t per = (nnz + gridDim.x - 1) / gridDim.x;
+    const int64_t e0 = blockIdx.x * per, e1 = e0 + per < nnz ? e0 + per : nnz;
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const int32_t c = xi[e];
+        if (c < 0 || c >= n_feat) {
+            atomicOr(err, AC_ERR_INDEX);
+            continue;
+        }
+        if (hist_smem)
+            atomicAdd(&s_hist[c], 1u);
+        else
+            atomicAdd(&cnt[c], 1u);
+    }
+    if (!hist_smem) return;
+    __syncthreads();
+    for (int64_t c = threadIdx.x; c < n_feat; c += blockDim.x) {
+        const unsigned int v = s_hist[c];
+        if (v) atomicAdd(&cnt[c], v);
+    }
+}
+
+// ptr[g] = exclusive prefix of cnt, pad[g] = exclusive prefix of cnt rounded up to 4, cursor[g] = ptr[g]
+// (single CTA; n_feat + 1 outputs)
+__global__ void __launch_bounds__(1024) ac_scan_counts_kernel(const unsigned int* __restrict__ cnt, int64_t n_feat,
+                                                              int64_t* __restrict__ ptr, int64_t* __restrict__ pad,
+                                                              unsigned long long* __restrict__ cursor) {
+    __shared__ int64_t s_a[32], s_b[32];
+    __shared__ int64_t s_run[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run[0] = s_run[1] = 0;
+    __syncthreads();
+    for (int64_t base = 0; base <= n_feat; base += 1024) {
+        const int64_t g = base + threadIdx.x;
+        const int64_t c = g < n_feat ? (int64_t)cnt[g] : 0;
+        int64_t a = c, b = (c + 3) & ~(int64_t)3;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t ta = __shfl_up_sync(0xffffffffu, a, d), tb = __shfl_up_sync(0xffffffffu, b, d);
+            if (lane >= d) {
+                a += ta;
+                b += tb;
+            }
+        }
+        if (lane == 31) {
+            s_a[warp] = a;
+            s_b[warp] = b;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int64_t va = s_a[lane], vb = s_b[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int64_t ta = __shfl_up_sync(0xffffffffu, va, d), tb = __shfl_up_sync(0xffffffffu, vb, d);
+                if (lane >= d) {
+                    va += ta;
+                    vb += tb;
+                }
+            }
+            s_a[lane] = va - s_a[lane];  // exclusive over warps
+            s_b[lane] = vb - s_b[lane];
+        }
+        __syncthreads();
+        const int64_t ea = s_run[0] + s_a[warp] + a - c, eb = s_run[1] + s_b[warp] + b - ((c + 3) & ~(int64_t)3);
+        if (g <= n_feat) {
+            if (ptr) ptr[g] = ea;
+            pad[g] = eb;
+            if (cursor) cursor[g] = (unsigned long long)ea;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) {
+            s_run[0] = ea + c;
+            s_run[1] = eb + ((c + 3) & ~(int64_t)3);
+        }
+        __syncthreads();
+    }
+}
+
+// padded starts for a caller-supplied CSR by feature: cnt[g] = ptr[g+1] - ptr[g]
+__global__ void ac_seglen_kernel(const int64_t* __restrict__ ptr, int64_t n_feat, int64_t n, unsigned int* __restrict__ cnt,
+                                 int* __restrict__ err) {
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_feat; g += (int64_t)gridDim.x * blockDim.x) {
+        int64_t d = ptr[g + 1] - ptr[g];
+        if (d < 0) d = 0;  // flagged by ac_check_indptr_kernel
+        if (d > n) {
+            atomicOr(err, AC_ERR_DUP);  // more entries than observations: some index repeats
+            d = n;
+        }
+        cnt[g] = (unsigned int)d;
+    }
+}
+
+// CSR by observation -> unsorted segments by feature (atomic cursor; the rank sort below orders them)
 template <typename XT>
 __global__ void ac_coltranspose_kernel(const int64_t* __restrict__ xp, const int32_t* __restrict__ xi,
-                                       const XT* __restrict__ xv, int64_t n_obs, unsigned long long* __restrict__ cursor,
-                                       int32_t* __restrict__ oi, XT* __restrict__ ov) {
+                                       const XT* __restrict__ xv, int64_t n_obs, int64_t n_feat,
+                                       unsigned long long* __restrict__ cursor, int32_t* __restrict__ oi, XT* __restrict__ ov) {
     const int lane = threadIdx.x & 31;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; r < n_obs; r += nw) {
         for (int64_t e = xp[r] + lane; e < xp[r + 1]; e += 32) {
-            const unsigned long long pos = atomicAdd(&cursor[xi[e]], 1ULL);
+            const int32_t c = xi[e];
+            if (c < 0 || c >= n_feat) continue;  // flagged by the count kernel
+            const unsigned long long pos = atomicAdd(&cursor[c], 1ULL);
             oi[pos] = (int32_t)r;
             ov[pos] = xv[e];
         }
+    }
+}
+
+// ---- bitmap + rank structure ------------------------------------------------------------------------------
+// S[w] = { bits of the observations 32w .. 32w+31 stored for the feature, rank of the first of them }
+__device__ __forceinline__ void ac_zero_words(uint2* S, int nwords) {
+    for (int w = threadIdx.x; w < nwords; w += AC_T) S[w] = make_uint2(0u, 0u);
+}
+
+// exclusive prefix of popc(S[w].x) into S[w].y; returns the total through s_tmp[32] (all threads must call)
+__device__ __forceinline__ unsigned int ac_scan_words(uint2* S, int nwords, unsigned int* s_tmp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = (nwords + AC_T - 1) / AC_T;
+    int w0 = threadIdx.x * chunk, w1 = w0 + chunk;
+    if (w0 > nwords) w0 = nwords;
+    if (w1 > nwords) w1 = nwords;
+    unsigned int cnt = 0;
+    for (int w = w0; w < w1; ++w) cnt += __popc(S[w].x);
+    unsigned int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_tmp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned int v = lane < AC_NW ? s_tmp[lane] : 0u;
+        unsigned int s = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += t;
+        }
+        if (lane < AC_NW) s_tmp[lane] = s - v;
+        if (lane == AC_NW - 1) s_tmp[AC_NW] = s;
+    }
+    __syncthreads();
+    unsigned int run = inc - cnt + s_tmp[warp];
+    for (int w = w0; w < w1; ++w) {
+        const unsigned int b = S[w].x;
+        S[w].y = run;
+        run += __popc(b);
+    }
+    const unsigned int total = s_tmp[AC_NW];
+    __syncthreads();
+    return total;
+}
+
+// One CTA per feature: order the (observation, value) pairs of a segment by observation (rank = number of stored
+// observations below), write them to the padded segment, pad with index -1 / value 0.  Out-of-range or repeated
+// observation indices raise the error flag.
+template <typename XT>
+__global__ void __launch_bounds__(AC_T) ac_rank_sort_kernel(const int64_t* __restrict__ in_ptr, const int32_t* __restrict__ in_idx,
+                                                             const XT* __restrict__ in_val, const int64_t* __restrict__ out_start,
+                                                             int32_t* __restrict__ out_idx, XT* __restrict__ out_val,
+                                                             int32_t* __restrict__ seg_len, int64_t n, int64_t n_feat,
+                                                             int nwords, uint2* __restrict__ s_global, int* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char ac_smem[];
+    __shared__ unsigned int s_tmp[AC_NW + 1];
+    uint2* S = s_global ? s_global + (size_t)blockIdx.x * nwords : reinterpret_cast<uint2*>(ac_smem);
+    ac_zero_words(S, nwords);
+    __syncthreads();
+    for (int64_t g = blockIdx.x; g < n_feat; g += gridDim.x) {
+        const int64_t rb = in_ptr[g];
+        int64_t len64 = in_ptr[g + 1] - rb;
+        if (len64 < 0) len64 = 0;
+        if (len64 > n) len64 = n;  // flagged by ac_seglen_kernel
+        const int len = (int)len64;
+        const int64_t os = out_start[g];
+        for (int e = threadIdx.x; e < len; e += AC_T) {
+            const int32_t i = in_idx[rb + e];
+            if (i < 0 || i >= n) {
+                atomicOr(err, AC_ERR_INDEX);
+                continue;
+            }
+            const unsigned int bit = 1u << (i & 31);
+            if (atomicOr(&S[i >> 5].x, bit) & bit) atomicOr(err, AC_ERR_DUP);
+        }
+        __syncthreads();
+        ac_scan_words(S, nwords, s_tmp);
+        for (int e = threadIdx.x; e < len; e += AC_T) {
+            const int32_t i = in_idx[rb + e];
+            if (i < 0 || i >= n) continue;
+            const uint2 s = S[i >> 5];
+            const unsigned int bit = 1u << (i & 31);
+            const int64_t pos = os + s.y + __popc(s.x & (bit - 1u));
+            out_idx[pos] = i;
+            out_val[pos] = in_val[rb + e];
+        }
+        const int lenp = (len + 3) & ~3;
+        for (int e = len + threadIdx.x; e < lenp; e += AC_T) {
+            out_idx[os + e] = -1;
+            out_val[os + e] = (XT)0;
+        }
+        if (threadIdx.x == 0) seg_len[g] = len;
+        __syncthreads();
+        ac_zero_words(S, nwords);
+        __syncthreads();
+    }
+}
+
+// ---- W preprocessing ---------------------------------------------------------------------------------------
+// packed rows: LPR slots of 8 bytes; slots 0..LPR-2 = {column (int32, -1 = empty), weight (float32)}, slot LPR-1 = the
+// column sum c_i of W as float64.
+template <int LPR>
+__global__ void ac_pack_rows_kernel(const int32_t* __restrict__ wp, const int32_t* __restrict__ wi, const double* __restrict__ wd,
+                                    const double* __restrict__ csum, int64_t n, uint2* __restrict__ rows) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n * LPR; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / LPR;
+        const int slot = (int)(t % LPR);
+        uint2 v;
+        if (slot == LPR - 1) {
+            const long long bits = __double_as_longlong(csum[r]);
+            v = make_uint2((unsigned int)(bits & 0xffffffffLL), (unsigned int)((unsigned long long)bits >> 32));
+        } else {
+            const int32_t e = wp[r] + slot;
+            if (e < wp[r + 1])
+                v = make_uint2((unsigned int)wi[e], __float_as_uint((float)wd[e]));
+            else
+                v = make_uint2(0xffffffffu, 0u);
+        }
+        rows[t] = v;
+    }
+}
+
+// row permutation: int64 host layout -> int32, validated on the device (bitmap of seen sources)
+__global__ void ac_perm_prepare_kernel(const int64_t* __restrict__ in, int64_t n, int32_t* __restrict__ out,
+                                       unsigned int* __restrict__ seen, int* __restrict__ err) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = in[r];
+        if (s < 0 || s >= n) {
+            atomicOr(err, AC_ERR_PERM);
+            out[r] = 0;
+            continue;
+        }
+        const unsigned int bit = 1u << (s & 31);
+        if (atomicOr(&seen[s >> 5], bit) & bit) atomicOr(err, AC_ERR_PERM);
+        out[r] = (int32_t)s;
+    }
+}
+
+// ---- the per-feature kernel ---------------------------------------------------------------------------------
+struct AcSparseParams {
+    int64_t n, n_feat;
+    int nwords;
+    uint2* s_global;  // bitmap scratch in global memory (nwords per CTA) when it does not fit shared memory, else null
+    const int64_t* seg_start;
+    const int32_t* seg_len;
+    const int32_t* order;  // features by decreasing length (longest first), or null
+    const int32_t* xi;
+    const void* xv;
+    // W
+    const uint2* rows;  // packed rows (FMT 0 / 1)
+    const int32_t* wp;  // CSR (FMT 2)
+    const int32_t* wi;
+    const double* wd;
+    const double* csum;
+    double s0;
+    const int32_t* perm;  // row permutation (PERM) or null
+    double* aux;          // [5][n_feat]: mean, sum z^2 over stored, D, E, Geary column term (written by unpermuted runs)
+    double* out;
+    int* counter;  // dynamic feature queue
+};
+
+// fixed-order block reduction of NQ doubles; result valid in thread 0
+template <int NQ>
+__device__ __forceinline__ void ac_block_reduce(double (&q)[NQ], double (*s_red)[AC_NW]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) q[k] += __shfl_xor_sync(0xffffffffu, q[k], d);
+        if (lane == 0) s_red[k][warp] = q[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < AC_NW; ++w) t += s_red[k][w];
+            q[k] = t;
+        }
+    }
+}
+
+template <typename XT>
+__device__ __forceinline__ bool ac_lookup(const uint2* __restrict__ S, int j, const XT* __restrict__ xv, double& xj) {
+    const uint2 s = S[j >> 5];
+    const unsigned int bit = 1u << (j & 31);
+    if (s.x & bit) {
+        xj = (double)__ldg(xv + (s.y + __popc(s.x & (bit - 1u))));
+        return true;
+    }
+    xj = 0.0;
+    return false;
+}
+
+// one slot of one row: Moran  acc0 += z_i * w z_j, acc1 += w z_j;   Geary  acc0 += w ((x_i - x_j)^2 - [j stored] x_j^2)
+template <typename XT, int MODE>
+__device__ __forceinline__ void ac_slot(const uint2* __restrict__ S, const XT* __restrict__ xv, int j, double w, double xi_v,
+                                        double zi, double m, double& acc0, double& acc1) {
+    double xj;
+    const bool hit = ac_lookup<XT>(S, j, xv, xj);
+    if (MODE == 0) {
+        const double t = w * (hit ? xj - m : -m);
+        acc0 = fma(zi, t, acc0);
+        acc1 += t;
+    } else {
+        const double d = xi_v - xj;
+        acc0 += w * (d * d - xj * xj);  // xj == 0 when not stored
+    }
+}
+
+// FMT 0: packed rows, 8 lanes per row (<= 7 entries);  FMT 1: packed rows, 16 lanes per row (<= 15 entries);
+// FMT 2: CSR rows, 8 lanes per row (any length; float64 weights).
+template <typename XT, int MODE, int FMT, bool PERM>
+__global__ void __launch_bounds__(AC_T, 4) ac_sparse_kernel(const __grid_constant__ AcSparseParams p) {
+    constexpr int LPR = FMT == 1 ? 16 : 8;
+    constexpr int RPW = 32 / LPR;        // rows per warp step
+    constexpr int NSUB = 32 / RPW;       // warp steps per block of 32 entries
+    constexpr int GRP = 4;               // warp steps whose row slots are loaded together (independent loads in flight)
+    extern __shared__ __align__(16) unsigned char ac_smem[];
+    __shared__ double s_red[6][AC_NW];
+    __shared__ double s_mean;
+    __shared__ int s_next;
+    uint2* S = p.s_global ? p.s_global + (size_t)blockIdx.x * p.nwords : reinterpret_cast<uint2*>(ac_smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = lane % LPR, sub = lane / LPR;
+    const double dn = (double)p.n;
+    ac_zero_words(S, p.nwords);
+    __syncthreads();
+    for (;;) {
+        if (threadIdx.x == 0) s_next = atomicAdd(p.counter, 1);
+        __syncthreads();
+        const int k = s_next;
+        if (k >= p.n_feat) break;
+        const int g = p.order ? p.order[k] : k;
+        const int64_t b = p.seg_start[g];
+        const int len = p.seg_len[g];
+        const int32_t* __restrict__ xi = p.xi + b;
+        const XT* __restrict__ xv = reinterpret_cast<const XT*>(p.xv) + b;
+        const int len4 = (len + 3) >> 2;
+        // ---- phase 1: mark the stored observations, rank of the first one of every word, sum of the values ----
+        double q[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int v = threadIdx.x; v < len4; v += AC_T) {
+            const int4 iv = __ldg(reinterpret_cast<const int4*>(xi) + v);
+            const int prev = v > 0 ? __ldg(xi + 4 * v - 1) : -1;
+            const int ii[4] = {iv.x, iv.y, iv.z, iv.w};
+            if (!PERM) {
+                double xs[4];
+                if (sizeof(XT) == 4) {
+                    const float4 f = __ldg(reinterpret_cast<const float4*>(xv) + v);
+                    xs[0] = f.x, xs[1] = f.y, xs[2] = f.z, xs[3] = f.w;
+                } else {
+                    const double2 d0 = __ldg(reinterpret_cast<const double2*>(xv) + 2 * v);
+                    const double2 d1 = __ldg(reinterpret_cast<const double2*>(xv) + 2 * v + 1);
+                    xs[0] = d0.x, xs[1] = d0.y, xs[2] = d1.x, xs[3] = d1.y;
+                }
+                q[0] += ((xs[0] + xs[1]) + xs[2]) + xs[3];  // pads hold 0
+            }
+            int cur_w = prev >= 0 ? prev >> 5 : -1;  // word of the previous entry
+            int open_w = -1;
+            unsigned int mask = 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = ii[t];
+                if (i < 0) break;
+                const int w = i >> 5;
+                if (w != open_w) {
+                    if (open_w >= 0) atomicOr(&S[open_w].x, mask);
+                    open_w = w;
+                    mask = 0;
+                }
+                mask |= 1u << (i & 31);
+                if (w != cur_w) {
+                    S[w].y = (unsigned int)(4 * v + t);  // first stored observation of this word
+                    cur_w = w;
+                }
+            }
+            if (open_w >= 0) atomicOr(&S[open_w].x, mask);
+        }
+        double m;
+        if (!PERM) {
+            double q1[1] = {q[0]};
+            ac_block_reduce<1>(q1, s_red);  // contains a __syncthreads after the shuffles
+            if (threadIdx.x == 0) s_mean = q1[0] / dn;
+            __syncthreads();
+            m = s_mean;
+            q[0] = 0.0;
+        } else {
+            m = p.aux[g];
+            __syncthreads();
+        }
+        // ---- phase 2: walk the rows of W of the stored observations ----
+        // q[0], q[1]: slot accumulators;  q[2..5] (unpermuted pass only): D, E, sum z^2, Geary column term
+        for (int base = warp * 32; base < len; base += AC_NW * 32) {
+            const int e = base + lane;
+            const int my_i = e < len ? __ldg(xi + e) : -1;
+            const XT my_x = e < len ? __ldg(xv + e) : (XT)0;
+#pragma unroll
+            for (int s0 = 0; s0 < NSUB; s0 += GRP) {
+                int ri[GRP];
+                double rx[GRP];
+                uint2 rs[GRP];
+                int rbeg[GRP], rend[GRP];
+#pragma unroll
+                for (int s = 0; s < GRP; ++s) {
+                    const int src = (s0 + s) * RPW + sub;
+                    ri[s] = __shfl_sync(0xffffffffu, my_i, src);
+                    rx[s] = (double)__shfl_sync(0xffffffffu, my_x, src);
+                    rs[s] = make_uint2(0xffffffffu, 0u);
+                    rbeg[s] = rend[s] = 0;
+                    if (ri[s] >= 0) {
+                        const int64_t r = PERM ? (int64_t)__ldg(p.perm + ri[s]) : (int64_t)ri[s];
+                        if (FMT == 2) {
+                            rbeg[s] = __ldg(p.wp + r);
+                            rend[s] = __ldg(p.wp + r + 1);
+                        } else {
+                            rs[s] = __ldg(p.rows + r * LPR + slot);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < GRP; ++s) {
+                    if (ri[s] < 0) continue;
+                    const double xv_i = rx[s], zi = xv_i - m;
+                    if (FMT == 2) {
+                        for (int ew = rbeg[s] + slot; ew < rend[s]; ew += LPR)
+                            ac_slot<XT, MODE>(S, xv, __ldg(p.wi + ew), __ldg(p.wd + ew), xv_i, zi, m, q[0], q[1]);
+                        if (!PERM && slot == 0) {
+                            const double c = __ldg(p.csum + ri[s]);
+                            q[2] = fma(c, zi, q[2]);
+                            q[3] += c;
+                            q[4] = fma(zi, zi, q[4]);
+                            q[5] = fma(c, xv_i * xv_i, q[5]);
+                        }
+                    } else if (slot == LPR - 1) {
+                        if (!PERM) {
+                            const double c = __longlong_as_double((long long)(((unsigned long long)rs[s].y << 32) | rs[s].x));
+                            q[2] = fma(c, zi, q[2]);
+                            q[3] += c;
+                            q[4] = fma(zi, zi, q[4]);
+                            q[5] = fma(c, xv_i * xv_i, q[5]);
+                        }
+                    } else {
+                        const int j = (int)rs[s].x;
+                        if (j >= 0) ac_slot<XT, MODE>(S, xv, j, (double)__uint_as_float(rs[s].y), xv_i, zi, m, q[0], q[1]);
+                    }
+                }
+            }
+        }
+        // ---- phase 3: combine, finish the feature, clear the touched words ----
+        if (!PERM) {
+            ac_block_reduce<6>(q, s_red);
+        } else {
+            double q2[2] = {q[0], q[1]};
+            ac_block_reduce<2>(q2, s_red);
+            q[0] = q2[0];
+            q[1] = q2[1];
+        }
+        if (threadIdx.x == 0) {
+            double D, E, Z2, CX;
+            if (!PERM) {
+                D = q[2], E = q[3], Z2 = q[4], CX = q[5];
+                p.aux[g] = m;
+                p.aux[p.n_feat + g] = Z2;
+                p.aux[2 * p.n_feat + g] = D;
+                p.aux[3 * p.n_feat + g] = E;
+                p.aux[4 * p.n_feat + g] = CX;
+            } else {
+                Z2 = p.aux[p.n_feat + g];
+                D = p.aux[2 * p.n_feat + g];
+                E = p.aux[3 * p.n_feat + g];
+                CX = p.aux[4 * p.n_feat + g];
+            }
+            const double den = Z2 + (dn - (double)len) * m * m;
+            double r;
+            if (den == 0.0) {
+                r = __longlong_as_double(0x7ff8000000000000LL);  // constant feature -> NaN (scanpy)
+            } else if (MODE == 0) {
+                const double num = q[0] - m * (D - m * (p.s0 - E) - q[1]);
+                r = dn / p.s0 * num / den;
+            } else {
+                const double num = q[0] + CX;
+                r = ((dn - 1.0) * num) / (2.0 * p.s0 * den);
+            }
+            p.out[g] = r;
+        }
+        for (int v = threadIdx.x; v < len4; v += AC_T) {
+            const int4 iv = __ldg(reinterpret_cast<const int4*>(xi) + v);
+            if (iv.x >= 0) S[iv.x >> 5] = make_uint2(0u, 0u);
+            if (iv.y >= 0) S[iv.y >> 5] = make_uint2(0u, 0u);
+            if (iv.z >= 0) S[iv.z >> 5] = make_uint2(0u, 0u);
+            if (iv.w >= 0) S[iv.w >> 5] = make_uint2(0u, 0u);
+        }
+        __syncthreads();
     }
 }
 
@@ -216,26 +719,127 @@ struct sqb_autocorr {
     sqb_ctx* ctx = nullptr;
     int64_t n = 0, nnz = 0;
     double s0 = 0.0;
+    int w_fmt = 2;  // 0 packed 8 lanes, 1 packed 16 lanes, 2 CSR
     DevBuf<int32_t> d_wp, d_wi;
-    DevBuf<double> d_wd;
+    DevBuf<double> d_wd, d_csum;
+    DevBuf<uint2> d_rows;
     // loaded X
-    int kind = 0;     // 0 none, 1 dense feat x obs, 2 dense obs x feat (zero copy tiles), 3 CSR by feature
+    int kind = 0;     // 0 none, 1 dense feat x obs, 2 dense obs x feat (zero copy tiles), 3 sparse (padded CSR by feature)
     int x_dtype = 0;  // 0 f32, 1 f64
     int64_t n_feat = 0, x_nnz = 0;
-    DevBuf<uint8_t> d_x;   // dense matrix or CSR values
-    DevBuf<int64_t> d_xp;
-    DevBuf<int32_t> d_xi;
+    DevBuf<uint8_t> d_x;  // dense matrix or padded sparse values
+    DevBuf<int64_t> d_xp;  // padded segment starts (n_feat + 1)
+    DevBuf<int32_t> d_xi, d_len, d_order;
     DevBuf<uint8_t> d_tile;
-    DevBuf<double> d_sums, d_partial, d_pnum, d_pden, d_out;
+    DevBuf<double> d_sums, d_partial, d_pnum, d_pden, d_out, d_aux, d_out_perms;
     DevBuf<int64_t> d_perm;
-    int tiles_per_launch = 8;  // 256 features per launch: enough CTAs to fill 148 SMs in every phase
+    DevBuf<int32_t> d_perm32;
+    DevBuf<unsigned int> d_seen;
+    DevBuf<uint2> d_bitmap;  // global-memory bitmap scratch (large n)
+    DevBuf<int> d_flags;     // [0] error flags, [1] feature queue counter
+    bool aux_valid = false;
+    int tiles_per_launch = 8;  // dense path: 256 features per launch
     bool ran = false;
 };
 
 static int xsize(int dt) { return dt == 0 ? 4 : 8; }
 
+static const char* ac_err_text(int f) {
+    if (f & AC_ERR_INDPTR) return "indptr is not a non-decreasing sequence from 0 to nnz";
+    if (f & AC_ERR_INDEX) return "index out of range";
+    if (f & AC_ERR_DUP) return "an observation is stored twice for one feature (sum duplicates first)";
+    if (f & AC_ERR_PERM) return "row_perm is not a permutation";
+    return "invalid input";
+}
+
+// bitmap placement: shared memory when 8 bytes per 32 observations fit, else one global scratch slice per CTA
+struct AcGeom {
+    int nwords = 0;
+    size_t smem = 0;
+    int ctas = 0;
+    bool global = false;
+};
+
+static int ac_geometry(sqb_autocorr* h, const void* kernel, AcGeom* g) {
+    sqb_ctx* c = h->ctx;
+    g->nwords = (int)ceil_div64(h->n, 32);
+    const size_t need = (size_t)g->nwords * sizeof(uint2);
+    const size_t avail = c->smem_optin > 4096 ? c->smem_optin - 4096 : 0;  // static shared memory of the kernels
+    g->global = need > avail;
+    g->smem = g->global ? 0 : need;
+    if (!g->global && g->smem > 48 * 1024) SQB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem));
+    int per_sm = 0;
+    SQB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, AC_T, g->smem));
+    if (per_sm < 1) per_sm = 1;
+    g->ctas = per_sm * c->sm_count;
+    if (g->global) SQB_TRY(h->d_bitmap.alloc((size_t)g->ctas * g->nwords));
+    return SQB_OK;
+}
+
+template <typename XT, int MODE, int FMT, bool PERM>
+static int ac_sparse_launch(sqb_autocorr* h, const AcSparseParams& base) {
+    sqb_ctx* c = h->ctx;
+    const void* kernel = (const void*)ac_sparse_kernel<XT, MODE, FMT, PERM>;
+    AcGeom geo;
+    SQB_TRY(ac_geometry(h, kernel, &geo));
+    AcSparseParams p = base;
+    p.nwords = geo.nwords;
+    p.s_global = geo.global ? h->d_bitmap.p : nullptr;
+    int64_t ctas = geo.ctas;
+    if (ctas > h->n_feat) ctas = h->n_feat;
+    SQB_CUDA(cudaMemsetAsync(h->d_flags.p + 1, 0, sizeof(int), c->stream));
+    SqbLaunchScope scope(c, SQB_K_AUTOCORR_MAIN);
+    ac_sparse_kernel<XT, MODE, FMT, PERM><<<(unsigned)ctas, AC_T, geo.smem, c->stream>>>(p);
+    SQB_POST_LAUNCH();
+    return SQB_OK;
+}
+
+template <typename XT, int MODE, bool PERM>
+static int ac_sparse_fmt(sqb_autocorr* h, const AcSparseParams& p) {
+    switch (h->w_fmt) {
+        case 0: return ac_sparse_launch<XT, MODE, 0, PERM>(h, p);
+        case 1: return ac_sparse_launch<XT, MODE, 1, PERM>(h, p);
+        default: return ac_sparse_launch<XT, MODE, 2, PERM>(h, p);
+    }
+}
+
+// one pass over all features; d_perm32 == nullptr: unpermuted (also refreshes the per-feature invariants)
+static int ac_run_sparse(sqb_autocorr* h, int mode, const int32_t* d_perm32, double* d_out) {
+    AcSparseParams p;
+    memset(&p, 0, sizeof(p));
+    p.n = h->n;
+    p.n_feat = h->n_feat;
+    p.seg_start = h->d_xp.p;
+    p.seg_len = h->d_len.p;
+    p.order = h->d_order.p;
+    p.xi = h->d_xi.p;
+    p.xv = h->d_x.p;
+    p.rows = h->d_rows.p;
+    p.wp = h->d_wp.p;
+    p.wi = h->d_wi.p;
+    p.wd = h->d_wd.p;
+    p.csum = h->d_csum.p;
+    p.s0 = h->s0;
+    p.perm = d_perm32;
+    p.aux = h->d_aux.p;
+    p.out = d_out;
+    p.counter = h->d_flags.p + 1;
+    const bool f32 = h->x_dtype == 0;
+    if (!d_perm32) {
+        int rc;
+        if (mode == 0)
+            rc = f32 ? ac_sparse_fmt<float, 0, false>(h, p) : ac_sparse_fmt<double, 0, false>(h, p);
+        else
+            rc = f32 ? ac_sparse_fmt<float, 1, false>(h, p) : ac_sparse_fmt<double, 1, false>(h, p);
+        if (rc == SQB_OK) h->aux_valid = true;
+        return rc;
+    }
+    if (mode == 0) return f32 ? ac_sparse_fmt<float, 0, true>(h, p) : ac_sparse_fmt<double, 0, true>(h, p);
+    return f32 ? ac_sparse_fmt<float, 1, true>(h, p) : ac_sparse_fmt<double, 1, true>(h, p);
+}
+
 template <typename XT>
-static int ac_run_typed(sqb_autocorr* h, int mode, const int64_t* d_perm) {
+static int ac_run_dense(sqb_autocorr* h, int mode, const int64_t* d_perm) {
     sqb_ctx* c = h->ctx;
     const int64_t n = h->n, G = h->n_feat;
     const int64_t ntiles = ceil_div64(G, TILE);
@@ -252,7 +856,6 @@ static int ac_run_typed(sqb_autocorr* h, int mode, const int64_t* d_perm) {
     SQB_TRY(h->d_partial.alloc((size_t)TPL * nw * TILE));
     SQB_TRY(h->d_pnum.alloc((size_t)TPL * nw * TILE));
     SQB_TRY(h->d_pden.alloc((size_t)TPL * nw * TILE));
-    SQB_TRY(h->d_out.alloc((size_t)G));
     const bool zero_copy = (h->kind == 2);
     if (!zero_copy) SQB_TRY(h->d_tile.alloc((size_t)TPL * n * TILE * sizeof(XT)));
     XT* Dbuf = reinterpret_cast<XT*>(h->d_tile.p);
@@ -270,31 +873,21 @@ static int ac_run_typed(sqb_autocorr* h, int mode, const int64_t* d_perm) {
             D = Dbuf;
             pitch = TILE;
             tile_stride = n * TILE;
-        }
-        if (h->kind == 3) {
-            SQB_CUDA(cudaMemsetAsync(Dbuf, 0, (size_t)nt * n * TILE * sizeof(XT), c->stream));
             SqbLaunchScope scope(c, SQB_K_AUTOCORR_PREP);
-            ac_scatter_kernel<XT><<<(unsigned)(nt * TILE), 256, 0, c->stream>>>(h->d_xp.p, h->d_xi.p, X, g0, G, n, Dbuf,
-                                                                                  h->d_sums.p);
+            dim3 grid((unsigned)ceil_div64(n, 32), (unsigned)nt);
+            ac_transpose_kernel<XT><<<grid, 256, 0, c->stream>>>(X, g0, G, n, Dbuf);
             SQB_POST_LAUNCH();
-        } else {
-            if (h->kind == 1) {
-                SqbLaunchScope scope(c, SQB_K_AUTOCORR_PREP);
-                dim3 grid((unsigned)ceil_div64(n, 32), (unsigned)nt);
-                ac_transpose_kernel<XT><<<grid, 256, 0, c->stream>>>(X, g0, G, n, Dbuf);
-                SQB_POST_LAUNCH();
-            }
-            {
-                SqbLaunchScope scope(c, SQB_K_AUTOCORR_PREP);
-                dim3 grid((unsigned)ctas, (unsigned)nt);
-                ac_colsum_kernel<XT><<<grid, 256, 0, c->stream>>>(D, pitch, tile_stride, n, obs_per_warp, h->d_partial.p, g0, G);
-                SQB_POST_LAUNCH();
-            }
-            {
-                SqbLaunchScope scope(c, SQB_K_AUTOCORR_PREP);
-                ac_colsum_final_kernel<<<nt, 32, 0, c->stream>>>(h->d_partial.p, nw, h->d_sums.p);
-                SQB_POST_LAUNCH();
-            }
+        }
+        {
+            SqbLaunchScope scope(c, SQB_K_AUTOCORR_PREP);
+            dim3 grid((unsigned)ctas, (unsigned)nt);
+            ac_colsum_kernel<XT><<<grid, 256, 0, c->stream>>>(D, pitch, tile_stride, n, obs_per_warp, h->d_partial.p, g0, G);
+            SQB_POST_LAUNCH();
+        }
+        {
+            SqbLaunchScope scope(c, SQB_K_AUTOCORR_PREP);
+            ac_colsum_final_kernel<<<nt, 32, 0, c->stream>>>(h->d_partial.p, nw, h->d_sums.p);
+            SQB_POST_LAUNCH();
         }
         {
             SqbLaunchScope scope(c, SQB_K_AUTOCORR_MAIN);
@@ -321,79 +914,174 @@ static int ac_run_typed(sqb_autocorr* h, int mode, const int64_t* d_perm) {
     return SQB_OK;
 }
 
-template <typename XT>
-static int ac_transpose_csr(sqb_autocorr* h, const int64_t* h_xp, const int32_t* h_xi, const void* h_xv, int64_t n_feat) {
-    // input: CSR by observation (n rows, n_feat columns) on the host -> CSR by feature on the device
+// read the error flag word (synchronises the stream)
+static int ac_check_flags(sqb_autocorr* h, const char* where) {
     sqb_ctx* c = h->ctx;
-    const int64_t n = h->n, nnz = h_xp[n];
-    DevBuf<int64_t> t_xp;
-    DevBuf<int32_t> t_xi;
-    DevBuf<uint8_t> t_xv;
-    DevBuf<unsigned long long> cnt;
-    int rc;
+    int f = 0;
+    SQB_CUDA(cudaMemcpyAsync(&f, h->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SQB_CUDA(cudaStreamSynchronize(c->stream));
+    if (f != 0) {
+        SQB_CUDA(cudaMemsetAsync(h->d_flags.p, 0, sizeof(int), c->stream));
+        sqb_set_error("%s: %s", where, ac_err_text(f));
+        return SQB_ERR_INVALID;
+    }
+    return SQB_OK;
+}
+
+// raw segments by feature (ptr / idx / val on the device, any order inside a segment) -> padded, ordered layout
+template <typename XT>
+static int ac_build_segments(sqb_autocorr* h, const int64_t* d_ptr, const unsigned int* d_cnt, int64_t* d_pad,
+                             const int32_t* d_idx, const XT* d_val, int64_t nnz, int64_t n_feat) {
+    sqb_ctx* c = h->ctx;
+    const int64_t cap = nnz + 4 * n_feat + 4;
+    SQB_TRY(h->d_xi.alloc((size_t)cap));
+    SQB_TRY(h->d_x.alloc((size_t)cap * sizeof(XT)));
+    SQB_TRY(h->d_len.alloc((size_t)n_feat));
+    SQB_TRY(h->d_order.alloc((size_t)n_feat));
+    SQB_TRY(h->d_aux.alloc((size_t)5 * n_feat));
+    SQB_TRY(h->d_out.alloc((size_t)n_feat));
+    const void* kernel = (const void*)ac_rank_sort_kernel<XT>;
+    AcGeom geo;
+    SQB_TRY(ac_geometry(h, kernel, &geo));
+    int64_t ctas = geo.ctas < n_feat ? geo.ctas : n_feat;
+    {
+        SqbLaunchScope scope(c, SQB_K_AUTOCORR_PREP);
+        ac_rank_sort_kernel<XT><<<(unsigned)ctas, AC_T, geo.smem, c->stream>>>(d_ptr, d_idx, d_val, d_pad, h->d_xi.p,
+                                                                             reinterpret_cast<XT*>(h->d_x.p), h->d_len.p, h->n,
+                                                                             n_feat, geo.nwords, geo.global ? h->d_bitmap.p : nullptr,
+                                                                             h->d_flags.p);
+        SQB_POST_LAUNCH();
+    }
+    // features by decreasing length: the queue hands out the long ones first (LPT), the tail of the grid stays short
+    {
+        DevBuf<unsigned int> keys_out;
+        DevBuf<int32_t> iota;
+        DevBuf<uint8_t> tmp;
+        keys_out.bind(c->stream);
+        iota.bind(c->stream);
+        tmp.bind(c->stream);
+        int rc;
+        if ((rc = keys_out.alloc(n_feat)) || (rc = iota.alloc(n_feat))) {
+            keys_out.release();
+            iota.release();
+            return rc;
+        }
+        std::vector<int32_t> hi((size_t)n_feat);
+        for (int64_t g = 0; g < n_feat; ++g) hi[g] = (int32_t)g;
+        cudaError_t e = cudaMemcpyAsync(iota.p, hi.data(), n_feat * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+        size_t tmp_bytes = 0;
+        if (e == cudaSuccess)
+            e = cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, d_cnt, keys_out.p, iota.p, h->d_order.p, (int)n_feat, 0, 32,
+                                                          c->stream);
+        if (e == cudaSuccess && tmp.alloc(tmp_bytes > 0 ? tmp_bytes : 1) != SQB_OK) e = cudaErrorMemoryAllocation;
+        if (e == cudaSuccess)
+            e = cub::DeviceRadixSort::SortPairsDescending(tmp.p, tmp_bytes, d_cnt, keys_out.p, iota.p, h->d_order.p, (int)n_feat, 0, 32,
+                                                          c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // hi must outlive the copy
+        keys_out.release();
+        iota.release();
+        tmp.release();
+        if (e != cudaSuccess) {
+            sqb_set_error("autocorr load: %s", cudaGetErrorString(e));
+            return SQB_ERR_CUDA;
+        }
+        c->launches += 2;
+    }
+    // the padded starts now belong to the handle
+    SQB_TRY(h->d_xp.alloc((size_t)n_feat + 1));
+    SQB_CUDA(cudaMemcpyAsync(h->d_xp.p, d_pad, (n_feat + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, c->stream));
+    return SQB_OK;
+}
+
+template <typename XT>
+static int ac_load_csr_typed(sqb_autocorr* h, const int64_t* h_xp, const int32_t* h_xi, const void* h_xv, int layout,
+                             int64_t n_feat, int64_t nnz) {
+    sqb_ctx* c = h->ctx;
+    const int64_t n = h->n;
+    const int64_t rows = layout == 0 ? n_feat : n;
+    const int64_t nz1 = nnz > 0 ? nnz : 1;
+    DevBuf<int64_t> r_ptr, t_ptr, pad;
+    DevBuf<int32_t> r_idx, t_idx;
+    DevBuf<uint8_t> r_val, t_val;
+    DevBuf<unsigned int> cnt;
+    DevBuf<unsigned long long> cursor;
     auto cleanup = [&]() {
-        t_xp.release();
-        t_xi.release();
-        t_xv.release();
-        cnt.release();
+        r_ptr.release(), t_ptr.release(), pad.release(), r_idx.release(), t_idx.release(), r_val.release(), t_val.release();
+        cnt.release(), cursor.release();
     };
-    if ((rc = t_xp.alloc(n + 1)) || (rc = t_xi.alloc(nnz > 0 ? nnz : 1)) || (rc = t_xv.alloc((size_t)(nnz > 0 ? nnz : 1) * sizeof(XT))) ||
-        (rc = cnt.alloc(n_feat + 1)) || (rc = h->d_xp.alloc(n_feat + 1)) || (rc = h->d_xi.alloc(nnz > 0 ? nnz : 1)) ||
-        (rc = h->d_x.alloc((size_t)(nnz > 0 ? nnz : 1) * sizeof(XT)))) {
+    int rc;
+    if ((rc = r_ptr.alloc(rows + 1)) || (rc = r_idx.alloc(nz1)) || (rc = r_val.alloc((size_t)nz1 * sizeof(XT))) ||
+        (rc = cnt.alloc(n_feat + 1)) || (rc = pad.alloc(n_feat + 1)) || (rc = h->d_flags.alloc(2))) {
         cleanup();
         return rc;
     }
-    cudaError_t e = cudaMemcpyAsync(t_xp.p, h_xp, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess && nnz > 0 && sqb_h2d(c, t_xi.p, h_xi, nnz * sizeof(int32_t)) != SQB_OK) e = cudaErrorUnknown;
-    if (e == cudaSuccess && nnz > 0 && sqb_h2d(c, t_xv.p, h_xv, nnz * sizeof(XT)) != SQB_OK) e = cudaErrorUnknown;
-    if (e == cudaSuccess) e = cudaMemsetAsync(cnt.p, 0, (n_feat + 1) * sizeof(unsigned long long), c->stream);
-    if (e != cudaSuccess) {
+    auto fail = [&](cudaError_t e) {
         cleanup();
         sqb_set_error("autocorr load: %s", cudaGetErrorString(e));
         return SQB_ERR_CUDA;
+    };
+    cudaError_t e = cudaMemsetAsync(h->d_flags.p, 0, 2 * sizeof(int), c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r_ptr.p, h_xp, (rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) return fail(e);
+    if (nnz > 0) {
+        if ((rc = sqb_h2d(c, r_idx.p, h_xi, nnz * sizeof(int32_t))) || (rc = sqb_h2d(c, r_val.p, h_xv, (size_t)nnz * sizeof(XT)))) {
+            cleanup();
+            return rc;
+        }
     }
     {
         SqbLaunchScope scope(c, SQB_K_AUTOCORR_PREP);
-        ac_colcount_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(t_xi.p, nnz, cnt.p);
+        ac_check_indptr_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(r_ptr.p, rows, nnz, h->d_flags.p);
     }
-    std::vector<unsigned long long> hc(n_feat + 1);
-    e = cudaMemcpyAsync(hc.data(), cnt.p, (n_feat + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    if (e != cudaSuccess) {
-        cleanup();
-        sqb_set_error("autocorr load: %s", cudaGetErrorString(e));
-        return SQB_ERR_CUDA;
-    }
-    std::vector<int64_t> ptr(n_feat + 1);
-    std::vector<unsigned long long> cur(n_feat + 1);
-    int64_t run = 0;
-    for (int64_t g = 0; g < n_feat; ++g) {
-        ptr[g] = run;
-        cur[g] = (unsigned long long)run;
-        run += (int64_t)hc[g];
-    }
-    ptr[n_feat] = run;
-    cur[n_feat] = (unsigned long long)run;
-    e = cudaMemcpyAsync(h->d_xp.p, ptr.data(), (n_feat + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(cnt.p, cur.data(), (n_feat + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream);
-    if (e != cudaSuccess) {
-        cleanup();
-        sqb_set_error("autocorr load: %s", cudaGetErrorString(e));
-        return SQB_ERR_CUDA;
+    const int64_t* seg_ptr;
+    const int32_t* seg_idx;
+    const XT* seg_val;
+    if (layout == 0) {
+        SqbLaunchScope scope(c, SQB_K_AUTOCORR_PREP);
+        ac_seglen_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(r_ptr.p, n_feat, n, cnt.p, h->d_flags.p);
+        seg_ptr = r_ptr.p;
+        seg_idx = r_idx.p;
+        seg_val = reinterpret_cast<const XT*>(r_val.p);
+    } else {
+        if ((rc = t_ptr.alloc(n_feat + 1)) || (rc = t_idx.alloc(nz1)) || (rc = t_val.alloc((size_t)nz1 * sizeof(XT))) ||
+            (rc = cursor.alloc(n_feat + 1))) {
+            cleanup();
+            return rc;
+        }
+        e = cudaMemsetAsync(cnt.p, 0, (n_feat + 1) * sizeof(unsigned int), c->stream);
+        if (e != cudaSuccess) return fail(e);
+        {
+            SqbLaunchScope scope(c, SQB_K_AUTOCORR_PREP);
+            const size_t hist_bytes = (size_t)n_feat * sizeof(unsigned int);
+            const int hist_smem = hist_bytes <= 160 * 1024 ? 1 : 0;
+            if (hist_smem && hist_bytes > 48 * 1024)
+                cudaFuncSetAttribute(ac_colcount_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes);
+            ac_colcount_kernel<<<c->sm_count * (hist_smem ? 1 : 8), 1024, hist_smem ? hist_bytes : 0, c->stream>>>(r_idx.p, nnz, n_feat,
+                                                                                                              hist_smem, cnt.p, h->d_flags.p);
+        }
     }
     {
         SqbLaunchScope scope(c, SQB_K_AUTOCORR_PREP);
-        ac_coltranspose_kernel<XT><<<c->sm_count * 8, 256, 0, c->stream>>>(t_xp.p, t_xi.p, reinterpret_cast<const XT*>(t_xv.p), n,
-                                                                           cnt.p, h->d_xi.p, reinterpret_cast<XT*>(h->d_x.p));
+        // layout 0: the caller's indptr already is the plain prefix, only the padded starts are needed
+        ac_scan_counts_kernel<<<1, 1024, 0, c->stream>>>(cnt.p, n_feat, layout == 0 ? nullptr : t_ptr.p, pad.p,
+                                                         layout == 0 ? nullptr : cursor.p);
     }
-    e = cudaStreamSynchronize(c->stream);
+    if (layout != 0) {
+        SqbLaunchScope scope(c, SQB_K_AUTOCORR_PREP);
+        ac_coltranspose_kernel<XT><<<c->sm_count * 8, 256, 0, c->stream>>>(r_ptr.p, r_idx.p, reinterpret_cast<const XT*>(r_val.p), n, n_feat,
+                                                                           cursor.p, t_idx.p, reinterpret_cast<XT*>(t_val.p));
+        seg_ptr = t_ptr.p;
+        seg_idx = t_idx.p;
+        seg_val = reinterpret_cast<const XT*>(t_val.p);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(e);
+    rc = ac_build_segments<XT>(h, seg_ptr, cnt.p, pad.p, seg_idx, seg_val, nnz, n_feat);
+    if (rc == SQB_OK) rc = ac_check_flags(h, "sqb_autocorr_load_csr");  // synchronises: the temporaries may go
+    else cudaStreamSynchronize(c->stream);
     cleanup();
-    if (e != cudaSuccess) {
-        sqb_set_error("autocorr load: %s", cudaGetErrorString(e));
-        return SQB_ERR_CUDA;
-    }
     h->x_nnz = nnz;
-    return SQB_OK;
+    return rc;
 }
 
 extern "C" {
@@ -406,29 +1094,57 @@ int sqb_autocorr_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const int32_t* w_i
     SQB_CHECK(w_dtype == 0 || w_dtype == 1, SQB_ERR_INVALID, "sqb_autocorr_create: w_dtype must be 0 (f32) or 1 (f64)");
     SQB_CHECK(w_indptr[0] == 0 && (int64_t)w_indptr[n] == nnz, SQB_ERR_INVALID, "sqb_autocorr_create: inconsistent indptr");
     SQB_CHECK(nnz == 0 || (w_indices && w_data), SQB_ERR_INVALID, "sqb_autocorr_create: null W arrays");
+    // one host pass over W (it is small next to X): validation, float64 weights (scanpy casts W.data to float64), S0 =
+    // sum(W.data), column sums in CSR order (deterministic), longest row
+    int64_t maxdeg = 0;
+    for (int64_t r = 0; r < n; ++r) {
+        const int64_t d = (int64_t)w_indptr[r + 1] - (int64_t)w_indptr[r];
+        SQB_CHECK(d >= 0 && w_indptr[r + 1] <= nnz, SQB_ERR_INVALID, "sqb_autocorr_create: indptr decreases at row %lld", (long long)r);
+        if (d > maxdeg) maxdeg = d;
+    }
+    std::vector<double> wd((size_t)(nnz > 0 ? nnz : 1)), csum((size_t)n, 0.0);
+    double s0 = 0.0;
+    for (int64_t e = 0; e < nnz; ++e) {
+        const int32_t j = w_indices[e];
+        SQB_CHECK(j >= 0 && j < n, SQB_ERR_INVALID, "sqb_autocorr_create: column index %d out of range at entry %lld", j, (long long)e);
+        wd[e] = w_dtype == 0 ? (double)((const float*)w_data)[e] : ((const double*)w_data)[e];
+        s0 += wd[e];
+        csum[j] += wd[e];
+    }
     SQB_CUDA(cudaSetDevice(ctx->device));
     sqb_autocorr* h = new sqb_autocorr();
     h->ctx = ctx;
     h->n = n;
     h->nnz = nnz;
-    std::vector<double> wd((size_t)(nnz > 0 ? nnz : 1));
-    double s0 = 0.0;
-    for (int64_t e = 0; e < nnz; ++e) {
-        wd[e] = w_dtype == 0 ? (double)((const float*)w_data)[e] : ((const double*)w_data)[e];
-        s0 += wd[e];  // S0 = sum(W.data) in float64 (scanpy casts W.data to float64 first)
-    }
     h->s0 = s0;
+    // packed rows hold float32 weights: only for float32 W (lossless); float64 W walks the CSR
+    h->w_fmt = (w_dtype == 0 && maxdeg <= 7) ? 0 : (w_dtype == 0 && maxdeg <= 15) ? 1 : 2;
+    const int lpr = h->w_fmt == 0 ? 8 : 16;
     int rc;
-    if ((rc = h->d_wp.alloc(n + 1)) || (rc = h->d_wi.alloc(nnz > 0 ? nnz : 1)) || (rc = h->d_wd.alloc(nnz > 0 ? nnz : 1))) {
+    if ((rc = h->d_wp.alloc(n + 1)) || (rc = h->d_wi.alloc(nnz > 0 ? nnz : 1)) || (rc = h->d_wd.alloc(nnz > 0 ? nnz : 1)) ||
+        (rc = h->d_csum.alloc(n)) || (rc = h->d_flags.alloc(2)) || (h->w_fmt != 2 && (rc = h->d_rows.alloc((size_t)n * lpr)))) {
         sqb_autocorr_destroy(h);
         return rc;
     }
-    SQB_CUDA(cudaMemcpyAsync(h->d_wp.p, w_indptr, (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    if (nnz > 0) {
-        SQB_CUDA(cudaMemcpyAsync(h->d_wi.p, w_indices, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-        SQB_CUDA(cudaMemcpyAsync(h->d_wd.p, wd.data(), nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = cudaMemcpyAsync(h->d_wp.p, w_indptr, (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(h->d_wi.p, w_indices, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(h->d_wd.p, wd.data(), nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_csum.p, csum.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->d_flags.p, 0, 2 * sizeof(int), ctx->stream);
+    if (e == cudaSuccess && h->w_fmt != 2) {
+        ctx->launches += 1;
+        if (h->w_fmt == 0)
+            ac_pack_rows_kernel<8><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(h->d_wp.p, h->d_wi.p, h->d_wd.p, h->d_csum.p, n, h->d_rows.p);
+        else
+            ac_pack_rows_kernel<16><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(h->d_wp.p, h->d_wi.p, h->d_wd.p, h->d_csum.p, n, h->d_rows.p);
+        e = cudaGetLastError();
     }
-    SQB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // wd / csum are host temporaries
+    if (e != cudaSuccess) {
+        sqb_autocorr_destroy(h);
+        sqb_set_error("sqb_autocorr_create: %s", cudaGetErrorString(e));
+        return SQB_ERR_CUDA;
+    }
     *out = h;
     return SQB_OK;
 }
@@ -439,16 +1155,26 @@ int sqb_autocorr_destroy(sqb_autocorr* h) {
     h->d_wp.release();
     h->d_wi.release();
     h->d_wd.release();
+    h->d_csum.release();
+    h->d_rows.release();
     h->d_x.release();
     h->d_xp.release();
     h->d_xi.release();
+    h->d_len.release();
+    h->d_order.release();
     h->d_tile.release();
     h->d_sums.release();
     h->d_partial.release();
     h->d_pnum.release();
     h->d_pden.release();
     h->d_out.release();
+    h->d_aux.release();
+    h->d_out_perms.release();
     h->d_perm.release();
+    h->d_perm32.release();
+    h->d_seen.release();
+    h->d_bitmap.release();
+    h->d_flags.release();
     delete h;
     return SQB_OK;
 }
@@ -463,12 +1189,14 @@ int sqb_autocorr_load_dense(sqb_autocorr* h, const void* x, int x_dtype, int lay
     const size_t bytes = (size_t)n_features * h->n * xsize(x_dtype);
     // zero-copy tiles read up to 31 elements past the last feature of a row: pad the allocation
     SQB_TRY(h->d_x.alloc(bytes + 64 * 8));
+    SQB_TRY(h->d_out.alloc((size_t)n_features));
     SQB_TRY(sqb_h2d(c, h->d_x.p, x, bytes));
     SQB_CUDA(cudaStreamSynchronize(c->stream));
     h->kind = layout == 0 ? 1 : 2;
     h->x_dtype = x_dtype;
     h->n_feat = n_features;
     h->ran = false;
+    h->aux_valid = false;
     return SQB_OK;
 }
 
@@ -477,38 +1205,56 @@ int sqb_autocorr_load_csr(sqb_autocorr* h, const int64_t* x_indptr, const int32_
     SQB_CHECK(h && x_indptr, SQB_ERR_INVALID, "sqb_autocorr_load_csr: null argument");
     SQB_CHECK(x_dtype == 0 || x_dtype == 1, SQB_ERR_INVALID, "sqb_autocorr_load_csr: x_dtype must be 0 or 1");
     SQB_CHECK(layout == 0 || layout == 1, SQB_ERR_INVALID, "sqb_autocorr_load_csr: layout must be 0 or 1");
-    SQB_CHECK(n_features >= 1, SQB_ERR_INVALID, "sqb_autocorr_load_csr: n_features must be positive");
+    SQB_CHECK(n_features >= 1 && n_features < 2147483647LL, SQB_ERR_INVALID, "sqb_autocorr_load_csr: n_features out of range");
     sqb_ctx* c = h->ctx;
     SQB_CUDA(cudaSetDevice(c->device));
     const int64_t rows = layout == 0 ? n_features : h->n;
-    const int64_t cols = layout == 0 ? h->n : n_features;
     const int64_t nnz = x_indptr[rows];
     SQB_CHECK(x_indptr[0] == 0 && nnz >= 0, SQB_ERR_INVALID, "sqb_autocorr_load_csr: bad indptr");
     SQB_CHECK(nnz == 0 || (x_indices && x_data), SQB_ERR_INVALID, "sqb_autocorr_load_csr: null X arrays");
-    for (int64_t e = 0; e < nnz; ++e)
-        SQB_CHECK(x_indices[e] >= 0 && x_indices[e] < cols, SQB_ERR_INVALID, "sqb_autocorr_load_csr: index %d out of range at %lld",
-                  x_indices[e], (long long)e);
-    if (layout == 0) {
-        SQB_TRY(h->d_xp.alloc(n_features + 1));
-        SQB_TRY(h->d_xi.alloc(nnz > 0 ? nnz : 1));
-        SQB_TRY(h->d_x.alloc((size_t)(nnz > 0 ? nnz : 1) * xsize(x_dtype)));
-        SQB_CUDA(cudaMemcpyAsync(h->d_xp.p, x_indptr, (n_features + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-        if (nnz > 0) {
-            SQB_TRY(sqb_h2d(c, h->d_xi.p, x_indices, nnz * sizeof(int32_t)));
-            SQB_TRY(sqb_h2d(c, h->d_x.p, x_data, (size_t)nnz * xsize(x_dtype)));
-        }
-        SQB_CUDA(cudaStreamSynchronize(c->stream));
-        h->x_nnz = nnz;
-    } else {
-        if (x_dtype == 0)
-            SQB_TRY(ac_transpose_csr<float>(h, x_indptr, x_indices, x_data, n_features));
-        else
-            SQB_TRY(ac_transpose_csr<double>(h, x_indptr, x_indices, x_data, n_features));
-    }
+    h->kind = 0;
+    h->aux_valid = false;
+    h->ran = false;
+    // index range, indptr monotonicity and duplicate observations are checked on the device while the matrix is
+    // re-laid out (no host pass over the non-zeros)
+    if (x_dtype == 0)
+        SQB_TRY(ac_load_csr_typed<float>(h, x_indptr, x_indices, x_data, layout, n_features, nnz));
+    else
+        SQB_TRY(ac_load_csr_typed<double>(h, x_indptr, x_indices, x_data, layout, n_features, nnz));
     h->kind = 3;
     h->x_dtype = x_dtype;
     h->n_feat = n_features;
-    h->ran = false;
+    return SQB_OK;
+}
+
+// upload + validate one or more row permutations (int64 host layout); d_perm (int64) and d_perm32 hold them afterwards
+static int ac_upload_perms(sqb_autocorr* h, const int64_t* row_perm, int64_t count) {
+    sqb_ctx* c = h->ctx;
+    const int64_t n = h->n;
+    const int64_t words = ceil_div64(n, 32);
+    SQB_TRY(h->d_perm.alloc((size_t)(n * count)));
+    SQB_TRY(h->d_perm32.alloc((size_t)(n * count)));
+    SQB_TRY(h->d_seen.alloc((size_t)(words * count)));
+    SQB_TRY(sqb_h2d(c, h->d_perm.p, row_perm, (size_t)(n * count) * sizeof(int64_t)));
+    SQB_CUDA(cudaMemsetAsync(h->d_seen.p, 0, (size_t)(words * count) * sizeof(unsigned int), c->stream));
+    for (int64_t k = 0; k < count; ++k) {
+        SqbLaunchScope scope(c, SQB_K_AUTOCORR_PREP);
+        ac_perm_prepare_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(h->d_perm.p + k * n, n, h->d_perm32.p + k * n, h->d_seen.p + k * words,
+                                                                       h->d_flags.p);
+        SQB_POST_LAUNCH();
+    }
+    return SQB_OK;
+}
+
+static int ac_run_one(sqb_autocorr* h, int mode, int64_t perm_index /* -1: none */, double* d_out) {
+    if (h->kind == 3) {
+        if (perm_index >= 0 && !h->aux_valid) SQB_TRY(ac_run_sparse(h, mode, nullptr, h->d_out.p));
+        return ac_run_sparse(h, mode, perm_index >= 0 ? h->d_perm32.p + perm_index * h->n : nullptr, d_out);
+    }
+    const int64_t* dp = perm_index >= 0 ? h->d_perm.p + perm_index * h->n : nullptr;
+    SQB_TRY(h->x_dtype == 0 ? ac_run_dense<float>(h, mode, dp) : ac_run_dense<double>(h, mode, dp));
+    if (d_out != h->d_out.p)
+        SQB_CUDA(cudaMemcpyAsync(d_out, h->d_out.p, h->n_feat * sizeof(double), cudaMemcpyDeviceToDevice, h->ctx->stream));
     return SQB_OK;
 }
 
@@ -518,20 +1264,11 @@ int sqb_autocorr_run_async(sqb_autocorr* h, int mode, const int64_t* row_perm) {
     SQB_CHECK(mode == 0 || mode == 1, SQB_ERR_INVALID, "sqb_autocorr_run_async: mode must be 0 (moran) or 1 (geary)");
     sqb_ctx* c = h->ctx;
     SQB_CUDA(cudaSetDevice(c->device));
-    const int64_t* d_perm = nullptr;
     if (row_perm) {
-        std::vector<uint8_t> seen((size_t)h->n, 0);
-        for (int64_t r = 0; r < h->n; ++r) {
-            SQB_CHECK(row_perm[r] >= 0 && row_perm[r] < h->n && !seen[row_perm[r]], SQB_ERR_INVALID,
-                      "sqb_autocorr_run_async: row_perm is not a permutation (entry %lld)", (long long)r);
-            seen[row_perm[r]] = 1;
-        }
-        SQB_TRY(h->d_perm.alloc(h->n));
-        SQB_CUDA(cudaMemcpyAsync(h->d_perm.p, row_perm, h->n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-        SQB_CUDA(cudaStreamSynchronize(c->stream));
-        d_perm = h->d_perm.p;
+        SQB_TRY(ac_upload_perms(h, row_perm, 1));
+        SQB_TRY(ac_check_flags(h, "sqb_autocorr_run_async"));
     }
-    int rc = h->x_dtype == 0 ? ac_run_typed<float>(h, mode, d_perm) : ac_run_typed<double>(h, mode, d_perm);
+    int rc = ac_run_one(h, mode, row_perm ? 0 : -1, h->d_out.p);
     if (rc == SQB_OK) h->ran = true;
     return rc;
 }
@@ -543,6 +1280,27 @@ int sqb_autocorr_download(sqb_autocorr* h, double* out) {
     SQB_CUDA(cudaSetDevice(c->device));
     SQB_CUDA(cudaMemcpyAsync(out, h->d_out.p, h->n_feat * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     SQB_CUDA(cudaStreamSynchronize(c->stream));
+    return SQB_OK;
+}
+
+int sqb_autocorr_run_perms(sqb_autocorr* h, int mode, const int64_t* row_perms, int64_t n_perms, double* out) {
+    SQB_CHECK(h && row_perms && out, SQB_ERR_INVALID, "sqb_autocorr_run_perms: null argument");
+    SQB_CHECK(h->kind != 0, SQB_ERR_STATE, "sqb_autocorr_run_perms: load X first");
+    SQB_CHECK(mode == 0 || mode == 1, SQB_ERR_INVALID, "sqb_autocorr_run_perms: mode must be 0 (moran) or 1 (geary)");
+    SQB_CHECK(n_perms >= 1, SQB_ERR_INVALID, "sqb_autocorr_run_perms: n_perms must be positive");
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    const int64_t G = h->n_feat;
+    // permutations are staged in batches of <= 64 (8 bytes + 4 bytes + 1 bit per entry on the device)
+    const int64_t batch = n_perms < 64 ? n_perms : 64;
+    SQB_TRY(h->d_out_perms.alloc((size_t)(batch * G)));
+    for (int64_t p0 = 0; p0 < n_perms; p0 += batch) {
+        const int64_t pb = n_perms - p0 < batch ? n_perms - p0 : batch;
+        SQB_TRY(ac_upload_perms(h, row_perms + p0 * h->n, pb));
+        for (int64_t k = 0; k < pb; ++k) SQB_TRY(ac_run_one(h, mode, k, h->d_out_perms.p + k * G));
+        SQB_CUDA(cudaMemcpyAsync(out + p0 * G, h->d_out_perms.p, (size_t)(pb * G) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        SQB_TRY(ac_check_flags(h, "sqb_autocorr_run_perms"));  // synchronises
+    }
     return SQB_OK;
 }
 

@@ -41,6 +41,8 @@ def main():
     a7 = {**base, "shuffle_algo": 7, "shuffle_threads": 1024, "shuffle_r": 2, "shuffle_low": 98304}
     for low in (0, 65536):
         variants.append({**a7, "shuffle_low": low})
+    variants.append({**a7, "shuffle_low": 65536, "shuffle_q": 8})
+    variants.append({**a7, "shuffle_low": 65536, "shuffle_q": 2})
     variants.append({**a7, "shuffle_r": 4, "shuffle_low": 0})
     variants.append({**base, "shuffle_algo": 6, "shuffle_threads": 1024, "shuffle_r": 2, "shuffle_wfactor_x100": 1600})
     variants.append({**base, "shuffle_algo": 5, "shuffle_threads": 512, "shuffle_r": 2})
