@@ -144,7 +144,9 @@ int sqb_interaction_matrix(sqb_ctx* ctx, int64_t n, int64_t nnz, const uint32_t*
  * X layout 0: features x obs (row-major dense, or CSR by feature); layout 1: obs x features (row-major
  * dense, or CSR by observation == CSC of the features x obs matrix, AnnData's native X).
  * x_dtype 0 = f32, 1 = f64.  row_perm (or NULL): length-n permutation p; row r of the permuted W is row p[r]
- * (g[idx_shuffle, :], _ppatterns.py:271-272).  out: n_features float64 (NaN for constant features).       */
+ * (g[idx_shuffle, :], _ppatterns.py:271-272).  out: n_features float64 (NaN for constant features).
+ * Sparse X must not store an observation twice for one feature (scipy: sum_duplicates()); indices need not be
+ * sorted.  Index ranges, indptr monotonicity and duplicates are checked on the device (SQB_ERR_INVALID).   */
 int sqb_autocorr_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const int32_t* w_indptr, const int32_t* w_indices,
                         const void* w_data, int w_dtype, sqb_autocorr** out);
 int sqb_autocorr_destroy(sqb_autocorr* h);
@@ -153,6 +155,10 @@ int sqb_autocorr_load_csr(sqb_autocorr* h, const int64_t* x_indptr, const int32_
                           int x_dtype, int layout, int64_t n_features);
 int sqb_autocorr_run_async(sqb_autocorr* h, int mode, const int64_t* row_perm);
 int sqb_autocorr_download(sqb_autocorr* h, double* out);
+/* The permutation variant in one call (_score_helper, _ppatterns.py:258-280): row_perms = n_perms x n int64 (row p is
+ * idx_shuffle of permutation p), out = n_perms x n_features float64.  X stays resident; the permutations are validated
+ * on the device (one error flag per batch) and every permutation is one kernel launch.                      */
+int sqb_autocorr_run_perms(sqb_autocorr* h, int mode, const int64_t* row_perms, int64_t n_perms, double* out);
 /* load + run + download */
 int sqb_autocorr_dense(sqb_autocorr* h, int mode, const void* x, int x_dtype, int layout, int64_t n_features,
                        const int64_t* row_perm, double* out);

@@ -68,6 +68,7 @@ _SIGNATURES: dict[str, tuple] = {
     "sqb_autocorr_load_csr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64]),
     "sqb_autocorr_run_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "sqb_autocorr_download": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sqb_autocorr_run_perms": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "sqb_autocorr_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "sqb_autocorr_csr": (
         C.c_int,

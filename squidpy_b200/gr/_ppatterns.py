@@ -111,6 +111,17 @@ class AutocorrPlan:
         self.run_async(mode, row_perm)
         return self.download()
 
+    def score_perms(self, mode: SpatialAutocorr | str, row_perms: np.ndarray) -> np.ndarray:
+        """``_score_helper`` (``_ppatterns.py:258-280``) for a stack of permutations: ``row_perms`` is (P, n) with row p the
+        ``idx_shuffle`` of permutation p; returns float64 (P, n_features).  X stays on the device."""
+        mode = SpatialAutocorr(mode)
+        rp = np.ascontiguousarray(np.atleast_2d(row_perms), dtype=np.int64)
+        if rp.shape[1] != self.n:
+            raise ValueError(f"Expected permutations of length `{self.n}`, found `{rp.shape[1]}`.")
+        out = np.empty((rp.shape[0], self.n_features), dtype=np.float64)
+        check(self._lib.sqb_autocorr_run_perms(self._h, 0 if mode == SpatialAutocorr.MORAN else 1, rp.ctypes.data, rp.shape[0], out.ctypes.data))
+        return out
+
     def close(self) -> None:
         if self._h is not None:
             self._lib.sqb_autocorr_destroy(self._h)
@@ -229,10 +240,12 @@ def spatial_autocorr(
             assert_positive(n_perms, name="n_perms")
             generators = spawn_generators(seed, int(n_perms))
             sp_local = np.empty((int(n_perms), hi - lo), dtype=np.float64)
-            for p in range(int(n_perms)):
-                idx_shuffle = generators[p].permutation(g.shape[0])  # _score_helper, :258-280
+            batch = max(1, min(64, (256 << 20) // (8 * g.shape[0])))  # <= 256 MB of int64 permutations per device call
+            for p0 in range(0, int(n_perms), batch):
+                p1 = min(p0 + batch, int(n_perms))
+                idx = np.stack([generators[p].permutation(g.shape[0]) for p in range(p0, p1)])  # _score_helper, :258-280
                 if hi > lo:
-                    sp_local[p] = plan.score(mode, row_perm=idx_shuffle)
+                    sp_local[p0:p1] = plan.score_perms(mode, idx)
             score_perms = np.ascontiguousarray(all_gather_rows(np.ascontiguousarray(sp_local.T), n_feat).T)
     finally:
         plan.close()

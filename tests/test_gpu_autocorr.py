@@ -55,10 +55,21 @@ def test_sparse_layouts(mode, fmt):
     got = plan.score(mode)
     np.testing.assert_allclose(got, exp, rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(got, exp, **TIGHT)
-    plan.load(x.toarray(), obs_major=True)
-    np.testing.assert_array_equal(plan.score(mode), got)
     plan.load(x.T.tocsr(), obs_major=False)
-    np.testing.assert_array_equal(plan.score(mode), got)
+    np.testing.assert_array_equal(plan.score(mode), got)  # both sparse layouts end in the same ordered device layout
+    xs = x.tocsr()
+    perm = np.random.default_rng(0).permutation(xs.nnz)  # the same entries, shuffled inside every row (non-canonical order)
+    rows = np.repeat(np.arange(n), np.diff(xs.indptr))[perm]
+    o = np.argsort(rows, kind="stable")
+    shuffled = sp.csr_matrix((xs.data[perm][o], xs.indices[perm][o], xs.indptr), shape=xs.shape)
+    from squidpy_b200._lib import check, load
+
+    out = np.empty(133)
+    xp, xi = shuffled.indptr.astype(np.int64), shuffled.indices.astype(np.int32)
+    check(load().sqb_autocorr_csr(plan._h, 0 if mode == "moran" else 1, xp.ctypes.data, xi.ctypes.data, shuffled.data.ctypes.data, 0, 1, 133, None, out.ctypes.data))
+    np.testing.assert_array_equal(out, got)  # entry order of the input does not matter
+    plan.load(x.toarray(), obs_major=True)
+    np.testing.assert_allclose(plan.score(mode), got, **TIGHT)  # dense tiles: another formulation, same value to ~1e-14
 
 
 def test_constant_feature_nan_and_row_perm():
@@ -77,6 +88,98 @@ def test_constant_feature_nan_and_row_perm():
         np.testing.assert_allclose(plan.score(mode, row_perm=idx), f(w[idx, :], x2.T), **TIGHT)  # g[idx_shuffle, :], _ppatterns.py:271-272
     with pytest.raises(ValueError, match="not a permutation"):
         plan.score("moran", row_perm=np.zeros(n, np.int64))
+
+
+@pytest.mark.parametrize("mode", ["moran", "geary"])
+@pytest.mark.parametrize("kind", ["deg12_f32", "deg40_f32", "deg6_f64", "deg12_f64"])
+def test_sparse_weight_formats(mode, kind):
+    """Packed 8-lane rows (<= 7 entries, float32), packed 16-lane rows (<= 15), CSR rows (anything else / float64 weights)."""
+    rng = np.random.default_rng(7)
+    n, deg = 3000, int(kind.split("_")[0][3:])
+    cols = np.stack([rng.choice(n, deg, replace=False) for _ in range(n)])
+    dt = np.float32 if kind.endswith("f32") else np.float64
+    w = sp.csr_matrix((rng.random(n * deg).astype(dt), cols.ravel(), np.arange(0, n * deg + 1, deg)), shape=(n, n))
+    w.sort_indices()
+    x = sp.random(n, 40, density=0.15, format="csr", random_state=1, dtype=np.float64)
+    x.data = np.round(x.data * 8) / 4 - 0.5  # negative values and explicit zeros among the stored entries
+    exp = (ref.morans_i if mode == "moran" else ref.gearys_c)(w, x.T.tocsr())
+    plan = AutocorrPlan(w)
+    plan.load(x, obs_major=True)
+    np.testing.assert_allclose(plan.score(mode), exp, **TIGHT)
+    idx = rng.permutation(n)
+    exp_p = (ref.morans_i if mode == "moran" else ref.gearys_c)(w[idx, :], x.T.tocsr())
+    np.testing.assert_allclose(plan.score(mode, row_perm=idx), exp_p, **TIGHT)
+    plan.load(x.astype(np.float32), obs_major=True)
+    np.testing.assert_allclose(plan.score(mode), (ref.morans_i if mode == "moran" else ref.gearys_c)(w, x.astype(np.float32).T.tocsr()), **TIGHT)
+
+
+def test_sparse_run_to_run_bitwise_and_perm_batch():
+    """float64 CSR by observation: the device transposition is ordered, so repeated loads give bit-identical scores;
+    score_perms == one score(row_perm=...) per permutation == the oracle on g[idx, :]."""
+    w = _w(60, 70)
+    n = w.shape[0]
+    x = sp.random(n, 90, density=0.2, format="csr", random_state=11, dtype=np.float64)
+    plan = AutocorrPlan(w)
+    runs = []
+    for _ in range(3):
+        plan.load(x, obs_major=True)
+        runs.append((plan.score("moran"), plan.score("geary")))
+    for a, b in runs[1:]:
+        np.testing.assert_array_equal(a, runs[0][0])
+        np.testing.assert_array_equal(b, runs[0][1])
+    rng = np.random.default_rng(2)
+    idx = np.stack([rng.permutation(n) for _ in range(5)])
+    for mode, f in (("moran", ref.morans_i), ("geary", ref.gearys_c)):
+        got = plan.score_perms(mode, idx)
+        for p in range(5):
+            np.testing.assert_array_equal(got[p], plan.score(mode, row_perm=idx[p]))
+            np.testing.assert_allclose(got[p], f(w[idx[p], :], x.T.tocsr()), **TIGHT)
+    bad = idx.copy()
+    bad[3, 10] = bad[3, 11]
+    with pytest.raises(ValueError, match="not a permutation"):
+        plan.score_perms("moran", bad)
+    plan.load(x.toarray(), obs_major=True)  # dense path through the same entry point
+    np.testing.assert_allclose(plan.score_perms("moran", idx[:2])[1], ref.morans_i(w[idx[1], :], x.T.tocsr()), **TIGHT)
+
+
+def test_sparse_invalid_input_is_rejected():
+    from squidpy_b200._lib import check, load
+
+    w = _w(20, 20)
+    n = w.shape[0]
+    plan = AutocorrPlan(w)
+    lib = load()
+    out = np.empty(3)
+
+    def run(xp, xi, xv, layout, nf=3):
+        xp, xi, xv = np.asarray(xp, np.int64), np.asarray(xi, np.int32), np.asarray(xv, np.float32)
+        check(lib.sqb_autocorr_csr(plan._h, 0, xp.ctypes.data, xi.ctypes.data, xv.ctypes.data, 0, layout, nf, None, out.ctypes.data))
+
+    run([0, 2, 2, 3], [5, 7, 1], [1, 2, 3], 0)  # fine (feature 1 is empty -> NaN)
+    assert np.isnan(out[1]) and np.isfinite(out[[0, 2]]).all()
+    with pytest.raises(ValueError, match="stored twice"):
+        run([0, 2, 2, 3], [5, 5, 1], [1, 2, 3], 0)
+    with pytest.raises(ValueError, match="out of range"):
+        run([0, 2, 2, 3], [5, n, 1], [1, 2, 3], 0)
+    with pytest.raises(ValueError, match="indptr"):
+        run([0, 2, 1, 3], [5, 6, 1], [1, 2, 3], 0)
+    xp = np.zeros(n + 1, np.int64)
+    xp[4:] = 2
+    with pytest.raises(ValueError, match="out of range"):
+        run(xp, [0, 3], [1, 2], 1)  # observation 3 stores feature 3 of 3
+    run(xp, [0, 2], [1, 2], 1)
+    plan.close()
+
+
+def test_sparse_million_observations_global_bitmap():
+    """1M observations: the bitmap (8 B per 32 observations = 250 KB) no longer fits shared memory -> global scratch."""
+    g = _w(1000, 1000)
+    n = g.shape[0]
+    x = sp.random(n, 6, density=0.05, format="csr", random_state=5, dtype=np.float32)
+    plan = AutocorrPlan(g)
+    plan.load(x, obs_major=True)
+    np.testing.assert_allclose(plan.score("moran"), ref.morans_i(g, x.T.tocsr()), **TIGHT)
+    np.testing.assert_allclose(plan.score("geary"), ref.gearys_c(g, x.T.tocsr()), **TIGHT)
 
 
 def test_midsize_sparse_20k():
