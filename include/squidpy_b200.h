@@ -96,6 +96,14 @@ int sqb_nhood_permute(sqb_nhood* h, const uint64_t* states, int64_t n_perms, uin
 int sqb_nhood_permute_upload(sqb_nhood* h, const uint64_t* states, int64_t n_perms);
 int sqb_nhood_permute_run_async(sqb_nhood* h);
 int sqb_nhood_permute_download(sqb_nhood* h, uint32_t* out_counts);
+/* Fast RNG mode (NOT the reference's permutations): permutation p (global index first_perm + p) of every library
+ * segment is a keyed bijection — 4-round Feistel network with cycle walking, round keys = splitmix64(seed, global
+ * permutation index, segment, round) — applied to the segment's labels sorted by class; labels are written straight into
+ * the permutation-minor matrix the count kernel reads (no stream replay, no Fisher-Yates, no transposition).  Same
+ * null distribution as numpy's shuffle, different draws: z-scores agree with the exact mode to O(n_perms^-1/2)
+ * (SURVEY.md 8d "Fast-RNG validation"); tests/philox_ref.py is the executable specification.  After this upload,
+ * run_async / download / stats / sums / var_chain / shuffled_labels work as in the exact mode.                     */
+int sqb_nhood_permute_upload_philox(sqb_nhood* h, uint64_t seed, int64_t first_perm, int64_t n_perms);
 /* Mean and standard deviation over the permutations of every count bin (n_cls x n_cls float64 each), computed on the
  * device in the operation order of numpy's perms.mean(axis=0) / perms.std(axis=0) on the float64 counts
  * (_nhood.py:231), i.e. bit-identical to the reference's host computation; saves the download of all counts.          */

@@ -28,6 +28,25 @@ def shard_range(n: int, rank: int, world_size: int) -> tuple[int, int]:
     return lo, min(lo + step, n)
 
 
+def shared_seed(seed):
+    """``seed`` itself, or — for ``seed=None`` under ``torch.distributed`` — one 128-bit OS-entropy draw made on rank 0 and
+    broadcast, so that every rank spawns the same generator family (with per-rank entropy the ranks' shards would come
+    from different families: irreproducible for nhood / autocorr, plainly wrong for the Ripley simulations, whose pair
+    tiles are summed across ranks)."""
+    rank, ws = world()
+    if seed is not None or ws == 1:
+        return seed
+    import torch
+    import torch.distributed as dist
+
+    ent = np.random.SeedSequence().entropy if rank == 0 else 0
+    words = np.array([(ent >> (32 * k)) & 0xFFFFFFFF for k in range(4)], dtype=np.int64)
+    t = torch.from_numpy(words).to(_device_for_backend())
+    dist.broadcast(t, src=0)
+    words = t.cpu().numpy()
+    return int(sum(int(w) << (32 * k) for k, w in enumerate(words)))
+
+
 def _device_for_backend():
     import torch
     import torch.distributed as dist

@@ -52,6 +52,7 @@ _SIGNATURES: dict[str, tuple] = {
     "sqb_nhood_set_base": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "sqb_nhood_permute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "sqb_nhood_permute_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "sqb_nhood_permute_upload_philox": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64]),
     "sqb_nhood_permute_run_async": (C.c_int, [C.c_void_p]),
     "sqb_nhood_permute_download": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sqb_nhood_permute_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

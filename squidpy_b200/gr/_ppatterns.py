@@ -23,7 +23,7 @@ from scipy import stats
 from scipy.sparse import issparse, spmatrix
 
 from .._constants import Key, SpatialAutocorr
-from .._dist import all_gather_rows, all_reduce_sum, shard_range, world
+from .._dist import all_gather_rows, all_reduce_sum, shard_range, shared_seed, world
 from .._lib import Context, check, default_context, load
 from .._rng import spawn_generators
 from .._validators import (
@@ -238,7 +238,7 @@ def spatial_autocorr(
         score_perms = None
         if n_perms is not None:
             assert_positive(n_perms, name="n_perms")
-            generators = spawn_generators(seed, int(n_perms))
+            generators = spawn_generators(shared_seed(seed), int(n_perms))
             sp_local = np.empty((int(n_perms), hi - lo), dtype=np.float64)
             batch = max(1, min(64, (256 << 20) // (8 * g.shape[0])))  # <= 256 MB of int64 permutations per device call
             for p0 in range(0, int(n_perms), batch):

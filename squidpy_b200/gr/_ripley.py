@@ -16,7 +16,7 @@ import numpy as np
 import pandas as pd
 
 from .._constants import Key, RipleyStat
-from .._dist import all_reduce_sum, world
+from .._dist import all_reduce_sum, world, shared_seed
 from .._lib import Context, check, default_context, load
 from .._rng import spawn_generators
 from .._validators import assert_categorical_obs, assert_spatial_basis, extract_adata_if_sdata
@@ -87,7 +87,7 @@ def ripley(
 
     start = time.perf_counter()
     logg.info("Calculating Ripley's %s statistic for `%d` clusters and `%d` simulations", mode, n_cls, n_simulations)
-    obs_rng, *sim_rngs = spawn_generators(seed, n_simulations + 1)
+    obs_rng, *sim_rngs = spawn_generators(shared_seed(seed), n_simulations + 1)  # one family for all ranks (pair tiles are summed)
     bins = support
 
     if mode == RipleyStat.L:

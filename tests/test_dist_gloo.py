@@ -53,6 +53,14 @@ WORKER = textwrap.dedent(
     # int64 partial pair counts (co_occurrence / ripley tile sharding)
     part = np.full((3, 3, 5), rank + 1, dtype=np.int64)
     assert (all_reduce_sum(part) == 3).all()
+    # seed=None: every rank must end up with the SAME entropy (rank 0 draws, broadcast), an explicit seed passes through
+    from squidpy_b200._dist import shared_seed
+    s = shared_seed(None)
+    both = all_gather_rows(np.array([[s >> 64, s & ((1 << 64) - 1)]], dtype=np.uint64), 2)
+    assert s > (1 << 64) and (both[0] == both[1]).all(), "ranks drew different entropy for seed=None"
+    assert shared_seed(7) == 7
+    a = np.random.default_rng(np.random.SeedSequence(s).spawn(3)[2]).random(4)
+    assert (all_gather_rows(a[None, :].copy(), 2)[0] == all_gather_rows(a[None, :].copy(), 2)[1]).all()
     dist.destroy_process_group()
     print("RANK_OK", rank)
     """
