@@ -115,6 +115,12 @@ int sqb_nhood_permute_stats(sqb_nhood* h, double* mean_out, double* std_out);
 int sqb_nhood_permute_sums(sqb_nhood* h, int64_t* sums_out);
 int sqb_nhood_permute_var_chain(sqb_nhood* h, const double* mean, const double* acc_in, double* acc_out);
 
+/* The same statistics with DEVICE pointers (n_cls*n_cls elements each), asynchronous on the ctx stream: for callers that
+ * hand the buffers straight to a collective (torch tensors + NCCL) — no host round trip between count kernel and all-reduce. */
+int sqb_nhood_permute_stats_dev(sqb_nhood* h, double* d_mean, double* d_std);
+int sqb_nhood_permute_sums_dev(sqb_nhood* h, int64_t* d_sums);
+int sqb_nhood_permute_var_chain_dev(sqb_nhood* h, const double* d_mean, const double* d_acc_in, double* d_acc_out);
+
 /* Test hook: shuffled label vectors of permutations [p0, p1) of the last upload, recomputed on the device
  * (original node order), out: (p1-p0) x n uint32.                                                        */
 int sqb_nhood_shuffled_labels(sqb_nhood* h, int64_t p0, int64_t p1, uint32_t* out);
@@ -161,6 +167,12 @@ int sqb_autocorr_destroy(sqb_autocorr* h);
 int sqb_autocorr_load_dense(sqb_autocorr* h, const void* x, int x_dtype, int layout, int64_t n_features);
 int sqb_autocorr_load_csr(sqb_autocorr* h, const int64_t* x_indptr, const int32_t* x_indices, const void* x_data,
                           int x_dtype, int layout, int64_t n_features);
+/* Feature shard of a CSR-by-observation matrix (multi-GPU: every rank takes a contiguous range of features): uploads only
+ * the columns col_lo <= c < col_hi of every row (rows must hold ascending column indices — scipy's sorted indices; the
+ * slices are found with two binary searches per row and packed into pinned staging buffers by host threads) and loads them
+ * as features 0 .. col_hi - col_lo.                                                                          */
+int sqb_autocorr_load_csr_cols(sqb_autocorr* h, const int64_t* x_indptr, const int32_t* x_indices, const void* x_data,
+                               int x_dtype, int64_t n_features_total, int64_t col_lo, int64_t col_hi);
 int sqb_autocorr_run_async(sqb_autocorr* h, int mode, const int64_t* row_perm);
 int sqb_autocorr_download(sqb_autocorr* h, double* out);
 /* The permutation variant in one call (_score_helper, _ppatterns.py:258-280): row_perms = n_perms x n int64 (row p is

@@ -7,7 +7,7 @@ in ``libsquidpy_b200.so`` through a ctypes C ABI (``include/squidpy_b200.h``).  
 
 from . import gr
 from ._adata import AnnDataLite
-from ._lib import Context, SquidpyB200Error, default_context, device_count
+from ._lib import Context, SquidpyB200Error, default_context, device_count, set_default_context
 
 __version__ = "0.1.0"
-__all__ = ["gr", "AnnDataLite", "Context", "SquidpyB200Error", "default_context", "device_count", "__version__"]
+__all__ = ["gr", "AnnDataLite", "Context", "SquidpyB200Error", "default_context", "set_default_context", "device_count", "__version__"]

@@ -123,3 +123,54 @@ def sequential_stats(sums_local: np.ndarray, var_step, n_total: int) -> tuple[np
         dist.broadcast(t, src=ws - 1)
         acc = t.cpu().numpy()
     return mean, np.sqrt(acc / n_total)
+
+
+def nccl_cuda() -> bool:
+    """True when the default process group runs NCCL (one process per GPU): collectives take device tensors."""
+    try:
+        import torch.distributed as dist
+
+        return dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
+    except Exception:  # pragma: no cover
+        return False
+
+
+def sequential_stats_device(plan, n_total: int, has_rows: bool) -> tuple[np.ndarray, np.ndarray]:
+    """:func:`sequential_stats` with everything on the device (NCCL): the exact int64 per-bin sums of ``plan``'s permutation
+    counts are all-reduced as a device tensor, the mean is formed on the device, the variance accumulation travels rank to
+    rank as a device tensor (``sqb_nhood_permute_var_chain_dev``), and one (2, C, C) float64 tensor comes back to the host.
+    Bit-identical to numpy's ``mean`` / ``std`` over the concatenated float64 counts (same operations in the same order;
+    IEEE division and square root are exact in torch as in numpy)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, ws = world()
+    dev = torch.device("cuda", plan.ctx.device)
+    cc = plan.n_cls * plan.n_cls
+    stream = torch.cuda.current_stream(dev)
+    shared = plan.ctx.stream == stream.cuda_stream  # the library launches on torch's current stream: everything is ordered
+    sums = torch.zeros(cc, dtype=torch.int64, device=dev)
+    if has_rows:
+        if not shared:
+            stream.synchronize()
+        plan.sums_dev(sums.data_ptr())
+        if not shared:
+            plan.ctx.sync()
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    mean = sums.to(torch.float64) / float(n_total)
+    acc = torch.zeros(cc, dtype=torch.float64, device=dev)
+    if rank > 0:
+        dist.recv(acc, src=rank - 1)
+    if has_rows:
+        out = torch.empty_like(acc)
+        if not shared:
+            stream.synchronize()
+        plan.var_chain_dev(mean.data_ptr(), acc.data_ptr(), out.data_ptr())
+        if not shared:
+            plan.ctx.sync()
+        acc = out
+    if rank < ws - 1:
+        dist.send(acc, dst=rank + 1)
+    dist.broadcast(acc, src=ws - 1)
+    res = torch.stack([mean, torch.sqrt(acc / float(n_total))]).cpu().numpy()
+    return res[0].reshape(plan.n_cls, plan.n_cls), res[1].reshape(plan.n_cls, plan.n_cls)

@@ -60,6 +60,9 @@ _SIGNATURES: dict[str, tuple] = {
                                           C.c_int, C.c_void_p, C.c_void_p]),
     "sqb_nhood_permute_sums": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sqb_nhood_permute_var_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sqb_nhood_permute_stats_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sqb_nhood_permute_sums_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sqb_nhood_permute_var_chain_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sqb_nhood_shuffled_labels": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "sqb_nhood_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "sqb_nhood_bytes_per_perm": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
@@ -67,6 +70,7 @@ _SIGNATURES: dict[str, tuple] = {
     "sqb_autocorr_destroy": (C.c_int, [C.c_void_p]),
     "sqb_autocorr_load_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64]),
     "sqb_autocorr_load_csr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64]),
+    "sqb_autocorr_load_csr_cols": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64]),
     "sqb_autocorr_run_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "sqb_autocorr_download": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sqb_autocorr_run_perms": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -159,6 +163,7 @@ class Context:
         check(self._lib.sqb_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
         self._h = h
         self.device = int(device)
+        self.lock = threading.RLock()  # held by the sq.gr.* calls while they use this context's stream / scratch buffers
 
     @property
     def handle(self) -> C.c_void_p:
@@ -212,17 +217,31 @@ class Context:
 
 
 _default_ctx: dict[int, Context] = {}
+_default_ctx_lock = threading.Lock()
 
 
 def default_context(device: int | None = None) -> Context:
-    """Per-device shared context.  ``device=None`` resolves to ``$LOCAL_RANK`` (one process per GPU) or 0."""
+    """Per-device shared context.  ``device=None`` resolves to ``$LOCAL_RANK`` (one process per GPU) or 0.
+    The context (stream, scratch buffers, staging ring) is shared by every ``sq.gr.*`` call on that device: the calls hold
+    ``ctx.lock`` while they use it, so concurrent calls from several Python threads serialise instead of interleaving."""
     if device is None:
         device = int(os.environ.get("SQB_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         n = device_count()
         device = device % max(n, 1)
-    if device not in _default_ctx:
-        _default_ctx[device] = Context(device)
-    return _default_ctx[device]
+    with _default_ctx_lock:
+        if device not in _default_ctx:
+            _default_ctx[device] = Context(device)
+        return _default_ctx[device]
+
+
+def set_default_context(ctx: Context | None, device: int | None = None) -> None:
+    """Make ``ctx`` the context ``sq.gr.*`` uses on its device (e.g. one created on torch's current stream, so that CUDA
+    events and NCCL collectives issued by the caller are ordered with the library's kernels); ``None`` removes it."""
+    with _default_ctx_lock:
+        if ctx is None:
+            _default_ctx.pop(int(device or 0), None)
+        else:
+            _default_ctx[ctx.device] = ctx
 
 
 def pinned_empty(shape, dtype) -> np.ndarray:

@@ -30,6 +30,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
+#include <thread>
+
 #include "common.cuh"
 
 #define TILE 32
@@ -201,7 +204,7 @@ __global__ void ac_check_indptr_kernel(const int64_t* __restrict__ ptr, int64_t 
 
 // per-column entry counts of a CSR-by-observation matrix; out-of-range column -> error flag.
 // Shared-memory histogram per CTA when n_feat fits (hist_smem), else global atomics.
-__global__ void ac_colcount_kernel(const int32_t* __restrict__ xi, int64_t nnz, int64_t n_feat, int hist_smem,
+__global__ void ac_colcount_kernel(const int32_t* __restrict__ xi, int64_t nnz, int64_t n_feat, int32_t col_lo, int hist_smem,
                                    unsigned int* __restrict__ cnt, int* __restrict__ err) {
     extern __shared__ unsigned int s_hist[];
     if (hist_smem)
@@ -210,7 +213,7 @@ __global__ void ac_colcount_kernel(const int32_t* __restrict__ xi, int64_t nnz, 
     const int64_t per = (nnz + gridDim.x - 1) / gridDim.x;
     const int64_t e0 = blockIdx.x * per, e1 = e0 + per < nnz ? e0 + per : nnz;
     for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-        const int32_t c = xi[e];
+        const int32_t c = xi[e] - col_lo;
         if (c < 0 || c >= n_feat) {
             atomicOr(err, AC_ERR_INDEX);
             continue;
@@ -301,13 +304,13 @@ __global__ void ac_seglen_kernel(const int64_t* __restrict__ ptr, int64_t n_feat
 // CSR by observation -> unsorted segments by feature (atomic cursor; the rank sort below orders them)
 template <typename XT>
 __global__ void ac_coltranspose_kernel(const int64_t* __restrict__ xp, const int32_t* __restrict__ xi,
-                                       const XT* __restrict__ xv, int64_t n_obs, int64_t n_feat,
+                                       const XT* __restrict__ xv, int64_t n_obs, int64_t n_feat, int32_t col_lo,
                                        unsigned long long* __restrict__ cursor, int32_t* __restrict__ oi, XT* __restrict__ ov) {
     const int lane = threadIdx.x & 31;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; r < n_obs; r += nw) {
         for (int64_t e = xp[r] + lane; e < xp[r + 1]; e += 32) {
-            const int32_t c = xi[e];
+            const int32_t c = xi[e] - col_lo;
             if (c < 0 || c >= n_feat) continue;  // flagged by the count kernel
             const unsigned long long pos = atomicAdd(&cursor[c], 1ULL);
             oi[pos] = (int32_t)r;
@@ -416,26 +419,14 @@ __global__ void __launch_bounds__(AC_T) ac_rank_sort_kernel(const int64_t* __res
 }
 
 // ---- W preprocessing ---------------------------------------------------------------------------------------
-// packed rows: LPR slots of 8 bytes; slots 0..LPR-2 = {column (int32, -1 = empty), weight (float32)}, slot LPR-1 = the
-// column sum c_i of W as float64.
+// packed rows: LPR slots of 8 bytes {column (int32, -1 = empty), weight (float32)}
 template <int LPR>
 __global__ void ac_pack_rows_kernel(const int32_t* __restrict__ wp, const int32_t* __restrict__ wi, const double* __restrict__ wd,
-                                    const double* __restrict__ csum, int64_t n, uint2* __restrict__ rows) {
+                                    int64_t n, uint2* __restrict__ rows) {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n * LPR; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = t / LPR;
-        const int slot = (int)(t % LPR);
-        uint2 v;
-        if (slot == LPR - 1) {
-            const long long bits = __double_as_longlong(csum[r]);
-            v = make_uint2((unsigned int)(bits & 0xffffffffLL), (unsigned int)((unsigned long long)bits >> 32));
-        } else {
-            const int32_t e = wp[r] + slot;
-            if (e < wp[r + 1])
-                v = make_uint2((unsigned int)wi[e], __float_as_uint((float)wd[e]));
-            else
-                v = make_uint2(0xffffffffu, 0u);
-        }
-        rows[t] = v;
+        const int32_t e = wp[r] + (int)(t % LPR);
+        rows[t] = e < wp[r + 1] ? make_uint2((unsigned int)wi[e], __float_as_uint((float)wd[e])) : make_uint2(0xffffffffu, 0u);
     }
 }
 
@@ -500,42 +491,14 @@ __device__ __forceinline__ void ac_block_reduce(double (&q)[NQ], double (*s_red)
     }
 }
 
-template <typename XT>
-__device__ __forceinline__ bool ac_lookup(const uint2* __restrict__ S, int j, const XT* __restrict__ xv, double& xj) {
-    const uint2 s = S[j >> 5];
-    const unsigned int bit = 1u << (j & 31);
-    if (s.x & bit) {
-        xj = (double)__ldg(xv + (s.y + __popc(s.x & (bit - 1u))));
-        return true;
-    }
-    xj = 0.0;
-    return false;
-}
-
-// one slot of one row: Moran  acc0 += z_i * w z_j, acc1 += w z_j;   Geary  acc0 += w ((x_i - x_j)^2 - [j stored] x_j^2)
-template <typename XT, int MODE>
-__device__ __forceinline__ void ac_slot(const uint2* __restrict__ S, const XT* __restrict__ xv, int j, double w, double xi_v,
-                                        double zi, double m, double& acc0, double& acc1) {
-    double xj;
-    const bool hit = ac_lookup<XT>(S, j, xv, xj);
-    if (MODE == 0) {
-        const double t = w * (hit ? xj - m : -m);
-        acc0 = fma(zi, t, acc0);
-        acc1 += t;
-    } else {
-        const double d = xi_v - xj;
-        acc0 += w * (d * d - xj * xj);  // xj == 0 when not stored
-    }
-}
-
-// FMT 0: packed rows, 8 lanes per row (<= 7 entries);  FMT 1: packed rows, 16 lanes per row (<= 15 entries);
+// FMT 0: packed rows, 8 lanes per row (<= 8 entries);  FMT 1: packed rows, 16 lanes per row (<= 16 entries);
 // FMT 2: CSR rows, 8 lanes per row (any length; float64 weights).
 template <typename XT, int MODE, int FMT, bool PERM>
 __global__ void __launch_bounds__(AC_T, 4) ac_sparse_kernel(const __grid_constant__ AcSparseParams p) {
     constexpr int LPR = FMT == 1 ? 16 : 8;
     constexpr int RPW = 32 / LPR;        // rows per warp step
     constexpr int NSUB = 32 / RPW;       // warp steps per block of 32 entries
-    constexpr int GRP = 4;               // warp steps whose row slots are loaded together (independent loads in flight)
+    constexpr int GRP = 4;               // warp steps handled together: 4 independent row loads / lookups / value loads in flight
     extern __shared__ __align__(16) unsigned char ac_smem[];
     __shared__ double s_red[6][AC_NW];
     __shared__ double s_mean;
@@ -604,64 +567,133 @@ __global__ void __launch_bounds__(AC_T, 4) ac_sparse_kernel(const __grid_constan
             __syncthreads();
             m = s_mean;
             q[0] = 0.0;
+            // ---- phase 1b (unpermuted pass only): the column-sum terms D = sum c z, E = sum c, sum z^2, Geary's sum c x^2 ----
+            for (int v = threadIdx.x; v < len4; v += AC_T) {
+                const int4 iv = __ldg(reinterpret_cast<const int4*>(xi) + v);
+                const int ii[4] = {iv.x, iv.y, iv.z, iv.w};
+                double xs[4], cs[4];
+                if (sizeof(XT) == 4) {
+                    const float4 f = __ldg(reinterpret_cast<const float4*>(xv) + v);
+                    xs[0] = f.x, xs[1] = f.y, xs[2] = f.z, xs[3] = f.w;
+                } else {
+                    const double2 d0 = __ldg(reinterpret_cast<const double2*>(xv) + 2 * v);
+                    const double2 d1 = __ldg(reinterpret_cast<const double2*>(xv) + 2 * v + 1);
+                    xs[0] = d0.x, xs[1] = d0.y, xs[2] = d1.x, xs[3] = d1.y;
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) cs[t] = ii[t] >= 0 ? __ldg(p.csum + ii[t]) : 0.0;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (ii[t] < 0) continue;
+                    const double zi = xs[t] - m;
+                    q[2] = fma(cs[t], zi, q[2]);
+                    q[3] += cs[t];
+                    q[4] = fma(zi, zi, q[4]);
+                    q[5] = fma(cs[t], xs[t] * xs[t], q[5]);
+                }
+            }
         } else {
             m = p.aux[g];
             __syncthreads();
         }
-        // ---- phase 2: walk the rows of W of the stored observations ----
-        // q[0], q[1]: slot accumulators;  q[2..5] (unpermuted pass only): D, E, sum z^2, Geary column term
+        // ---- phase 2: walk the rows of W of the stored observations; q[0], q[1] = slot accumulators ----
+        // Moran: q[0] += z_i * w z_j, q[1] += w z_j;   Geary: q[0] += w ((x_i - x_j)^2 - [j stored] x_j^2)
+        int nxt_i = -1;
+        XT nxt_x = (XT)0;
+        {
+            const int e = warp * 32 + lane;
+            if (e < len) {
+                nxt_i = __ldg(xi + e);
+                nxt_x = __ldg(xv + e);
+            }
+        }
         for (int base = warp * 32; base < len; base += AC_NW * 32) {
-            const int e = base + lane;
-            const int my_i = e < len ? __ldg(xi + e) : -1;
-            const XT my_x = e < len ? __ldg(xv + e) : (XT)0;
+            const int my_i = nxt_i;
+            const XT my_x = nxt_x;
+            {  // prefetch this warp's next block of 32 entries
+                const int e = base + AC_NW * 32 + lane;
+                nxt_i = -1;
+                nxt_x = (XT)0;
+                if (e < len) {
+                    nxt_i = __ldg(xi + e);
+                    nxt_x = __ldg(xv + e);
+                }
+            }
 #pragma unroll
             for (int s0 = 0; s0 < NSUB; s0 += GRP) {
                 int ri[GRP];
                 double rx[GRP];
-                uint2 rs[GRP];
-                int rbeg[GRP], rend[GRP];
+                if (FMT != 2) {
+                    // stage 1: the row slots; stage 2: bitmap lookups; stage 3: values of the hits; stage 4: accumulate.
+                    // No branches: an empty slot / a missing row has weight 0, column 0 and a suppressed value load.
+                    uint2 rs[GRP];
 #pragma unroll
-                for (int s = 0; s < GRP; ++s) {
-                    const int src = (s0 + s) * RPW + sub;
-                    ri[s] = __shfl_sync(0xffffffffu, my_i, src);
-                    rx[s] = (double)__shfl_sync(0xffffffffu, my_x, src);
-                    rs[s] = make_uint2(0xffffffffu, 0u);
-                    rbeg[s] = rend[s] = 0;
-                    if (ri[s] >= 0) {
-                        const int64_t r = PERM ? (int64_t)__ldg(p.perm + ri[s]) : (int64_t)ri[s];
-                        if (FMT == 2) {
-                            rbeg[s] = __ldg(p.wp + r);
-                            rend[s] = __ldg(p.wp + r + 1);
-                        } else {
+                    for (int s = 0; s < GRP; ++s) {
+                        const int src = (s0 + s) * RPW + sub;
+                        ri[s] = __shfl_sync(0xffffffffu, my_i, src);
+                        rx[s] = (double)__shfl_sync(0xffffffffu, my_x, src);
+                        rs[s] = make_uint2(0xffffffffu, 0u);
+                        if (ri[s] >= 0) {
+                            const int64_t r = PERM ? (int64_t)__ldg(p.perm + ri[s]) : (int64_t)ri[s];
                             rs[s] = __ldg(p.rows + r * LPR + slot);
                         }
                     }
-                }
+                    bool hit[GRP];
+                    unsigned int rank[GRP];
 #pragma unroll
-                for (int s = 0; s < GRP; ++s) {
-                    if (ri[s] < 0) continue;
-                    const double xv_i = rx[s], zi = xv_i - m;
-                    if (FMT == 2) {
-                        for (int ew = rbeg[s] + slot; ew < rend[s]; ew += LPR)
-                            ac_slot<XT, MODE>(S, xv, __ldg(p.wi + ew), __ldg(p.wd + ew), xv_i, zi, m, q[0], q[1]);
-                        if (!PERM && slot == 0) {
-                            const double c = __ldg(p.csum + ri[s]);
-                            q[2] = fma(c, zi, q[2]);
-                            q[3] += c;
-                            q[4] = fma(zi, zi, q[4]);
-                            q[5] = fma(c, xv_i * xv_i, q[5]);
-                        }
-                    } else if (slot == LPR - 1) {
-                        if (!PERM) {
-                            const double c = __longlong_as_double((long long)(((unsigned long long)rs[s].y << 32) | rs[s].x));
-                            q[2] = fma(c, zi, q[2]);
-                            q[3] += c;
-                            q[4] = fma(zi, zi, q[4]);
-                            q[5] = fma(c, xv_i * xv_i, q[5]);
-                        }
-                    } else {
+                    for (int s = 0; s < GRP; ++s) {
                         const int j = (int)rs[s].x;
-                        if (j >= 0) ac_slot<XT, MODE>(S, xv, j, (double)__uint_as_float(rs[s].y), xv_i, zi, m, q[0], q[1]);
+                        const int jj = j >= 0 ? j : 0;
+                        const uint2 w = S[jj >> 5];
+                        const unsigned int bit = 1u << (jj & 31);
+                        hit[s] = j >= 0 && (w.x & bit) != 0u;
+                        rank[s] = w.y + __popc(w.x & (bit - 1u));
+                    }
+                    XT xj[GRP];
+#pragma unroll
+                    for (int s = 0; s < GRP; ++s) xj[s] = hit[s] ? __ldg(xv + rank[s]) : (XT)0;
+#pragma unroll
+                    for (int s = 0; s < GRP; ++s) {
+                        const double w = (int)rs[s].x >= 0 ? (double)__uint_as_float(rs[s].y) : 0.0;
+                        const double xjd = (double)xj[s];
+                        if (MODE == 0) {
+                            const double t = w * (hit[s] ? xjd - m : -m);
+                            q[0] = fma(rx[s] - m, t, q[0]);
+                            q[1] += t;
+                        } else {
+                            const double d = rx[s] - xjd;
+                            q[0] = fma(w, d * d - xjd * xjd, q[0]);  // xj == 0 when not stored
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int s = 0; s < GRP; ++s) {
+                        const int src = (s0 + s) * RPW + sub;
+                        ri[s] = __shfl_sync(0xffffffffu, my_i, src);
+                        rx[s] = (double)__shfl_sync(0xffffffffu, my_x, src);
+                    }
+#pragma unroll
+                    for (int s = 0; s < GRP; ++s) {
+                        if (ri[s] < 0) continue;
+                        const int64_t r = PERM ? (int64_t)__ldg(p.perm + ri[s]) : (int64_t)ri[s];
+                        const int rbeg = __ldg(p.wp + r), rend = __ldg(p.wp + r + 1);
+                        const double zi = rx[s] - m;
+                        for (int ew = rbeg + slot; ew < rend; ew += LPR) {
+                            const int j = __ldg(p.wi + ew);
+                            const double w = __ldg(p.wd + ew);
+                            const uint2 sw = S[j >> 5];
+                            const unsigned int bit = 1u << (j & 31);
+                            const bool h = (sw.x & bit) != 0u;
+                            const double xjd = h ? (double)__ldg(xv + (sw.y + __popc(sw.x & (bit - 1u)))) : 0.0;
+                            if (MODE == 0) {
+                                const double t = w * (h ? xjd - m : -m);
+                                q[0] = fma(zi, t, q[0]);
+                                q[1] += t;
+                            } else {
+                                const double d = rx[s] - xjd;
+                                q[0] = fma(w, d * d - xjd * xjd, q[0]);
+                            }
+                        }
                     }
                 }
             }
@@ -995,7 +1027,10 @@ static int ac_build_segments(sqb_autocorr* h, const int64_t* d_ptr, const unsign
 
 template <typename XT>
 static int ac_load_csr_typed(sqb_autocorr* h, const int64_t* h_xp, const int32_t* h_xi, const void* h_xv, int layout,
-                             int64_t n_feat, int64_t nnz) {
+                             int64_t n_feat, int64_t nnz, int32_t col_lo = 0, const int64_t* sub_start = nullptr,
+                             const int64_t* sub_cnt = nullptr) {
+    // sub_start / sub_cnt (layout 1 only): upload only the piece [sub_start[r], +sub_cnt[r]) of every observation's row (the
+    // columns col_lo .. col_lo + n_feat of rows with ascending indices); h_xp then is the indptr of the pieces, nnz their total
     sqb_ctx* c = h->ctx;
     const int64_t n = h->n;
     const int64_t rows = layout == 0 ? n_feat : n;
@@ -1024,9 +1059,14 @@ static int ac_load_csr_typed(sqb_autocorr* h, const int64_t* h_xp, const int32_t
     if (e == cudaSuccess) e = cudaMemcpyAsync(r_ptr.p, h_xp, (rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream);
     if (e != cudaSuccess) return fail(e);
     if (nnz > 0) {
-        if ((rc = sqb_h2d(c, r_idx.p, h_xi, nnz * sizeof(int32_t))) || (rc = sqb_h2d(c, r_val.p, h_xv, (size_t)nnz * sizeof(XT)))) {
+        if (sub_start)
+            rc = sqb_h2d_gather(c, r_idx.p, h_xi, sizeof(int32_t), sub_start, sub_cnt, h_xp, rows) ||
+                 sqb_h2d_gather(c, r_val.p, h_xv, sizeof(XT), sub_start, sub_cnt, h_xp, rows);
+        else
+            rc = sqb_h2d(c, r_idx.p, h_xi, nnz * sizeof(int32_t)) || sqb_h2d(c, r_val.p, h_xv, (size_t)nnz * sizeof(XT));
+        if (rc) {
             cleanup();
-            return rc;
+            return SQB_ERR_CUDA;
         }
     }
     {
@@ -1056,7 +1096,7 @@ static int ac_load_csr_typed(sqb_autocorr* h, const int64_t* h_xp, const int32_t
             const int hist_smem = hist_bytes <= 160 * 1024 ? 1 : 0;
             if (hist_smem && hist_bytes > 48 * 1024)
                 cudaFuncSetAttribute(ac_colcount_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes);
-            ac_colcount_kernel<<<c->sm_count * (hist_smem ? 1 : 8), 1024, hist_smem ? hist_bytes : 0, c->stream>>>(r_idx.p, nnz, n_feat,
+            ac_colcount_kernel<<<c->sm_count * (hist_smem ? 1 : 8), 1024, hist_smem ? hist_bytes : 0, c->stream>>>(r_idx.p, nnz, n_feat, col_lo,
                                                                                                               hist_smem, cnt.p, h->d_flags.p);
         }
     }
@@ -1069,7 +1109,7 @@ static int ac_load_csr_typed(sqb_autocorr* h, const int64_t* h_xp, const int32_t
     if (layout != 0) {
         SqbLaunchScope scope(c, SQB_K_AUTOCORR_PREP);
         ac_coltranspose_kernel<XT><<<c->sm_count * 8, 256, 0, c->stream>>>(r_ptr.p, r_idx.p, reinterpret_cast<const XT*>(r_val.p), n, n_feat,
-                                                                           cursor.p, t_idx.p, reinterpret_cast<XT*>(t_val.p));
+                                                                           col_lo, cursor.p, t_idx.p, reinterpret_cast<XT*>(t_val.p));
         seg_ptr = t_ptr.p;
         seg_idx = t_idx.p;
         seg_val = reinterpret_cast<const XT*>(t_val.p);
@@ -1118,7 +1158,7 @@ int sqb_autocorr_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const int32_t* w_i
     h->nnz = nnz;
     h->s0 = s0;
     // packed rows hold float32 weights: only for float32 W (lossless); float64 W walks the CSR
-    h->w_fmt = (w_dtype == 0 && maxdeg <= 7) ? 0 : (w_dtype == 0 && maxdeg <= 15) ? 1 : 2;
+    h->w_fmt = (w_dtype == 0 && maxdeg <= 8) ? 0 : (w_dtype == 0 && maxdeg <= 16) ? 1 : 2;
     const int lpr = h->w_fmt == 0 ? 8 : 16;
     int rc;
     if ((rc = h->d_wp.alloc(n + 1)) || (rc = h->d_wi.alloc(nnz > 0 ? nnz : 1)) || (rc = h->d_wd.alloc(nnz > 0 ? nnz : 1)) ||
@@ -1134,9 +1174,9 @@ int sqb_autocorr_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const int32_t* w_i
     if (e == cudaSuccess && h->w_fmt != 2) {
         ctx->launches += 1;
         if (h->w_fmt == 0)
-            ac_pack_rows_kernel<8><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(h->d_wp.p, h->d_wi.p, h->d_wd.p, h->d_csum.p, n, h->d_rows.p);
+            ac_pack_rows_kernel<8><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(h->d_wp.p, h->d_wi.p, h->d_wd.p, n, h->d_rows.p);
         else
-            ac_pack_rows_kernel<16><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(h->d_wp.p, h->d_wi.p, h->d_wd.p, h->d_csum.p, n, h->d_rows.p);
+            ac_pack_rows_kernel<16><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(h->d_wp.p, h->d_wi.p, h->d_wd.p, n, h->d_rows.p);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // wd / csum are host temporaries
@@ -1224,6 +1264,64 @@ int sqb_autocorr_load_csr(sqb_autocorr* h, const int64_t* x_indptr, const int32_
     h->kind = 3;
     h->x_dtype = x_dtype;
     h->n_feat = n_features;
+    return SQB_OK;
+}
+
+int sqb_autocorr_load_csr_cols(sqb_autocorr* h, const int64_t* x_indptr, const int32_t* x_indices, const void* x_data, int x_dtype,
+                               int64_t n_features_total, int64_t col_lo, int64_t col_hi) {
+    SQB_CHECK(h && x_indptr, SQB_ERR_INVALID, "sqb_autocorr_load_csr_cols: null argument");
+    SQB_CHECK(x_dtype == 0 || x_dtype == 1, SQB_ERR_INVALID, "sqb_autocorr_load_csr_cols: x_dtype must be 0 or 1");
+    SQB_CHECK(0 <= col_lo && col_lo < col_hi && col_hi <= n_features_total && n_features_total < 2147483647LL, SQB_ERR_INVALID,
+              "sqb_autocorr_load_csr_cols: bad column range [%lld, %lld) of %lld", (long long)col_lo, (long long)col_hi,
+              (long long)n_features_total);
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    const int64_t n = h->n;
+    const int64_t nnz_all = x_indptr[n];
+    SQB_CHECK(x_indptr[0] == 0 && nnz_all >= 0, SQB_ERR_INVALID, "sqb_autocorr_load_csr_cols: bad indptr");
+    SQB_CHECK(nnz_all == 0 || (x_indices && x_data), SQB_ERR_INVALID, "sqb_autocorr_load_csr_cols: null X arrays");
+    // per observation: the run of entries with col_lo <= column < col_hi (rows hold ascending columns: two binary searches)
+    std::vector<int64_t> start((size_t)n), cnt((size_t)n), ptr((size_t)n + 1);
+    {
+        int threads = (int)std::thread::hardware_concurrency() / 8;
+        threads = threads < 2 ? 2 : (threads > 16 ? 16 : threads);
+        std::vector<std::thread> pool;
+        std::vector<int> bad((size_t)threads, 0);
+        for (int t = 0; t < threads; ++t) {
+            pool.emplace_back([&, t]() {
+                for (int64_t r = n * t / threads; r < n * (t + 1) / threads; ++r) {
+                    const int64_t a = x_indptr[r], b = x_indptr[r + 1];
+                    if (a > b || a < 0 || b > nnz_all) {
+                        bad[t] = 1;
+                        start[r] = 0;
+                        cnt[r] = 0;
+                        continue;
+                    }
+                    const int32_t* lo = std::lower_bound(x_indices + a, x_indices + b, (int32_t)col_lo);
+                    const int32_t* hi = std::lower_bound(lo, x_indices + b, (int32_t)col_hi);
+                    start[r] = lo - x_indices;
+                    cnt[r] = hi - lo;
+                }
+            });
+        }
+        for (auto& th : pool) th.join();
+        for (int t = 0; t < threads; ++t) SQB_CHECK(!bad[t], SQB_ERR_INVALID, "sqb_autocorr_load_csr_cols: indptr is not non-decreasing");
+    }
+    ptr[0] = 0;
+    for (int64_t r = 0; r < n; ++r) ptr[r + 1] = ptr[r] + cnt[r];
+    h->kind = 0;
+    h->aux_valid = false;
+    h->ran = false;
+    // the device checks that every uploaded column lies in [col_lo, col_hi) (an unsorted row shows up there or as a
+    // duplicate) while it re-lays the slice out
+    const int64_t nf = col_hi - col_lo;
+    if (x_dtype == 0)
+        SQB_TRY(ac_load_csr_typed<float>(h, ptr.data(), x_indices, x_data, 1, nf, ptr[n], (int32_t)col_lo, start.data(), cnt.data()));
+    else
+        SQB_TRY(ac_load_csr_typed<double>(h, ptr.data(), x_indices, x_data, 1, nf, ptr[n], (int32_t)col_lo, start.data(), cnt.data()));
+    h->kind = 3;
+    h->x_dtype = x_dtype;
+    h->n_feat = nf;
     return SQB_OK;
 }
 

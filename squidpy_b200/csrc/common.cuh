@@ -111,10 +111,10 @@ struct sqb_ctx {
     // otherwise dominate the host-facing latency).  Work on one ctx is stream ordered, so handles can share them.
     DevBuf<uint8_t> scratch[3];
     // pinned staging ring for large host-to-device copies of pageable caller memory (sqb_h2d)
-    static constexpr int kStage = 4;
-    void* stage[kStage] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t stage_ev[kStage] = {nullptr, nullptr, nullptr, nullptr};
-    bool stage_used[kStage] = {false, false, false, false};
+    static constexpr int kStage = 16;
+    void* stage[kStage] = {};
+    cudaEvent_t stage_ev[kStage] = {};
+    bool stage_used[kStage] = {};
 };
 
 // Host-to-device copy of caller-owned (pageable) memory on the ctx stream.  Large copies go through a ring of pinned
@@ -122,6 +122,8 @@ struct sqb_ctx {
 // pageable memory ran at ~3-7 GB/s on the B200 hosts (3.2 GB of expression matrix = 1 s of a 1.08 s Moran call).
 // The source has been read completely when the call returns; the copy itself completes in stream order.
 int sqb_h2d(sqb_ctx* c, void* dst, const void* src, size_t bytes);
+int sqb_h2d_gather(sqb_ctx* c, void* dst, const void* src, size_t elem, const int64_t* start, const int64_t* cnt,
+                   const int64_t* out_ptr, int64_t rows);
 
 // Launch accounting.  In profile mode each launch is bracketed by events on the ctx stream and the elapsed
 // time accumulated per kernel class (the launch is synchronised; never used inside a timed bench region

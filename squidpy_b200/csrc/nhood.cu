@@ -2126,84 +2126,121 @@ __global__ void __launch_bounds__(256) nhood_transpose_kernel(const LT* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// 2c. Fast RNG mode ("philox"): no replay of numpy's stream, no label materialisation per permutation-major row, no
-//     Fisher-Yates at all.  Permutation p of a segment of m labels is a KEYED BIJECTION pi_p on [0, m): a 4-round
-//     balanced Feistel network on 2k bits (2^(2k) >= m, k = ceil(bits(m-1)/2)) with cycle walking (re-encrypt until
-//     the value falls below m; < 4 tries on average, 1.05 at m = 10^6), round function = keyed multiply-xorshift hash,
-//     round keys = splitmix64(seed, global permutation index, segment, round).  The segment's labels are used SORTED BY
-//     CLASS (cum[c] = number of labels below class c), so the label of position r under permutation p is
-//     class_of(pi_p(r)) = the last c with cum[c] <= pi_p(r): a 5-step binary search in shared memory instead of a
-//     random gather from a 1 MB array.  Shuffling the sorted vector is the same distribution as shuffling the original.
-//     One lane evaluates 4 consecutive permutations of one position and stores 4 labels straight into the
-//     permutation-minor matrix labT[node][PB] the count kernel reads: fill + target generation + apply + transpose
-//     (21 of the 25 ms of the exact mode at 1M x 1000) collapse into one streaming kernel.
-//     tests/philox_ref.py is the executable specification (numpy); results are validated statistically against the
-//     exact mode.
+// 2c. Fast RNG mode ("philox"): no replay of numpy's stream, no Fisher-Yates, no permutation-major label rows.
+//     Permutation p of a segment of m labels is a KEYED BIJECTION pi_p on [0, m): a generalised Feistel network
+//     (Black & Rogaway's FE2) on the mixed-radix domain [0, a) x [0, b), a = ceil(sqrt(m)), b = ceil(m / a), so that
+//     a*b - m < a and cycle walking (re-encrypt while the value is >= m) practically never happens (m = 10^6: 1 value
+//     in 1000);  x = L*b + R, six rounds alternate  L <- (L + mulhi(F(R ^ k_j), a)) mod a,
+//     R <- (R + mulhi(F(L ^ k_j), b)) mod b  with the multiply-xorshift hash F and a Philox-style Weyl key schedule
+//     k_j = k0 + j*k1, (k0, k1) = splitmix64(seed, global permutation index, segment).  The segment's labels are used
+//     SORTED BY CLASS (cum[c] = number of labels below class c): the label of position r under permutation p is
+//     class_of(pi_p(r)) = the last c with cum[c] <= pi_p(r), found through a shared-memory bucket table + a fixed
+//     number of bisection steps instead of a random gather from a 1 MB array.  Shuffling the sorted vector has the same
+//     distribution as shuffling the original.  One lane evaluates 4 consecutive permutations of one position (4
+//     independent dependency chains) and stores 4 labels straight into the permutation-minor matrix labT[node][PB] the
+//     count kernel reads: fill + target generation + apply + transpose (21 of the 25 ms of the exact mode at 1M x 1000)
+//     collapse into one streaming kernel.  tests/philox_ref.py is the executable specification (numpy, bit-identical);
+//     results are validated statistically against the exact mode.
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint32_t sqb_philox_key(uint64_t seed, uint64_t perm, uint32_t seg, uint32_t round) {
+__host__ __device__ __forceinline__ uint32_t sqb_philox_key(uint64_t seed, uint64_t perm, uint32_t seg, uint32_t which) {
     uint64_t z = seed + 0x9E3779B97F4A7C15ull * (perm + 1ull);
-    z ^= (uint64_t)(seg * 4u + round + 1u) * 0xD1B54A32D192ED03ull;
+    z ^= (uint64_t)(seg * 2u + which + 1u) * 0xD1B54A32D192ED03ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z ^= z >> 31;
     return (uint32_t)(z >> 32);
 }
 
-__device__ __forceinline__ uint32_t sqb_feistel_walk(uint32_t x, const uint32_t (&key)[4], uint32_t k, uint32_t mask, uint32_t m) {
-    do {
-        uint32_t L = x >> k, R = x & mask;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            uint32_t t = (R ^ key[r]) * 0x85EBCA6Bu;
-            t ^= t >> 13;
-            t *= 0xC2B2AE35u;
-            t ^= t >> 16;
-            const uint32_t nr = L ^ (t & mask);
-            L = R;
-            R = nr;
-        }
-        x = (L << k) | R;
-    } while (x >= m);
-    return x;
+__device__ __forceinline__ uint32_t sqb_fe2_hash(uint32_t v) {
+    v *= 0x9E3779B1u;
+    v ^= v >> 15;
+    v *= 0x85EBCA77u;
+    return v;  // only the high bits are used (mulhi)
 }
 
-template <typename LT>
-__global__ void __launch_bounds__(256) nhood_philox_labels_kernel(LT* __restrict__ labT, int PB, int64_t seg_start, int64_t seg_len,
-                                                                  const uint32_t* __restrict__ cum, int C, int cum_smem,
-                                                                  const uint32_t* __restrict__ order, uint64_t seed, int64_t perm0,
-                                                                  int seg, int kbits, int64_t pos_per_cta) {
-    extern __shared__ uint32_t s_cum[];
-    if (cum_smem) {
-        for (int c = threadIdx.x; c <= C; c += blockDim.x) s_cum[c] = cum[c];
-        __syncthreads();
+// one pass of the 6-round network over (L, R) in [0, a) x [0, b): every half is updated three times.  Four rounds are
+// measurably too few (the same-class neighbour counts of a lattice come out 3.5 % high and twice as dispersed, caught by
+// tests/test_gpu_philox.py::test_statistical_validation_against_exact_mode); six match numpy's shuffle in mean and variance.
+__device__ __forceinline__ void sqb_fe2(uint32_t& L, uint32_t& R, uint32_t k0, uint32_t k1, uint32_t a, uint32_t b) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const uint32_t kj = k0 + (uint32_t)j * k1;
+        if ((j & 1) == 0) {
+            L += __umulhi(sqb_fe2_hash(R ^ kj), a);
+            L -= L >= a ? a : 0u;
+        } else {
+            R += __umulhi(sqb_fe2_hash(L ^ kj), b);
+            R -= R >= b ? b : 0u;
+        }
     }
-    const uint32_t* __restrict__ tab = cum_smem ? s_cum : cum;
+}
+
+struct PhiloxSeg {
+    int64_t start, len;   // segment in grouped order
+    uint32_t a, b;        // Feistel radices
+    int shift, tsize;     // bucket = value >> shift; table of tsize + 1 entries
+    int steps;            // bisection steps after the bucket lookup
+    int seg;
+};
+
+template <typename LT>
+__global__ void __launch_bounds__(256) nhood_philox_labels_kernel(LT* __restrict__ labT, int PB, PhiloxSeg sg,
+                                                                  const uint32_t* __restrict__ cum, int C,
+                                                                  const uint32_t* __restrict__ bucket,
+                                                                  const uint32_t* __restrict__ order, uint64_t seed, int64_t perm0,
+                                                                  int64_t pos_per_cta) {
+    extern __shared__ uint32_t s_tab[];  // [C + 1] class offsets, then [tsize + 1] class at the start of every bucket
+    uint32_t* __restrict__ s_cum = s_tab;
+    uint32_t* __restrict__ s_bkt = s_tab + (C + 1);
+    for (int c = threadIdx.x; c <= C; c += blockDim.x) s_cum[c] = cum[c];
+    for (int c = threadIdx.x; c <= sg.tsize; c += blockDim.x) s_bkt[c] = bucket[c];
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int p4 = (blockIdx.y * 32 + lane) * 4;
     if (p4 >= PB) return;
-    const uint32_t k = (uint32_t)kbits, mask = (1u << k) - 1u, m = (uint32_t)seg_len;
-    uint32_t key[4][4];
+    const uint32_t a = sg.a, b = sg.b, m = (uint32_t)sg.len;
+    uint32_t k0[4], k1[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) key[q][r] = sqb_philox_key(seed, (uint64_t)(perm0 + p4 + q), (uint32_t)seg, (uint32_t)r);
+    for (int q = 0; q < 4; ++q) {
+        k0[q] = sqb_philox_key(seed, (uint64_t)(perm0 + p4 + q), (uint32_t)sg.seg, 0u);
+        k1[q] = sqb_philox_key(seed, (uint64_t)(perm0 + p4 + q), (uint32_t)sg.seg, 1u) | 1u;
+    }
     int64_t r0 = (int64_t)blockIdx.x * pos_per_cta, r1 = r0 + pos_per_cta;
-    if (r1 > seg_len) r1 = seg_len;
+    if (r1 > sg.len) r1 = sg.len;
     for (int64_t r = r0 + warp; r < r1; r += nwarps) {
-        const int64_t node = order ? (int64_t)order[seg_start + r] : seg_start + r;
+        const int64_t node = order ? (int64_t)order[sg.start + r] : sg.start + r;
+        const uint32_t L0 = (uint32_t)r / b, R0 = (uint32_t)r - L0 * b;
+        uint32_t y[4];
+        bool walk = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t L = L0, R = R0;
+            sqb_fe2(L, R, k0[q], k1[q], a, b);
+            y[q] = L * b + R;
+            walk |= y[q] >= m;
+        }
+        if (walk) {  // a*b - m < a values fall outside [0, m): rare
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                while (y[q] >= m) {
+                    uint32_t L = y[q] / b, R = y[q] - L * b;
+                    sqb_fe2(L, R, k0[q], k1[q], a, b);
+                    y[q] = L * b + R;
+                }
+            }
+        }
         uint32_t cls[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint32_t x = m > 1u ? sqb_feistel_walk((uint32_t)r, key[q], k, mask, m) : 0u;
-            int lo = 0, hi = C;  // last class c with tab[c] <= x  (tab[0] = 0; empty classes are skipped by "last")
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (tab[mid] <= x)
-                    lo = mid;
-                else
-                    hi = mid;
+            const uint32_t bk = y[q] >> sg.shift;
+            uint32_t lo = s_bkt[bk], hi = s_bkt[bk + 1];  // last class with cum <= first / last value of the bucket
+            for (int s = 0; s < sg.steps; ++s) {           // invariant: cum[lo] <= y <  cum[hi + 1]
+                const uint32_t mid = (lo + hi + 1u) >> 1;
+                const bool le = s_cum[mid] <= y[q];
+                lo = le ? mid : lo;
+                hi = le ? hi : mid - 1u;
             }
-            cls[q] = (uint32_t)lo;
+            cls[q] = lo;
         }
         LT* dst = labT + node * PB + p4;
         if (sizeof(LT) == 1) {
@@ -2448,7 +2485,9 @@ struct sqb_nhood {
     uint64_t philox_seed = 0;
     int64_t perm_first = 0;  // global index of permutation 0 of this handle (multi-GPU shards keep their global indices)
     DevBuf<uint32_t> d_cum;  // [nseg][n_cls + 1] class offsets of every segment's sorted labels (fast mode)
-    std::vector<int64_t> h_seg_start, h_seg_len;
+    DevBuf<uint32_t> d_bkt;  // per segment: class at the first value of every bucket (fast mode class lookup)
+    std::vector<int64_t> h_seg_start, h_seg_len, h_bkt_off;
+    std::vector<PhiloxSeg> h_pseg;
     // label matrices [chunk][stride] and [n][PB] live in ctx->scratch[0..1]
     DevBuf<uint32_t> d_counts;  // [P][C*C]
     DevBuf<uint32_t> d_tmp_u32;
@@ -2836,14 +2875,14 @@ template <typename LT>
 static int philox_labels(sqb_nhood* h, int64_t p0, int64_t np, LT* labT, int PB) {
     sqb_ctx* c = h->ctx;
     const int C = h->n_cls;
-    const int cum_smem = ((size_t)(C + 1) * 4 <= 40 * 1024) ? 1 : 0;
     for (int sgm = 0; sgm < h->nseg; ++sgm) {
-        const int64_t m = h->h_seg_len[sgm];
+        const PhiloxSeg& ps = h->h_pseg[sgm];
+        const int64_t m = ps.len;
         if (m <= 0) continue;
-        int bits = 0;
-        while (bits < 32 && ((uint64_t)(m - 1) >> bits) != 0) ++bits;
-        int kbits = (bits + 1) / 2;
-        if (kbits < 1) kbits = 1;
+        const size_t smem = ((size_t)(C + 1) + (size_t)ps.tsize + 1) * sizeof(uint32_t);
+        SQB_CHECK(smem <= h->ctx->smem_optin, SQB_ERR_UNSUPPORTED, "fast RNG mode: %d classes do not fit the shared-memory class table", C);
+        if (smem > 48 * 1024)
+            SQB_CUDA(cudaFuncSetAttribute(nhood_philox_labels_kernel<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int gy = (PB / 4 + 31) / 32;
         int64_t gx = ceil_div64((int64_t)c->sm_count * 8, gy);
         if (gx > ceil_div64(m, 8)) gx = ceil_div64(m, 8);
@@ -2851,9 +2890,9 @@ static int philox_labels(sqb_nhood* h, int64_t p0, int64_t np, LT* labT, int PB)
         const int64_t pos_per_cta = ceil_div64(m, gx);
         gx = ceil_div64(m, pos_per_cta);
         SqbLaunchScope scope(c, SQB_K_NHOOD_SHUFFLE);
-        nhood_philox_labels_kernel<LT><<<dim3((unsigned)gx, (unsigned)gy), 256, cum_smem ? (size_t)(C + 1) * 4 : 0, c->stream>>>(
-            labT, PB, h->h_seg_start[sgm], m, h->d_cum.p + (size_t)sgm * (C + 1), C, cum_smem, h->has_order ? h->d_order.p : nullptr,
-            h->philox_seed, h->perm_first + p0, sgm, kbits, pos_per_cta);
+        nhood_philox_labels_kernel<LT><<<dim3((unsigned)gx, (unsigned)gy), 256, smem, c->stream>>>(
+            labT, PB, ps, h->d_cum.p + (size_t)sgm * (C + 1), C, h->d_bkt.p + h->h_bkt_off[sgm], h->has_order ? h->d_order.p : nullptr,
+            h->philox_seed, h->perm_first + p0, pos_per_cta);
         SQB_POST_LAUNCH();
     }
     (void)np;
@@ -2991,6 +3030,8 @@ int sqb_nhood_destroy(sqb_nhood* h) {
     h->d_seg_len.release();
     h->d_states.release();
     h->d_counts.release();
+    h->d_cum.release();
+    h->d_bkt.release();
     h->d_tmp_u32.release();
     delete h;
     return SQB_OK;
@@ -3147,16 +3188,56 @@ int sqb_nhood_set_base(sqb_nhood* h, const uint32_t* base_labels, const int32_t*
     h->nseg = (int)seg_start.size();
     h->h_seg_start = seg_start;
     h->h_seg_len = seg_len;
-    {  // fast RNG mode: class offsets of every segment's labels sorted by class
+    {  // fast RNG mode: per segment the class offsets of its labels sorted by class, the Feistel radices and a bucket table
+       // (class at the first value of every bucket of 2^shift values) that shortens the class search to `steps` bisections
         const int64_t C1 = (int64_t)h->n_cls + 1;
-        std::vector<uint32_t> cum((size_t)h->nseg * C1, 0u);
+        std::vector<uint32_t> cum((size_t)h->nseg * C1, 0u), bkt;
+        h->h_pseg.assign(h->nseg, PhiloxSeg());
+        h->h_bkt_off.assign(h->nseg, 0);
         for (int sgm = 0; sgm < h->nseg; ++sgm) {
             uint32_t* row = cum.data() + (size_t)sgm * C1;
-            for (int64_t k = seg_start[sgm]; k < seg_start[sgm] + seg_len[sgm]; ++k) row[grouped[k] + 1]++;
+            const int64_t m = seg_len[sgm];
+            for (int64_t k = seg_start[sgm]; k < seg_start[sgm] + m; ++k) row[grouped[k] + 1]++;
             for (int64_t cc = 0; cc < h->n_cls; ++cc) row[cc + 1] += row[cc];
+            PhiloxSeg& ps = h->h_pseg[sgm];
+            ps.start = seg_start[sgm];
+            ps.len = m;
+            ps.seg = sgm;
+            uint64_t a = (uint64_t)sqrt((double)(m > 0 ? m : 1));
+            while (a * a < (uint64_t)m) ++a;
+            while (a > 1 && (a - 1) * (a - 1) >= (uint64_t)m) --a;
+            if (a < 1) a = 1;
+            ps.a = (uint32_t)a;
+            ps.b = (uint32_t)((m + (int64_t)a - 1) / (int64_t)a);
+            if (ps.b < 1) ps.b = 1;
+            int bits = 0;
+            while (bits < 32 && ((uint64_t)(m > 0 ? m - 1 : 0) >> bits) != 0) ++bits;
+            ps.shift = bits > 11 ? bits - 11 : 0;  // <= 2048 buckets
+            ps.tsize = (int)((((uint64_t)(m > 0 ? m - 1 : 0)) >> ps.shift) + 1);
+            h->h_bkt_off[sgm] = (int64_t)bkt.size();
+            auto class_of = [&](uint64_t v) {  // last c in [0, n_cls) with row[c] <= v
+                int lo = 0, hi = h->n_cls - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if ((uint64_t)row[mid] <= v) lo = mid; else hi = mid - 1;
+                }
+                return (uint32_t)lo;
+            };
+            for (int t = 0; t <= ps.tsize; ++t) bkt.push_back(class_of((uint64_t)t << ps.shift));
+            // the kernel searches [table[bucket], table[bucket + 1]] (class at the first value of this / of the next bucket)
+            uint32_t maxrange = 0;
+            for (int t = 0; t < ps.tsize; ++t) {
+                const uint32_t d = bkt[h->h_bkt_off[sgm] + t + 1] - bkt[h->h_bkt_off[sgm] + t];
+                if (d > maxrange) maxrange = d;
+            }
+            int steps = 0;
+            while ((1u << steps) < maxrange + 1u) ++steps;
+            ps.steps = steps;
         }
         SQB_TRY(h->d_cum.alloc(cum.size()));
+        SQB_TRY(h->d_bkt.alloc(bkt.size() > 0 ? bkt.size() : 1));
         SQB_CUDA(cudaMemcpy(h->d_cum.p, cum.data(), cum.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        SQB_CUDA(cudaMemcpy(h->d_bkt.p, bkt.data(), bkt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     SQB_TRY(h->d_seg_start.alloc(h->nseg));
     SQB_TRY(h->d_seg_len.alloc(h->nseg));
@@ -3392,6 +3473,45 @@ int sqb_nhood_permute_var_chain(sqb_nhood* h, const double* mean, const double* 
         sqb_set_error("sqb_nhood_permute_var_chain: %s", cudaGetErrorString(e));
         return SQB_ERR_CUDA;
     }
+    return SQB_OK;
+}
+
+// Device-pointer forms of the statistics (asynchronous on the ctx stream; the caller owns the device buffers, e.g. torch
+// tensors handed to NCCL): nothing crosses the PCIe bus between the count kernel and the collective.
+int sqb_nhood_permute_stats_dev(sqb_nhood* h, double* d_mean, double* d_std) {
+    SQB_CHECK(h && d_mean && d_std, SQB_ERR_INVALID, "sqb_nhood_permute_stats_dev: null argument");
+    SQB_CHECK(h->ran, SQB_ERR_STATE, "sqb_nhood_permute_stats_dev: nothing has run");
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    const int CC = h->n_cls * h->n_cls;
+    SqbLaunchScope scope(c, SQB_K_MISC);
+    nhood_stats_kernel<<<(unsigned)ceil_div64(CC, 64), 64, 0, c->stream>>>(h->d_counts.p, h->n_perms, CC, d_mean, d_std);
+    SQB_POST_LAUNCH();
+    return SQB_OK;
+}
+
+int sqb_nhood_permute_sums_dev(sqb_nhood* h, int64_t* d_sums) {
+    SQB_CHECK(h && d_sums, SQB_ERR_INVALID, "sqb_nhood_permute_sums_dev: null argument");
+    SQB_CHECK(h->ran, SQB_ERR_STATE, "sqb_nhood_permute_sums_dev: nothing has run");
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    const int CC = h->n_cls * h->n_cls;
+    SqbLaunchScope scope(c, SQB_K_MISC);
+    nhood_sums_kernel<<<(unsigned)ceil_div64(CC, 64), 64, 0, c->stream>>>(h->d_counts.p, h->n_perms, CC,
+                                                                           reinterpret_cast<unsigned long long*>(d_sums));
+    SQB_POST_LAUNCH();
+    return SQB_OK;
+}
+
+int sqb_nhood_permute_var_chain_dev(sqb_nhood* h, const double* d_mean, const double* d_acc_in, double* d_acc_out) {
+    SQB_CHECK(h && d_mean && d_acc_in && d_acc_out, SQB_ERR_INVALID, "sqb_nhood_permute_var_chain_dev: null argument");
+    SQB_CHECK(h->ran, SQB_ERR_STATE, "sqb_nhood_permute_var_chain_dev: nothing has run");
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    const int CC = h->n_cls * h->n_cls;
+    SqbLaunchScope scope(c, SQB_K_MISC);
+    nhood_var_chain_kernel<<<(unsigned)ceil_div64(CC, 64), 64, 0, c->stream>>>(h->d_counts.p, h->n_perms, CC, d_mean, d_acc_in, d_acc_out);
+    SQB_POST_LAUNCH();
     return SQB_OK;
 }
 

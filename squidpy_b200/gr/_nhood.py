@@ -17,7 +17,7 @@ from typing import Any, NamedTuple
 import numpy as np
 
 from .._constants import Key
-from .._dist import sequential_stats, shard_range, shared_seed, world
+from .._dist import nccl_cuda, sequential_stats, sequential_stats_device, shard_range, shared_seed, world
 from .._lib import Context, check, default_context, load
 from .._rng import spawn_states
 from .._validators import assert_categorical_obs, assert_connectivity_key, assert_positive, extract_adata_if_sdata
@@ -133,6 +133,16 @@ class NhoodPlan:
         check(self._lib.sqb_nhood_permute_var_chain(self._h, mean.ctypes.data, acc_in.ctypes.data, out.ctypes.data))
         return out
 
+    def stats_dev(self, d_mean: int, d_std: int) -> None:
+        """``stats`` into caller-owned device buffers (raw pointers), asynchronous on the context's stream."""
+        check(self._lib.sqb_nhood_permute_stats_dev(self._h, C.c_void_p(d_mean), C.c_void_p(d_std)))
+
+    def sums_dev(self, d_sums: int) -> None:
+        check(self._lib.sqb_nhood_permute_sums_dev(self._h, C.c_void_p(d_sums)))
+
+    def var_chain_dev(self, d_mean: int, d_acc_in: int, d_acc_out: int) -> None:
+        check(self._lib.sqb_nhood_permute_var_chain_dev(self._h, C.c_void_p(d_mean), C.c_void_p(d_acc_in), C.c_void_p(d_acc_out)))
+
     def permute(self, states: np.ndarray) -> np.ndarray:
         """uint32 (n_perms, n_cls, n_cls) neighbour-pair counts of every permutation."""
         states = np.ascontiguousarray(states, dtype=np.uint64)
@@ -208,40 +218,38 @@ def nhood_enrichment(
         raise ValueError(f"Expected `rng` to be 'numpy' or 'philox', found `{rng!r}`.")
     start = time.perf_counter()
     ctx = default_context(device)
-    plan = NhoodPlan(adj.indptr, adj.indices, n_cls, ctx)
-    try:
-        count = plan.count(int_clust)
-        rank, ws = world()
-        lo, hi = shard_range(int(n_perms), rank, ws)
-        seed = shared_seed(seed)  # seed=None: one entropy draw for all ranks (every rank must spawn the same family)
-        if rng == "philox":
-            fast_seed = int(np.random.SeedSequence(seed).generate_state(1, np.uint64)[0])
-
-        def upload():
-            plan.set_base(int_clust, lib_codes, n_libs)
-            if rng == "philox":
-                plan.upload_philox(fast_seed, lo, hi - lo)
-            else:
-                plan.upload(spawn_states(seed, int(n_perms), lo, hi))
-        logg.info("Calculating neighborhood enrichment on cuda:%d (rank %d/%d, permutations %d..%d)", ctx.device, rank, ws, lo, hi)
-        if ws == 1:
-            # single GPU: mean / std over the permutations on the device, in numpy's operation order (bit-identical to the
-            # host expression below); the per-permutation counts never leave the GPU
-            upload()
-            plan.run_async()
-            mean, std = plan.stats()
-        else:
-            # several GPUs: exact integer sums all-reduced, the order-dependent variance accumulation chained through the
-            # ranks in permutation order (bit-identical to mean/std of the gathered counts; nothing but [C, C] tensors moves)
+    with ctx.lock:
+        plan = NhoodPlan(adj.indptr, adj.indices, n_cls, ctx)
+        try:
+            count = plan.count(int_clust)
+            rank, ws = world()
+            lo, hi = shard_range(int(n_perms), rank, ws)
+            logg.info("Calculating neighborhood enrichment on cuda:%d (rank %d/%d, permutations %d..%d)", ctx.device, rank, ws, lo, hi)
+            seed = shared_seed(seed)  # seed=None: one entropy draw for all ranks (every rank must spawn the same family)
             if hi > lo:
-                upload()
+                plan.set_base(int_clust, lib_codes, n_libs)
+                if rng == "philox":
+                    plan.upload_philox(int(np.random.SeedSequence(seed).generate_state(1, np.uint64)[0]), lo, hi - lo)
+                else:
+                    plan.upload(spawn_states(seed, int(n_perms), lo, hi))
                 plan.run_async()
-                sums_local, step = plan.sums(), plan.var_chain
-            else:  # more ranks than permutations
-                sums_local, step = np.zeros((n_cls, n_cls), dtype=np.int64), (lambda mean, acc: acc)
-            mean, std = sequential_stats(sums_local, step, int(n_perms))
-    finally:
-        plan.close()
+            if ws == 1:
+                # single GPU: mean / std over the permutations on the device, in numpy's operation order (bit-identical to
+                # the host expression of the reference); the per-permutation counts never leave the GPU
+                mean, std = plan.stats()
+            elif nccl_cuda():
+                # several GPUs: exact integer sums all-reduced, the order-dependent variance accumulation chained through the
+                # ranks in permutation order — device tensors end to end, one [2, C, C] download (bit-identical to mean/std of
+                # the gathered counts; nothing but [C, C] tensors moves)
+                mean, std = sequential_stats_device(plan, int(n_perms), hi > lo)
+            else:  # gloo (CPU tests of the host logic): the same chain through host buffers
+                if hi > lo:
+                    sums_local, step = plan.sums(), plan.var_chain
+                else:  # more ranks than permutations
+                    sums_local, step = np.zeros((n_cls, n_cls), dtype=np.int64), (lambda mean, acc: acc)
+                mean, std = sequential_stats(sums_local, step, int(n_perms))
+        finally:
+            plan.close()
     with np.errstate(divide="ignore", invalid="ignore"):
         zscore = (count - mean) / std  # _nhood.py:231 (no zero-std guard there either)
 

@@ -73,29 +73,49 @@ class AutocorrPlan:
             return np.ascontiguousarray(a), 0
         return np.ascontiguousarray(a, dtype=np.float64), 1  # ints, float16, float64 ... -> float64 like scanpy's astype
 
-    def load(self, m: Any, *, obs_major: bool) -> None:
-        """``m``: observations x features if ``obs_major`` else features x observations; dense or scipy sparse."""
+    def load(self, m: Any, *, obs_major: bool, cols: tuple[int, int] | None = None) -> None:
+        """``m``: observations x features if ``obs_major`` else features x observations; dense or scipy sparse.
+        ``cols=(lo, hi)`` loads only features ``lo..hi`` (the shard of one rank): for CSR-by-observation input the slice is
+        cut while the matrix is staged for the upload (``sqb_autocorr_load_csr_cols``), nothing is copied on the host."""
         n_feat = m.shape[1] if obs_major else m.shape[0]
         n_obs = m.shape[0] if obs_major else m.shape[1]
         if n_obs != self.n:
             raise ValueError(f"Expected `{self.n}` observations, found `{n_obs}`.")
+        if cols is not None and tuple(cols) == (0, n_feat):
+            cols = None
         if issparse(m):
             if m.format == "csc":  # CSC of (a x b) == CSR of (b x a): flip the orientation instead of converting
                 m = m.T
                 obs_major = not obs_major
             elif m.format != "csr":
                 m = m.tocsr()
-            if not m.has_canonical_format:
-                m = m.copy()
-                m.sum_duplicates()
+            # entry order inside a row does not matter and repeated entries are rejected by the device (no host pass over
+            # the non-zeros); only the column-sliced upload needs ascending indices
+            if cols is not None and obs_major:
+                if not m.has_sorted_indices:
+                    m = m.copy()
+                    m.sort_indices()
+                data, dt = self._dt(m.data)
+                xp = np.ascontiguousarray(m.indptr, dtype=np.int64)
+                xi = np.ascontiguousarray(m.indices, dtype=np.int32)
+                check(self._lib.sqb_autocorr_load_csr_cols(self._h, xp.ctypes.data, xi.ctypes.data, data.ctypes.data, dt, n_feat, int(cols[0]), int(cols[1])))
+                self.n_features = int(cols[1] - cols[0])
+                return
+            if cols is not None:
+                m = m[cols[0] : cols[1]]  # features x observations: a row slice of the CSR is cheap
+                n_feat = m.shape[0]
             data, dt = self._dt(m.data)
             xp = np.ascontiguousarray(m.indptr, dtype=np.int64)
             xi = np.ascontiguousarray(m.indices, dtype=np.int32)
             check(self._lib.sqb_autocorr_load_csr(self._h, xp.ctypes.data, xi.ctypes.data, data.ctypes.data, dt, int(obs_major), n_feat))
         else:
-            a, dt = self._dt(np.asarray(m))
+            a = np.asarray(m)
+            if cols is not None:
+                a = a[:, cols[0] : cols[1]] if obs_major else a[cols[0] : cols[1]]
+                n_feat = cols[1] - cols[0]
+            a, dt = self._dt(a)
             check(self._lib.sqb_autocorr_load_dense(self._h, a.ctypes.data, dt, int(obs_major), n_feat))
-        self.n_features = n_feat
+        self.n_features = int(n_feat)
 
     def run_async(self, mode: SpatialAutocorr | str, row_perm: np.ndarray | None = None) -> None:
         mode = SpatialAutocorr(mode)
@@ -177,6 +197,10 @@ def spatial_autocorr(
         elif isinstance(genes, str):
             genes = [genes]
         if not use_raw:
+            if len(genes) == adata.shape[1] and np.array_equal(np.asarray(genes), np.asarray(adata.var_names)):
+                # all variables in their own order: the subset is the matrix itself (the reference's adata[:, genes] copies it
+                # on the host; at 4e8 non-zeros that copy alone costs seconds)
+                return (adata.X if layer is None else adata.layers[layer]), genes
             subset = adata[:, genes]
             return (subset.X if layer is None else subset.layers[layer]), genes
         if adata.raw is None:
@@ -227,28 +251,29 @@ def spatial_autocorr(
     lo, hi = shard_range(n_feat, rank, ws)
     ctx = default_context(device)
     logg.info("Calculating %s's statistic for `%s` permutations on cuda:%d (rank %d/%d, features %d..%d)", mode, n_perms, ctx.device, rank, ws, lo, hi)
-    plan = AutocorrPlan(g, ctx)
-    try:
-        if hi > lo:
-            plan.load(mat if ws == 1 else mat[:, lo:hi], obs_major=True)
-            score_local = plan.score(mode)
-        else:
-            score_local = np.empty(0, np.float64)
-        score = all_gather_rows(score_local, n_feat)
-        score_perms = None
-        if n_perms is not None:
-            assert_positive(n_perms, name="n_perms")
-            generators = spawn_generators(shared_seed(seed), int(n_perms))
-            sp_local = np.empty((int(n_perms), hi - lo), dtype=np.float64)
-            batch = max(1, min(64, (256 << 20) // (8 * g.shape[0])))  # <= 256 MB of int64 permutations per device call
-            for p0 in range(0, int(n_perms), batch):
-                p1 = min(p0 + batch, int(n_perms))
-                idx = np.stack([generators[p].permutation(g.shape[0]) for p in range(p0, p1)])  # _score_helper, :258-280
-                if hi > lo:
-                    sp_local[p0:p1] = plan.score_perms(mode, idx)
-            score_perms = np.ascontiguousarray(all_gather_rows(np.ascontiguousarray(sp_local.T), n_feat).T)
-    finally:
-        plan.close()
+    with ctx.lock:
+        plan = AutocorrPlan(g, ctx)
+        try:
+            if hi > lo:
+                plan.load(mat, obs_major=True, cols=(lo, hi))
+                score_local = plan.score(mode)
+            else:
+                score_local = np.empty(0, np.float64)
+            score = all_gather_rows(score_local, n_feat)
+            score_perms = None
+            if n_perms is not None:
+                assert_positive(n_perms, name="n_perms")
+                generators = spawn_generators(shared_seed(seed), int(n_perms))
+                sp_local = np.empty((int(n_perms), hi - lo), dtype=np.float64)
+                batch = max(1, min(64, (256 << 20) // (8 * g.shape[0])))  # <= 256 MB of int64 permutations per device call
+                for p0 in range(0, int(n_perms), batch):
+                    p1 = min(p0 + batch, int(n_perms))
+                    idx = np.stack([generators[p].permutation(g.shape[0]) for p in range(p0, p1)])  # _score_helper, :258-280
+                    if hi > lo:
+                        sp_local[p0:p1] = plan.score_perms(mode, idx)
+                score_perms = np.ascontiguousarray(all_gather_rows(np.ascontiguousarray(sp_local.T), n_feat).T)
+        finally:
+            plan.close()
 
     with np.errstate(divide="ignore", invalid="ignore"):
         pval_results = _p_value_calc(score, score_perms, g, params)

@@ -3,47 +3,66 @@
 
 Permutation ``p`` (global index) of library segment ``s`` (``m`` observations, in ``np.where(libraries == c)[0]`` order
 like ``gr/_utils.py:208-209``) assigns to the observation at position ``r`` of the segment the label
-``sorted_labels_of_segment[pi(r)]`` where ``pi`` is a 4-round Feistel network on ``2k`` bits (``k = ceil(bits(m-1)/2)``,
-at least 1) with cycle walking, round keys ``philox_key(seed, p, s, round)``.
+``sorted_labels_of_segment[pi(r)]`` where ``pi`` is a 6-round generalised Feistel network (FE2) on
+``[0, a) x [0, b)``, ``a = ceil(sqrt(m))``, ``b = ceil(m / a)``, with cycle walking; round keys ``k0 + j*k1`` with
+``(k0, k1 | 1) = philox_key(seed, p, s, 0 / 1)``.
 TEST INFRASTRUCTURE: the CUDA kernel is checked bit-for-bit against this file.
 """
 
 from __future__ import annotations
+
+import math
 
 import numpy as np
 
 M64 = (1 << 64) - 1
 
 
-def philox_key(seed: int, perm: int, seg: int, rnd: int) -> int:
+def philox_key(seed: int, perm: int, seg: int, which: int) -> int:
     z = (seed + 0x9E3779B97F4A7C15 * (perm + 1)) & M64
-    z ^= ((seg * 4 + rnd + 1) * 0xD1B54A32D192ED03) & M64
+    z ^= ((seg * 2 + which + 1) * 0xD1B54A32D192ED03) & M64
     z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
     z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
     z ^= z >> 31
     return z >> 32
 
 
-def feistel_perm(m: int, keys: list[int]) -> np.ndarray:
+def _hash(v: np.ndarray) -> np.ndarray:
+    v = v * np.uint32(0x9E3779B1)
+    v ^= v >> np.uint32(15)
+    v *= np.uint32(0x85EBCA77)
+    return v
+
+
+def radices(m: int) -> tuple[int, int]:
+    a = math.isqrt(m)
+    if a * a < m:
+        a += 1
+    a = max(a, 1)
+    return a, max(1, -(-m // a))
+
+
+def feistel_perm(m: int, k0: int, k1: int) -> np.ndarray:
     """pi(r) for r in [0, m) (vectorised cycle walking)."""
     if m <= 1:
         return np.zeros(m, dtype=np.int64)
-    bits = int(m - 1).bit_length()
-    k = max(1, (bits + 1) // 2)
-    mask = np.uint32((1 << k) - 1)
+    a, b = radices(m)
     x = np.arange(m, dtype=np.uint32)
     todo = np.ones(m, dtype=bool)
+    k1 |= 1
     with np.errstate(over="ignore"):
         while todo.any():
             v = x[todo]
-            left, right = v >> np.uint32(k), v & mask
-            for key in keys:
-                t = (right ^ np.uint32(key)) * np.uint32(0x85EBCA6B)
-                t ^= t >> np.uint32(13)
-                t *= np.uint32(0xC2B2AE35)
-                t ^= t >> np.uint32(16)
-                left, right = right, left ^ (t & mask)
-            v = (left << np.uint32(k)) | right
+            left, right = v // np.uint32(b), v % np.uint32(b)
+            for j in range(6):
+                kj = np.uint32((k0 + j * k1) & 0xFFFFFFFF)
+                if j % 2 == 0:
+                    add = ((_hash(right ^ kj).astype(np.uint64) * np.uint64(a)) >> np.uint64(32)).astype(np.uint32)
+                    left = (left + add) % np.uint32(a)
+                else:
+                    add = ((_hash(left ^ kj).astype(np.uint64) * np.uint64(b)) >> np.uint64(32)).astype(np.uint32)
+                    right = (right + add) % np.uint32(b)
+            v = left * np.uint32(b) + right
             x[todo] = v
             todo[todo] = v >= m
     return x.astype(np.int64)
@@ -63,6 +82,6 @@ def philox_labels(base: np.ndarray, seed: int, perms, lib_codes=None, n_libs: in
             if idx.size == 0:
                 continue
             srt = np.sort(base[idx])
-            pi = feistel_perm(idx.size, [philox_key(seed, int(p), s, r) for r in range(4)])
+            pi = feistel_perm(idx.size, philox_key(seed, int(p), s, 0), philox_key(seed, int(p), s, 1))
             out[row, idx] = srt[pi]
     return out

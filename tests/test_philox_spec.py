@@ -11,8 +11,9 @@ from tests import philox_ref as pr
 
 @pytest.mark.parametrize("m", [1, 2, 3, 4, 5, 17, 64, 65, 1000, 4097, 70001])
 def test_feistel_is_a_bijection(m):
-    keys = [pr.philox_key(12345, 7, 0, r) for r in range(4)]
-    pi = pr.feistel_perm(m, keys)
+    pi = pr.feistel_perm(m, pr.philox_key(12345, 7, 0, 0), pr.philox_key(12345, 7, 0, 1))
+    a, b = pr.radices(m)
+    assert a * b >= m and (a - 1) * (a - 1) < m and a * b - m < a
     assert pi.shape == (m,) and np.array_equal(np.sort(pi), np.arange(m))
 
 
@@ -35,3 +36,22 @@ def test_first_order_uniformity():
     exp = np.array([50, 100, 150, 200]) / 500 * 2000
     chi = np.array([((np.bincount(lab[:, k], minlength=4) - exp) ** 2 / exp).sum() for k in range(40)])
     assert chi.mean() < 4.5 and chi.max() < 25  # 3 degrees of freedom: mean 3, P(chi2 > 25) ~ 1.5e-5
+
+
+def test_second_order_statistics_match_numpy_shuffle():
+    """Same-class neighbour pairs of a lattice under the bijection vs under numpy's shuffle (what nhood_enrichment
+    measures).  A 4-round network fails this (mean +3.5 %, std x2); the 6-round one must match."""
+    from tools import synth
+
+    g = synth.hex_graph(71, 71)
+    n = g.shape[0]
+    base = np.random.default_rng(0).integers(0, 10, n).astype(np.uint32)
+    rows, cols = np.repeat(np.arange(n), np.diff(g.indptr)), g.indices
+    P = 300
+    fast = pr.philox_labels(base, 42, range(P))
+    rng = np.random.default_rng(1)
+    d_fast = np.array([(lab[rows] == lab[cols]).sum() for lab in fast], dtype=np.float64)
+    d_np = np.array([(lab[rows] == lab[cols]).sum() for lab in (rng.permutation(base) for _ in range(P))], dtype=np.float64)
+    sd = d_np.std()
+    assert abs(d_fast.mean() - d_np.mean()) < 4 * sd * np.sqrt(2 / P)
+    assert abs(d_fast.std() - sd) / sd < 4 / np.sqrt(P)
