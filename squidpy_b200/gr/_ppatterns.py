@@ -265,12 +265,21 @@ def spatial_autocorr(
                 assert_positive(n_perms, name="n_perms")
                 generators = spawn_generators(shared_seed(seed), int(n_perms))
                 sp_local = np.empty((int(n_perms), hi - lo), dtype=np.float64)
-                batch = max(1, min(64, (256 << 20) // (8 * g.shape[0])))  # <= 256 MB of int64 permutations per device call
-                for p0 in range(0, int(n_perms), batch):
-                    p1 = min(p0 + batch, int(n_perms))
-                    idx = np.stack([generators[p].permutation(g.shape[0]) for p in range(p0, p1)])  # _score_helper, :258-280
-                    if hi > lo:
-                        sp_local[p0:p1] = plan.score_perms(mode, idx)
+                batch = max(1, min(32, (256 << 20) // (8 * g.shape[0])))  # <= 256 MB of int64 permutations per device call
+                from concurrent.futures import ThreadPoolExecutor
+
+                def draw(p0):  # idx_shuffle of _score_helper (:258-280) for one batch; numpy releases the GIL while it shuffles
+                    return np.stack([generators[p].permutation(g.shape[0]) for p in range(p0, min(p0 + batch, int(n_perms)))])
+
+                starts = list(range(0, int(n_perms), batch))
+                with ThreadPoolExecutor(max_workers=1) as pool:  # the next batch is drawn while the device scores this one
+                    nxt = pool.submit(draw, starts[0])
+                    for k, p0 in enumerate(starts):
+                        idx = nxt.result()
+                        if k + 1 < len(starts):
+                            nxt = pool.submit(draw, starts[k + 1])
+                        if hi > lo:
+                            sp_local[p0 : p0 + idx.shape[0]] = plan.score_perms(mode, idx)
                 score_perms = np.ascontiguousarray(all_gather_rows(np.ascontiguousarray(sp_local.T), n_feat).T)
         finally:
             plan.close()

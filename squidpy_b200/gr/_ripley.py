@@ -95,7 +95,10 @@ def ripley(
         # all simulations first (host RNG stream identical to the reference: one generator per simulation), then ONE
         # GPU launch counts pairs for the observed clusters and every simulated pattern
         groups = [coordinates[cluster_idx == i, :].astype(np.float64, copy=False) for i in range(int(np.max(cluster_idx)) + 1)]
-        sims_pts = [_ppp(hull, 1, n_observations, rng=sim_rngs[i]).reshape(-1, 2) for i in range(n_simulations)]
+        from scipy.spatial import Delaunay
+
+        deln = Delaunay(hull.points[hull.vertices])  # one triangulation of the hull for all simulations
+        sims_pts = [_ppp(hull, 1, n_observations, rng=sim_rngs[i], deln=deln).reshape(-1, 2) for i in range(n_simulations)]
         rank, ws = world()
         counts = pair_counts(groups + sims_pts, support, ctx=default_context(device), shard=(rank, ws))
         counts = all_reduce_sum(counts)
@@ -176,21 +179,44 @@ def _f_g_function(distances: np.ndarray, support: np.ndarray) -> tuple[np.ndarra
     return bins, np.concatenate((np.zeros((1,), dtype=float), fracs))
 
 
-def _ppp(hull, n_simulations: int, n_observations: int, rng: np.random.Generator) -> np.ndarray:
+def _ppp(hull, n_simulations: int, n_observations: int, rng: np.random.Generator, deln=None) -> np.ndarray:
     """Poisson point process on the convex hull by rejection from its bounding box (``_ripley.py:230-271``): one
-    ``rng.uniform`` draw for x then one for y per candidate, accepted if inside the hull — the draw order is part
-    of the result, so it is kept."""
+    ``rng.uniform`` draw for x then one for y per candidate, accepted if inside the hull.  The draw order is part of the
+    result.  The reference draws and tests one candidate at a time in Python; here candidates are drawn in blocks
+    (``low + (high - low) * rng.random()`` is ``rng.uniform(low, high)`` bit for bit), tested with one vectorised
+    ``find_simplex`` call, and the generator is then put back to the exact position the scalar loop would have reached
+    (PCG64 ``advance`` by two draws per consumed candidate), so both the points and every later draw are identical."""
     from scipy.spatial import Delaunay
 
     vxs = hull.points[hull.vertices]
-    deln = Delaunay(vxs)
+    if deln is None:
+        deln = Delaunay(vxs)
     bbox = np.array([*vxs.min(0), *vxs.max(0)])
+    wx, wy = bbox[2] - bbox[0], bbox[3] - bbox[1]
     result = np.empty((n_simulations, n_observations, 2))
+    exact_rewind = type(rng.bit_generator).__name__ == "PCG64"
     for i_sim in range(n_simulations):
-        i_obs = 0
-        while i_obs < n_observations:
-            x, y = rng.uniform(bbox[0], bbox[2]), rng.uniform(bbox[1], bbox[3])
-            if deln.find_simplex((x, y)) >= 0:
-                result[i_sim, i_obs] = (x, y)
-                i_obs += 1
+        if not exact_rewind:  # unknown bit generator: the reference's scalar loop
+            i_obs = 0
+            while i_obs < n_observations:
+                x, y = rng.uniform(bbox[0], bbox[2]), rng.uniform(bbox[1], bbox[3])
+                if deln.find_simplex((x, y)) >= 0:
+                    result[i_sim, i_obs] = (x, y)
+                    i_obs += 1
+            continue
+        got = 0
+        while got < n_observations:
+            k = max(64, int((n_observations - got) * 1.5) + 16)
+            state = rng.bit_generator.state
+            u = rng.random(2 * k)
+            pts = np.stack([bbox[0] + wx * u[0::2], bbox[1] + wy * u[1::2]], axis=1)
+            ok = np.flatnonzero(deln.find_simplex(pts) >= 0)
+            take = min(ok.size, n_observations - got)
+            result[i_sim, got : got + take] = pts[ok[:take]]
+            got += take
+            if got >= n_observations and take > 0:
+                used = int(ok[take - 1]) + 1  # candidates the scalar loop would have drawn in this block
+                if used < k:
+                    rng.bit_generator.state = state
+                    rng.bit_generator.advance(2 * used)
     return result.squeeze()

@@ -183,3 +183,32 @@ def test_spawn_states_fresh_entropy():
 
     a, b = spawn_states(None, 4), spawn_states(None, 4)
     assert a.shape == (4, 6) and not np.array_equal(a, b)  # seed=None draws OS entropy, like the reference
+
+
+def test_ppp_block_sampling_is_the_scalar_stream():
+    """``_ppp`` draws candidates in blocks; points AND the generator position afterwards must equal the reference's
+    one-candidate-at-a-time loop (``_ripley.py:255-269``)."""
+    from scipy.spatial import ConvexHull, Delaunay
+
+    from squidpy_b200.gr._ripley import _ppp
+
+    def scalar(hull, n_sim, n_obs, rng):
+        vxs = hull.points[hull.vertices]
+        deln = Delaunay(vxs)
+        bbox = np.array([*vxs.min(0), *vxs.max(0)])
+        out = np.empty((n_sim, n_obs, 2))
+        for i in range(n_sim):
+            k = 0
+            while k < n_obs:
+                x, y = rng.uniform(bbox[0], bbox[2]), rng.uniform(bbox[1], bbox[3])
+                if deln.find_simplex((x, y)) >= 0:
+                    out[i, k] = (x, y)
+                    k += 1
+        return out.squeeze()
+
+    pts = np.random.default_rng(0).normal(size=(400, 2)) * [3, 1] + [10, -4]
+    hull = ConvexHull(pts)
+    for n_obs in (1, 7, 100, 700):
+        a, b = np.random.default_rng(5), np.random.default_rng(5)
+        np.testing.assert_array_equal(scalar(hull, 2, n_obs, a), _ppp(hull, 2, n_obs, b))
+        assert a.random() == b.random()
