@@ -20,6 +20,8 @@
  *   sqb_autocorr_*             <- scanpy.metrics.morans_i / gearys_c call     src/squidpy/gr/_ppatterns.py:216,267-272
  *   sqb_cooc_counts            <- _occur_count(x, y, thresholds, labs, n,k,l) src/squidpy/gr/_ppatterns.py:283-310
  *   sqb_pair_counts_f64        <- KDTree.two_point_correlation(points, r)     src/squidpy/gr/_ripley.py:218-223
+ *   sqb_knn_2d / sqb_radius_2d <- NearestNeighbors.kneighbors / radius_neighbors src/squidpy/gr/neighbors.py:192-209,253-270,395-419
+ *   sqb_interaction_matrix     <- _interaction_matrix(data, indices, indptr, cats, out)  src/squidpy/gr/_nhood.py:412-429
  */
 #ifndef SQUIDPY_B200_H
 #define SQUIDPY_B200_H
@@ -200,6 +202,19 @@ int sqb_cooc_counts(sqb_ctx* ctx, const float* x, const float* y, int64_t n, con
  * i.e. sklearn KDTree.two_point_correlation(points_g, support).  support ascending.                        */
 int sqb_pair_counts_f64(sqb_ctx* ctx, const double* pts, const int64_t* group_ptr, int n_groups,
                         const double* support, int S, int shard_index, int shard_count, int64_t* out);
+
+/* ---- spatial neighbour graphs (what runs right before every hot-path call) ------------------------------------------
+ * Exact k nearest neighbours of every observation among the others (2-D float64 coordinates, interleaved x,y), the query
+ * itself excluded: NearestNeighbors(n_neighbors=k).fit(xy).kneighbors() of KNNBuilder.build_graph / GridBuilder._base_adjacency
+ * (src/squidpy/gr/neighbors.py:192-209, :395-419).  out_idx / out_dist: n x k, every row ordered by ASCENDING NEIGHBOUR INDEX
+ * (CSR-ready: indptr = k * arange(n + 1)); distances = sqrt(dx*dx + dy*dy) in float64 like sklearn's kd_tree.  Ties at the k-th
+ * distance go to the smaller index.  median_out (or NULL): np.median of the n*k distances (GridBuilder's cut = 1.3 x that).   */
+int sqb_knn_2d(sqb_ctx* ctx, const double* xy, int64_t n, int k, int32_t* out_idx, double* out_dist, double* median_out);
+/* All neighbours within `radius` (dx*dx + dy*dy <= radius*radius, self excluded): radius_neighbors() of RadiusBuilder.build_graph
+ * (neighbors.py:253-270).  Two calls: with out_idx == NULL only out_indptr (n + 1) and *nnz_out are produced; with buffers of
+ * `capacity` >= nnz entries the rows are filled in ascending column order.                                                 */
+int sqb_radius_2d(sqb_ctx* ctx, const double* xy, int64_t n, double radius, int64_t* out_indptr, int32_t* out_idx,
+                  double* out_dist, int64_t capacity, int64_t* nnz_out);
 
 #ifdef __cplusplus
 }

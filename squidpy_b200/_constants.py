@@ -40,6 +40,36 @@ class SpatialAutocorr(ModeEnum):
 
 
 @unique
+class Transform(Enum):
+    """Adjacency transforms of the graph builders (``_constants/_constants.py:33-36``); ``NONE`` carries the value ``None``."""
+
+    SPECTRAL = "spectral"
+    COSINE = "cosine"
+    NONE = None
+
+    @classmethod
+    def _missing_(cls, value):
+        raise ValueError(f"Invalid option `{value}` for `{cls.__name__}`. Valid options are: `{[m.value for m in cls]}`.")
+
+    @property
+    def s(self) -> str:
+        return str(self.value)
+
+    @property
+    def v(self):
+        return self.value
+
+    def __str__(self) -> str:
+        return str(self.value)
+
+
+@unique
+class CoordType(ModeEnum):
+    GRID = "grid"
+    GENERIC = "generic"
+
+
+@unique
 class RipleyStat(ModeEnum):
     F = "F"
     G = "G"
@@ -68,6 +98,10 @@ class Key:
             return cls._spatial_key(value, "connectivities")
 
     class uns:
+        @classmethod
+        def spatial_neighs(cls, value: str | None = None) -> str:
+            return f"{Key.obsm.spatial}_neighbors" if value is None else f"{value}_neighbors"
+
         @classmethod
         def nhood_enrichment(cls, cluster: str) -> str:
             return f"{cluster}_nhood_enrichment"

@@ -1,10 +1,21 @@
 """``squidpy_b200.gr`` — the spatial-statistics hot path of ``squidpy.gr`` on a B200."""
 
+from ._build import (GridBuilder, KNNBuilder, RadiusBuilder, SpatialNeighborsResult, knn_2d, radius_2d, spatial_neighbors_grid,
+                     spatial_neighbors_knn, spatial_neighbors_radius)
 from ._nhood import NhoodEnrichmentResult, NhoodPlan, interaction_matrix, nhood_enrichment
 from ._ppatterns import AutocorrPlan, co_occurrence, cooc_counts, spatial_autocorr
 from ._ripley import pair_counts, ripley
 
 __all__ = [
+    "spatial_neighbors_knn",
+    "spatial_neighbors_grid",
+    "spatial_neighbors_radius",
+    "SpatialNeighborsResult",
+    "KNNBuilder",
+    "GridBuilder",
+    "RadiusBuilder",
+    "knn_2d",
+    "radius_2d",
     "nhood_enrichment",
     "interaction_matrix",
     "spatial_autocorr",
