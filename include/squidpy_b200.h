@@ -20,6 +20,7 @@
  *   sqb_autocorr_*             <- scanpy.metrics.morans_i / gearys_c call     src/squidpy/gr/_ppatterns.py:216,267-272
  *   sqb_cooc_counts            <- _occur_count(x, y, thresholds, labs, n,k,l) src/squidpy/gr/_ppatterns.py:283-310
  *   sqb_pair_counts_f64        <- KDTree.two_point_correlation(points, r)     src/squidpy/gr/_ripley.py:218-223
+ *   sqb_ligrec_counts          <- _score_permutations(data, clustering, generators, ...)  src/squidpy/gr/_ligrec.py:616-676
  *   sqb_knn_2d / sqb_radius_2d <- NearestNeighbors.kneighbors / radius_neighbors src/squidpy/gr/neighbors.py:192-209,253-270,395-419
  *   sqb_interaction_matrix     <- _interaction_matrix(data, indices, indptr, cats, out)  src/squidpy/gr/_nhood.py:412-429
  */
@@ -153,6 +154,17 @@ int sqb_nhood_bytes_per_perm(sqb_nhood* h, int64_t* bytes);
 int sqb_interaction_matrix(sqb_ctx* ctx, int64_t n, int64_t nnz, const uint32_t* indptr, const uint32_t* indices,
                            const void* data, int data_dtype, const int32_t* codes, int n_cls, double* out_weighted,
                            int64_t* out_counts);
+
+/* ---- ligrec permutation test ------------------------------------------------------------------------------
+ * _score_permutations of the reference (src/squidpy/gr/_ligrec.py:616-676) for a handle whose base labels are the cells'
+ * cluster codes (sqb_nhood_set_base on a graph-less handle: nnz = 0) and whose numpy generator states are uploaded
+ * (sqb_nhood_permute_upload).  data: n x n_genes float64 row-major; inv_counts: n_cls; mean_obs: n_cls x n_genes;
+ * interactions: n_inter x 2 gene indices; inter_clusters: n_cpairs x 2 cluster indices; valid: n_inter x n_cpairs (uint8).
+ * out_counts[i, j] = #permutations with  mean_perm[a, g0] + mean_perm[b, g1] > mean_obs[a, g0] + mean_obs[b, g1]
+ * (int64; same float64 operation order as the reference, so the decisions are identical).                          */
+int sqb_ligrec_counts(sqb_nhood* h, const double* data, int64_t n_genes, const double* inv_counts, const double* mean_obs,
+                      const int32_t* interactions, int64_t n_inter, const int32_t* inter_clusters, int64_t n_cpairs,
+                      const uint8_t* valid, int64_t* out_counts);
 
 /* ---- spatial_autocorr (Moran's I / Geary's C) -------------------------------------------------------
  * W = obsp[connectivity_key] (after optional float32 row normalisation on the host) as CSR; w_dtype 0 = f32,

@@ -58,6 +58,8 @@ class _DocstringProcessor:
     def get_sections(self, **k):
         return lambda f: f
 
+    get_full_description = get_sections
+
 
 def load(morans_i=None, gearys_c=None, multipletests=None) -> dict[str, types.ModuleType]:
     """Import the reference hot-path modules.  ``morans_i``/``gearys_c`` (scanpy is not installed and its

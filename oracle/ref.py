@@ -284,3 +284,25 @@ def interaction_matrix(graph, codes, n_cats: int, weights: bool = False, normali
     if normalized:
         out = out / out.sum(axis=1).reshape((-1, 1))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# ligrec: src/squidpy/gr/_ligrec.py:616-676 (_score_permutations)
+# ---------------------------------------------------------------------------------------------------
+def ligrec_counts(data, clustering, n_cls, states, inv_counts, mean_obs, interactions, interaction_clusters, valid) -> np.ndarray:
+    """``_score_permutations`` restated with numpy: per permutation shuffle the cluster labels (exact numpy stream),
+    accumulate ``groups[cl, g] += data[cell, g]`` over the cells in ascending order (``np.add.at`` is unbuffered and
+    in-order, so the float64 sums are the reference's), scale by ``inv_counts`` and count ``shuf > obs``."""
+    data = np.asarray(data, np.float64)
+    labs = shuffle_labels(np.asarray(clustering, np.uint32), states)
+    rec, lig = interactions[:, 0], interactions[:, 1]
+    a, b = interaction_clusters[:, 0], interaction_clusters[:, 1]
+    obs = mean_obs[a][:, rec].T + mean_obs[b][:, lig].T
+    counts = np.zeros((interactions.shape[0], interaction_clusters.shape[0]), np.int64)
+    for p in range(labs.shape[0]):
+        groups = np.zeros((n_cls, data.shape[1]), np.float64)
+        np.add.at(groups, labs[p].astype(np.int64), data)
+        groups *= np.asarray(inv_counts)[:, None]
+        shuf = groups[a][:, rec].T + groups[b][:, lig].T
+        counts += ((shuf > obs) & valid).astype(np.int64)
+    return counts

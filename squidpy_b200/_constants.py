@@ -70,6 +70,18 @@ class CoordType(ModeEnum):
 
 
 @unique
+class CorrAxis(ModeEnum):
+    INTERACTIONS = "interactions"
+    CLUSTERS = "clusters"
+
+
+@unique
+class ComplexPolicy(ModeEnum):
+    MIN = "min"
+    ALL = "all"
+
+
+@unique
 class RipleyStat(ModeEnum):
     F = "F"
     G = "G"
@@ -101,6 +113,10 @@ class Key:
         @classmethod
         def spatial_neighs(cls, value: str | None = None) -> str:
             return f"{Key.obsm.spatial}_neighbors" if value is None else f"{value}_neighbors"
+
+        @classmethod
+        def ligrec(cls, cluster: str, value: str | None = None) -> str:
+            return f"{cluster}_ligrec" if value is None else value
 
         @classmethod
         def nhood_enrichment(cls, cluster: str) -> str:

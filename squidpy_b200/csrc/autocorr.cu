@@ -463,7 +463,8 @@ struct AcSparseParams {
     const double* wd;
     const double* csum;
     double s0;
-    const int32_t* perm;  // row permutation (PERM) or null
+    const int32_t* perm;  // PERM: n_perm row permutations [n_perm][n] (one feature pass serves all of them), else null
+    int n_perm;           // PERM: permutations per launch; outputs go to out[b * n_feat + g]
     double* aux;          // [5][n_feat]: mean, sum z^2 over stored, D, E, Geary column term (written by unpermuted runs)
     double* out;
     int* counter;  // dynamic feature queue
@@ -598,6 +599,10 @@ __global__ void __launch_bounds__(AC_T, 4) ac_sparse_kernel(const __grid_constan
         }
         // ---- phase 2: walk the rows of W of the stored observations; q[0], q[1] = slot accumulators ----
         // Moran: q[0] += z_i * w z_j, q[1] += w z_j;   Geary: q[0] += w ((x_i - x_j)^2 - [j stored] x_j^2)
+        // PERM: the bitmap of the feature is built once and walked once per row permutation of the batch
+        for (int pb = 0; pb < (PERM ? p.n_perm : 1); ++pb) {
+        const int32_t* __restrict__ perm = PERM ? p.perm + (int64_t)pb * p.n : nullptr;
+        if (PERM) q[0] = q[1] = 0.0;
         int nxt_i = -1;
         XT nxt_x = (XT)0;
         {
@@ -634,7 +639,7 @@ __global__ void __launch_bounds__(AC_T, 4) ac_sparse_kernel(const __grid_constan
                         rx[s] = (double)__shfl_sync(0xffffffffu, my_x, src);
                         rs[s] = make_uint2(0xffffffffu, 0u);
                         if (ri[s] >= 0) {
-                            const int64_t r = PERM ? (int64_t)__ldg(p.perm + ri[s]) : (int64_t)ri[s];
+                            const int64_t r = PERM ? (int64_t)__ldg(perm + ri[s]) : (int64_t)ri[s];
                             rs[s] = __ldg(p.rows + r * LPR + slot);
                         }
                     }
@@ -675,7 +680,7 @@ __global__ void __launch_bounds__(AC_T, 4) ac_sparse_kernel(const __grid_constan
 #pragma unroll
                     for (int s = 0; s < GRP; ++s) {
                         if (ri[s] < 0) continue;
-                        const int64_t r = PERM ? (int64_t)__ldg(p.perm + ri[s]) : (int64_t)ri[s];
+                        const int64_t r = PERM ? (int64_t)__ldg(perm + ri[s]) : (int64_t)ri[s];
                         const int rbeg = __ldg(p.wp + r), rend = __ldg(p.wp + r + 1);
                         const double zi = rx[s] - m;
                         for (int ew = rbeg + slot; ew < rend; ew += LPR) {
@@ -733,8 +738,10 @@ __global__ void __launch_bounds__(AC_T, 4) ac_sparse_kernel(const __grid_constan
                 const double num = q[0] + CX;
                 r = ((dn - 1.0) * num) / (2.0 * p.s0 * den);
             }
-            p.out[g] = r;
+            p.out[(int64_t)pb * p.n_feat + g] = r;
         }
+        if (PERM) __syncthreads();  // s_red is reused by the next permutation of the batch
+        }  // permutations of the batch
         for (int v = threadIdx.x; v < len4; v += AC_T) {
             const int4 iv = __ldg(reinterpret_cast<const int4*>(xi) + v);
             if (iv.x >= 0) S[iv.x >> 5] = make_uint2(0u, 0u);
@@ -836,7 +843,7 @@ static int ac_sparse_fmt(sqb_autocorr* h, const AcSparseParams& p) {
 }
 
 // one pass over all features; d_perm32 == nullptr: unpermuted (also refreshes the per-feature invariants)
-static int ac_run_sparse(sqb_autocorr* h, int mode, const int32_t* d_perm32, double* d_out) {
+static int ac_run_sparse(sqb_autocorr* h, int mode, const int32_t* d_perm32, double* d_out, int n_perm = 1) {
     AcSparseParams p;
     memset(&p, 0, sizeof(p));
     p.n = h->n;
@@ -853,6 +860,7 @@ static int ac_run_sparse(sqb_autocorr* h, int mode, const int32_t* d_perm32, dou
     p.csum = h->d_csum.p;
     p.s0 = h->s0;
     p.perm = d_perm32;
+    p.n_perm = n_perm;
     p.aux = h->d_aux.p;
     p.out = d_out;
     p.counter = h->d_flags.p + 1;
@@ -1389,13 +1397,18 @@ int sqb_autocorr_run_perms(sqb_autocorr* h, int mode, const int64_t* row_perms, 
     sqb_ctx* c = h->ctx;
     SQB_CUDA(cudaSetDevice(c->device));
     const int64_t G = h->n_feat;
-    // permutations are staged in batches of <= 64 (8 bytes + 4 bytes + 1 bit per entry on the device)
-    const int64_t batch = n_perms < 64 ? n_perms : 64;
+    // permutations are staged in batches of <= 32 (8 bytes + 4 bytes + 1 bit per entry on the device)
+    const int64_t batch = n_perms < 32 ? n_perms : 32;
     SQB_TRY(h->d_out_perms.alloc((size_t)(batch * G)));
     for (int64_t p0 = 0; p0 < n_perms; p0 += batch) {
         const int64_t pb = n_perms - p0 < batch ? n_perms - p0 : batch;
         SQB_TRY(ac_upload_perms(h, row_perms + p0 * h->n, pb));
-        for (int64_t k = 0; k < pb; ++k) SQB_TRY(ac_run_one(h, mode, k, h->d_out_perms.p + k * G));
+        if (h->kind == 3) {  // sparse X: one launch scores the whole batch (the feature's bitmap is built once per batch)
+            if (!h->aux_valid) SQB_TRY(ac_run_sparse(h, mode, nullptr, h->d_out.p));
+            SQB_TRY(ac_run_sparse(h, mode, h->d_perm32.p, h->d_out_perms.p, (int)pb));
+        } else {
+            for (int64_t k = 0; k < pb; ++k) SQB_TRY(ac_run_one(h, mode, k, h->d_out_perms.p + k * G));
+        }
         SQB_CUDA(cudaMemcpyAsync(out + p0 * G, h->d_out_perms.p, (size_t)(pb * G) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         SQB_TRY(ac_check_flags(h, "sqb_autocorr_run_perms"));  // synchronises
     }

@@ -3515,6 +3515,147 @@ int sqb_nhood_permute_var_chain_dev(sqb_nhood* h, const double* d_mean, const do
     return SQB_OK;
 }
 
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// 6. ligrec permutation test (src/squidpy/gr/_ligrec.py:616-676 `_score_permutations`): per permutation the cluster labels
+//    are shuffled with the SAME exact numpy-stream replay as above (numba's Generator.shuffle is numpy's), the per-cluster
+//    mean expression of every gene is re-formed and every (interaction, cluster pair) whose shuffled score exceeds the
+//    observed one counts one.  The reference accumulates groups[cl, g] += data[cell, g] over the cells in ascending order in
+//    float64 and then multiplies by 1/size: the kernel keeps exactly that order (one lane owns one gene, the cells are walked
+//    sequentially, accumulators [cluster][lane] in shared memory with bank == lane), so the scores and hence the `>`
+//    decisions are bit-identical.
+// ------------------------------------------------------------------------------------------------
+template <typename LT>
+__global__ void __launch_bounds__(128) ligrec_group_means_kernel(const LT* __restrict__ lab, int64_t stride,
+                                                                 const double* __restrict__ data, int64_t n_cells, int n_genes,
+                                                                 int n_cls, const double* __restrict__ inv_counts,
+                                                                 double* __restrict__ G) {
+    extern __shared__ double lg_acc[];  // [4 warps][n_cls][32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t p = blockIdx.y;
+    const int g = (blockIdx.x * 4 + warp) * 32 + lane;
+    double* __restrict__ acc = lg_acc + (size_t)warp * n_cls * 32 + lane;
+    for (int k = 0; k < n_cls; ++k) acc[k * 32] = 0.0;
+    const LT* __restrict__ row = lab + p * stride;
+    const bool ok = g < n_genes;
+    const double* __restrict__ col = data + (ok ? g : 0);
+    int64_t c = 0;
+    for (; c + 4 <= n_cells; c += 4) {
+        const int l0 = (int)row[c], l1 = (int)row[c + 1], l2 = (int)row[c + 2], l3 = (int)row[c + 3];
+        const double v0 = col[c * n_genes], v1 = col[(c + 1) * n_genes], v2 = col[(c + 2) * n_genes], v3 = col[(c + 3) * n_genes];
+        acc[l0 * 32] = __dadd_rn(acc[l0 * 32], v0);
+        acc[l1 * 32] = __dadd_rn(acc[l1 * 32], v1);
+        acc[l2 * 32] = __dadd_rn(acc[l2 * 32], v2);
+        acc[l3 * 32] = __dadd_rn(acc[l3 * 32], v3);
+    }
+    for (; c < n_cells; ++c) {
+        const int l0 = (int)row[c];
+        acc[l0 * 32] = __dadd_rn(acc[l0 * 32], col[c * n_genes]);
+    }
+    if (ok)
+        for (int k = 0; k < n_cls; ++k) G[((size_t)p * n_cls + k) * n_genes + g] = __dmul_rn(acc[k * 32], inv_counts[k]);
+}
+
+__global__ void ligrec_compare_kernel(const double* __restrict__ G, int64_t np, int n_cls, int n_genes,
+                                      const double* __restrict__ mean_obs, const int32_t* __restrict__ inter, int64_t n_inter,
+                                      const int32_t* __restrict__ cpairs, int64_t n_cpairs, const uint8_t* __restrict__ valid,
+                                      long long* __restrict__ counts) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_inter * n_cpairs || !valid[t]) return;
+    const int64_t i = t / n_cpairs, j = t % n_cpairs;
+    const int rec = inter[2 * i], lig = inter[2 * i + 1], a = cpairs[2 * j], b = cpairs[2 * j + 1];
+    const double obs = __dadd_rn(mean_obs[(size_t)a * n_genes + rec], mean_obs[(size_t)b * n_genes + lig]);
+    const size_t oa = (size_t)a * n_genes + rec, ob = (size_t)b * n_genes + lig, per = (size_t)n_cls * n_genes;
+    long long cnt = 0;
+    for (int64_t p = 0; p < np; ++p) cnt += __dadd_rn(G[p * per + oa], G[p * per + ob]) > obs ? 1 : 0;
+    counts[t] += cnt;
+}
+
+extern "C" {
+
+int sqb_ligrec_counts(sqb_nhood* h, const double* data, int64_t n_genes, const double* inv_counts, const double* mean_obs,
+                      const int32_t* interactions, int64_t n_inter, const int32_t* inter_clusters, int64_t n_cpairs,
+                      const uint8_t* valid, int64_t* out_counts) {
+    SQB_CHECK(h && data && inv_counts && mean_obs && interactions && inter_clusters && valid && out_counts, SQB_ERR_INVALID,
+              "sqb_ligrec_counts: null argument");
+    SQB_CHECK(h->uploaded && h->rng_mode == 0, SQB_ERR_STATE, "sqb_ligrec_counts: upload numpy generator states first (sqb_nhood_permute_upload)");
+    SQB_CHECK(!h->has_order, SQB_ERR_UNSUPPORTED, "sqb_ligrec_counts: library partitions are not part of the ligrec test");
+    SQB_CHECK(n_genes >= 1 && n_genes < 2147483647LL && n_inter >= 1 && n_cpairs >= 1, SQB_ERR_INVALID, "sqb_ligrec_counts: bad sizes");
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    const int C = h->n_cls;
+    const size_t smem = (size_t)4 * C * 32 * sizeof(double);
+    SQB_CHECK(smem <= c->smem_optin, SQB_ERR_UNSUPPORTED, "sqb_ligrec_counts: %d clusters exceed the shared-memory accumulators", C);
+    for (int64_t i = 0; i < n_inter * 2; ++i)
+        SQB_CHECK(interactions[i] >= 0 && interactions[i] < n_genes, SQB_ERR_INVALID, "sqb_ligrec_counts: gene index %d out of range", interactions[i]);
+    for (int64_t i = 0; i < n_cpairs * 2; ++i)
+        SQB_CHECK(inter_clusters[i] >= 0 && inter_clusters[i] < C, SQB_ERR_INVALID, "sqb_ligrec_counts: cluster index %d out of range", inter_clusters[i]);
+    const int64_t n = h->n, NT = n_inter * n_cpairs;
+    // permutations per pass: the shuffled label rows (upload chunk) and the [perm][cluster][gene] means (<= 1 GB)
+    int64_t chunk = h->chunk;
+    const int64_t gcap = ((int64_t)1 << 30) / ((int64_t)C * n_genes * 8);
+    if (chunk > gcap) chunk = gcap < 1 ? 1 : gcap;
+    DevBuf<double> d_data, d_inv, d_obs, d_G;
+    DevBuf<int32_t> d_inter, d_cp;
+    DevBuf<uint8_t> d_valid;
+    DevBuf<long long> d_cnt;
+    auto cleanup = [&]() {
+        d_data.release(), d_inv.release(), d_obs.release(), d_G.release(), d_inter.release(), d_cp.release(), d_valid.release(), d_cnt.release();
+    };
+    int rc;
+    if ((rc = d_data.alloc((size_t)n * n_genes)) || (rc = d_inv.alloc(C)) || (rc = d_obs.alloc((size_t)C * n_genes)) ||
+        (rc = d_G.alloc((size_t)chunk * C * n_genes)) || (rc = d_inter.alloc(2 * n_inter)) || (rc = d_cp.alloc(2 * n_cpairs)) ||
+        (rc = d_valid.alloc(NT)) || (rc = d_cnt.alloc(NT)) || (rc = ensure_buffers(h, h->chunk))) {
+        cleanup();
+        return rc;
+    }
+    cudaError_t e = cudaMemsetAsync(d_cnt.p, 0, NT * sizeof(long long), c->stream);
+    if (e == cudaSuccess && sqb_h2d(c, d_data.p, data, (size_t)n * n_genes * sizeof(double)) != SQB_OK) e = cudaErrorUnknown;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_inv.p, inv_counts, C * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_obs.p, mean_obs, (size_t)C * n_genes * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_inter.p, interactions, 2 * n_inter * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_cp.p, inter_clusters, 2 * n_cpairs * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_valid.p, valid, NT, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(ligrec_group_means_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ligrec_group_means_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    for (int64_t p0 = 0; p0 < h->n_perms && e == cudaSuccess; p0 += chunk) {
+        const int64_t np = h->n_perms - p0 < chunk ? h->n_perms - p0 : chunk;
+        rc = h->lt_bytes == 1 ? run_chunk<uint8_t>(h, p0, np, false) : run_chunk<uint16_t>(h, p0, np, false);
+        if (rc != SQB_OK) {
+            cudaStreamSynchronize(c->stream);
+            cleanup();
+            return rc;
+        }
+        {
+            SqbLaunchScope scope(c, SQB_K_MISC);
+            dim3 grid((unsigned)ceil_div64(n_genes, 128), (unsigned)np);
+            if (h->lt_bytes == 1)
+                ligrec_group_means_kernel<uint8_t><<<grid, 128, smem, c->stream>>>(c->scratch[0].p, h->stride, d_data.p, n, (int)n_genes, C, d_inv.p, d_G.p);
+            else
+                ligrec_group_means_kernel<uint16_t><<<grid, 128, smem, c->stream>>>(reinterpret_cast<const uint16_t*>(c->scratch[0].p), h->stride,
+                                                                                     d_data.p, n, (int)n_genes, C, d_inv.p, d_G.p);
+        }
+        {
+            SqbLaunchScope scope(c, SQB_K_MISC);
+            ligrec_compare_kernel<<<(unsigned)ceil_div64(NT, 256), 256, 0, c->stream>>>(d_G.p, np, C, (int)n_genes, d_obs.p, d_inter.p, n_inter, d_cp.p,
+                                                                                        n_cpairs, d_valid.p, d_cnt.p);
+        }
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_counts, d_cnt.p, NT * sizeof(long long), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    else cudaStreamSynchronize(c->stream);
+    cleanup();
+    if (e != cudaSuccess) {
+        sqb_set_error("sqb_ligrec_counts: %s", cudaGetErrorString(e));
+        return SQB_ERR_CUDA;
+    }
+    return SQB_OK;
+}
+
 int sqb_nhood_permute(sqb_nhood* h, const uint64_t* states, int64_t n_perms, uint32_t* out_counts) {
     SQB_TRY(sqb_nhood_permute_upload(h, states, n_perms));
     SQB_TRY(sqb_nhood_permute_run_async(h));

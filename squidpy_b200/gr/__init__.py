@@ -2,6 +2,7 @@
 
 from ._build import (GridBuilder, KNNBuilder, RadiusBuilder, SpatialNeighborsResult, knn_2d, radius_2d, spatial_neighbors_grid,
                      spatial_neighbors_knn, spatial_neighbors_radius)
+from ._ligrec import ligrec, ligrec_analysis
 from ._nhood import NhoodEnrichmentResult, NhoodPlan, interaction_matrix, nhood_enrichment
 from ._ppatterns import AutocorrPlan, co_occurrence, cooc_counts, spatial_autocorr
 from ._ripley import pair_counts, ripley
@@ -16,6 +17,8 @@ __all__ = [
     "RadiusBuilder",
     "knn_2d",
     "radius_2d",
+    "ligrec",
+    "ligrec_analysis",
     "nhood_enrichment",
     "interaction_matrix",
     "spatial_autocorr",

@@ -107,8 +107,11 @@ def _transform_spectral(a: csr_matrix) -> csr_matrix:
 
 
 def _apply_transform(adj: csr_matrix, dst: csr_matrix, transform: Transform) -> tuple[csr_matrix, csr_matrix]:
-    adj.eliminate_zeros()
-    dst.eliminate_zeros()
+    # eliminate_zeros() of the reference (neighbors.py:463-464); a full pass only when there is something to drop
+    if np.count_nonzero(adj.data) != adj.data.size:
+        adj.eliminate_zeros()
+    if np.count_nonzero(dst.data) != dst.data.size:
+        dst.eliminate_zeros()
     if transform == Transform.SPECTRAL:
         return _transform_spectral(adj), dst
     if transform == Transform.COSINE:
@@ -192,8 +195,10 @@ class KNNBuilder(_Builder):
         n = idx.shape[0]
         adj = _csr_from_rows(n, self.n_neighs, idx, np.ones(idx.shape, dtype=np.float32))
         dst = _csr_from_rows(n, self.n_neighs, idx, dist)
-        adj.setdiag(1.0 if self.set_diag else adj.diagonal())
-        dst.setdiag(0.0)
+        # neighbors.py:206-208: `adj.setdiag(1.0 if set_diag else adj.diagonal())`, `dst.setdiag(0.0)` — the search never returns
+        # the query itself, so both are no-ops unless set_diag
+        if self.set_diag:
+            adj.setdiag(1.0)
         return adj, dst
 
 
@@ -218,8 +223,8 @@ class RadiusBuilder(_Builder):
         adj = csr_matrix((np.ones(idx.size, dtype=np.float32), idx, ip), shape=(n, n))
         dst = csr_matrix((dist, idx.copy(), ip.copy()), shape=(n, n))
         adj.has_sorted_indices = dst.has_sorted_indices = True
-        adj.setdiag(1.0 if self.set_diag else adj.diagonal())
-        dst.setdiag(0.0)
+        if self.set_diag:  # no stored diagonal otherwise (neighbors.py:267-269 are no-ops then)
+            adj.setdiag(1.0)
         return adj, dst
 
 
@@ -243,7 +248,8 @@ class GridBuilder(_Builder):
         dist, idx, med = knn_2d(coords, self.n_neighs, median=True, ctx=self.ctx)
         keep = dist < med * 1.3  # neighbors.py:408-409
         adj = _csr_from_rows(idx.shape[0], self.n_neighs, idx, np.ones(idx.shape, dtype=np.float32), keep)
-        adj.setdiag(1.0 if set_diag else adj.diagonal())
+        if set_diag:
+            adj.setdiag(1.0)
         return adj
 
     def build_graph(self, coords):
@@ -264,7 +270,8 @@ class GridBuilder(_Builder):
         else:
             adj = self._base_adjacency(coords, set_diag=self.set_diag)
             dst = adj.copy()
-        dst.setdiag(0.0)
+        if self.set_diag or self.n_rings > 1:
+            dst.setdiag(0.0)
         return adj, dst
 
 

@@ -125,3 +125,20 @@ def test_rng_replay_vs_numpy():
     st = ref.spawn_states(5, 1)[0]
     gen = np.random.default_rng(np.random.SeedSequence(5).spawn(1)[0])
     np.testing.assert_array_equal(ref.permutation(st, 1234), gen.permutation(1234))
+
+
+def test_ligrec_restatement_matches_reference_golden():
+    """oracle.ref.ligrec_counts (numpy) against p-values produced by the reference's own _analysis (tests/golden/ligrec.npz)."""
+    import os
+
+    from tests.golden.make_golden_ligrec import CASES, frame, make_case
+
+    gold = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "ligrec.npz"), allow_pickle=False))
+    for name, (seed, n_cells, n_genes, n_cls, kind, thr, n_perms, pseed) in CASES.items():
+        x, cl, inter, cpairs = make_case(seed, n_cells, n_genes, n_cls, kind)
+        g = frame(x, cl, n_cls).groupby("clusters", observed=True)
+        mean_obs = g.mean().values
+        inv = 1.0 / np.maximum(g.size().values.astype(np.float64), 1)
+        valid = ~np.isnan(gold[f"{name}_pvalues"])
+        counts = ref.ligrec_counts(x, cl, n_cls, ref.spawn_states(pseed, n_perms), inv, mean_obs, inter, cpairs, valid)
+        np.testing.assert_array_equal(counts[valid] / n_perms, gold[f"{name}_pvalues"][valid])
