@@ -21,6 +21,7 @@
  *   sqb_cooc_counts            <- _occur_count(x, y, thresholds, labs, n,k,l) src/squidpy/gr/_ppatterns.py:283-310
  *   sqb_pair_counts_f64        <- KDTree.two_point_correlation(points, r)     src/squidpy/gr/_ripley.py:218-223
  *   sqb_ligrec_counts          <- _score_permutations(data, clustering, generators, ...)  src/squidpy/gr/_ligrec.py:616-676
+ *   sqb_sepal                  <- _diffusion(conc, use_hex, n_iter, sat, sat_idx, unsat, unsat_idx, dt, thresh)  src/squidpy/gr/_sepal.py:186-233
  *   sqb_knn_2d / sqb_radius_2d <- NearestNeighbors.kneighbors / radius_neighbors src/squidpy/gr/neighbors.py:192-209,253-270,395-419
  *   sqb_interaction_matrix     <- _interaction_matrix(data, indices, indptr, cats, out)  src/squidpy/gr/_nhood.py:412-429
  */
@@ -214,6 +215,15 @@ int sqb_cooc_counts(sqb_ctx* ctx, const float* x, const float* y, int64_t n, con
  * i.e. sklearn KDTree.two_point_correlation(points_g, support).  support ascending.                        */
 int sqb_pair_counts_f64(sqb_ctx* ctx, const double* pts, const int64_t* group_ptr, int n_groups,
                         const double* support, int S, int shard_index, int shard_count, int64_t* out);
+
+/* ---- sepal ---------------------------------------------------------------------------------------------------------
+ * `_diffusion` for every gene (src/squidpy/gr/_sepal.py:186-289): vals = n_genes x n float64 (one row per gene), sat / unsat =
+ * saturated / unsaturated node ids, sat_idx = n_sat x max_neighs neighbour ids, unsat_idx = nearest saturated node of every
+ * unsaturated node (`_compute_idxs`, :292-306).  out[g] = dt * (first iteration whose entropy change is <= thresh), NaN if
+ * n_iter iterations do not converge.                                                                                  */
+int sqb_sepal(sqb_ctx* ctx, const double* vals, int64_t n_genes, int64_t n, const int32_t* sat, int64_t n_sat,
+              const int32_t* sat_idx, int max_neighs, const int32_t* unsat, const int32_t* unsat_idx, int64_t n_unsat,
+              int n_iter, double dt, double thresh, double* out);
 
 /* ---- spatial neighbour graphs (what runs right before every hot-path call) ------------------------------------------
  * Exact k nearest neighbours of every observation among the others (2-D float64 coordinates, interleaved x,y), the query

@@ -6,6 +6,7 @@ from ._ligrec import ligrec, ligrec_analysis
 from ._nhood import NhoodEnrichmentResult, NhoodPlan, interaction_matrix, nhood_enrichment
 from ._ppatterns import AutocorrPlan, co_occurrence, cooc_counts, spatial_autocorr
 from ._ripley import pair_counts, ripley
+from ._sepal import sepal, sepal_scores
 
 __all__ = [
     "spatial_neighbors_knn",
@@ -18,6 +19,8 @@ __all__ = [
     "knn_2d",
     "radius_2d",
     "ligrec",
+    "sepal",
+    "sepal_scores",
     "ligrec_analysis",
     "nhood_enrichment",
     "interaction_matrix",

@@ -139,6 +139,15 @@ class _Builder:
     def _interval(self):
         return None
 
+    def _diagonals(self, adj: csr_matrix, dst: csr_matrix) -> None:
+        """``adj.setdiag(1.0 if set_diag else adj.diagonal()); dst.setdiag(0.0)`` (neighbors.py:206-208, :267-269).  scipy stores
+        the diagonal it is given EXPLICITLY (also zeros), and the percentile / interval post-processors look at ``.data`` before
+        ``eliminate_zeros`` runs, so those cases replay the calls literally; otherwise the explicit zeros would only be
+        inserted to be removed again (the searches never return the query itself) and are skipped."""
+        if self.set_diag or self.percentile is not None or self._interval() is not None:
+            adj.setdiag(1.0 if self.set_diag else adj.diagonal())
+            dst.setdiag(0.0)
+
     def build(self, coords) -> tuple[csr_matrix, csr_matrix]:
         import warnings
 
@@ -195,10 +204,7 @@ class KNNBuilder(_Builder):
         n = idx.shape[0]
         adj = _csr_from_rows(n, self.n_neighs, idx, np.ones(idx.shape, dtype=np.float32))
         dst = _csr_from_rows(n, self.n_neighs, idx, dist)
-        # neighbors.py:206-208: `adj.setdiag(1.0 if set_diag else adj.diagonal())`, `dst.setdiag(0.0)` — the search never returns
-        # the query itself, so both are no-ops unless set_diag
-        if self.set_diag:
-            adj.setdiag(1.0)
+        self._diagonals(adj, dst)
         return adj, dst
 
 
@@ -223,8 +229,7 @@ class RadiusBuilder(_Builder):
         adj = csr_matrix((np.ones(idx.size, dtype=np.float32), idx, ip), shape=(n, n))
         dst = csr_matrix((dist, idx.copy(), ip.copy()), shape=(n, n))
         adj.has_sorted_indices = dst.has_sorted_indices = True
-        if self.set_diag:  # no stored diagonal otherwise (neighbors.py:267-269 are no-ops then)
-            adj.setdiag(1.0)
+        self._diagonals(adj, dst)
         return adj, dst
 
 

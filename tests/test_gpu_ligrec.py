@@ -57,7 +57,8 @@ def test_public_api_frames():
     res = sq.gr.ligrec(ad, "cl", interactions=inter, use_raw=False, n_perms=50, seed=1, copy=True, threshold=0.0)
     assert set(res) == {"means", "pvalues", "metadata"}
     assert res["means"].shape == res["pvalues"].shape == (4, 9)  # the interaction with the unknown gene 'ZZ' is dropped
-    assert list(res["means"].index.names) == ["source", "target"] and list(res["means"].columns.names) == ["cluster_1", "cluster_2"]
+    assert list(res["means"].index.names) == ["source", "target"] and res["means"].columns.nlevels == 2
+    assert ("x", "y") in res["means"].columns and ("A", "B") in res["means"].index
     pv = res["pvalues"].to_numpy(dtype=float)
     assert np.nanmin(pv) >= 0.0 and np.nanmax(pv) <= 1.0
     again = sq.gr.ligrec(ad, "cl", interactions=inter, use_raw=False, n_perms=50, seed=1, copy=True, threshold=0.0)
