@@ -306,3 +306,31 @@ def ligrec_counts(data, clustering, n_cls, states, inv_counts, mean_obs, interac
         shuf = groups[a][:, rec].T + groups[b][:, lig].T
         counts += ((shuf > obs) & valid).astype(np.int64)
     return counts
+
+
+# ---------------------------------------------------------------------------------------------------
+# sepal: src/squidpy/gr/_sepal.py:236-289 (_diffusion)
+# ---------------------------------------------------------------------------------------------------
+def sepal_score(conc, use_hex, n_iter, sat, sat_idx, unsat, unsat_idx, dt=0.001, thresh=1e-8) -> float:
+    """``_diffusion`` restated with numpy (float64, no fastmath): dt * first iteration whose entropy change is <= thresh."""
+    conc = np.array(conc, dtype=np.float64)
+    eps = np.finfo(np.float64).eps
+    prev = 1.0
+    for i in range(n_iter):
+        nhood = conc[sat_idx].sum(axis=1)
+        c = conc[sat]
+        d2 = (2.0 * nhood - 12.0 * c) / 3.0 if use_hex else nhood - 4.0 * c
+        dcdt = np.zeros_like(conc)
+        dcdt[sat] = d2
+        conc[sat] += dcdt[sat] * dt
+        conc[unsat] += dcdt[unsat_idx] * dt
+        conc[conc < 0] = 0
+        x = conc[sat]
+        x = x[x > 0]
+        s = x.sum()
+        ent = 0.0 if s < eps else float((-np.log(np.maximum(x / s, eps)) * (x / s)).sum())
+        ent /= sat.shape[0]
+        if abs(ent - prev) <= thresh:
+            return dt * i
+        prev = ent
+    return float("nan")

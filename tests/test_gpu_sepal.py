@@ -57,15 +57,18 @@ def test_api_and_errors():
 
 
 def test_large_lattice_uses_global_scratch():
-    """160 x 160 spots: 2 x 8 B x 25 600 no longer fits shared memory; scores must equal the shared-memory path's on a crop-free
-    comparison of two identical runs and be finite for a smooth gene."""
+    """160 x 160 spots: 2 x 8 B x 25 600 no longer fits shared memory -> per-CTA global scratch; checked against the numpy
+    restatement of the diffusion loop (oracle.ref.sepal_score)."""
+    from oracle import ref
     from tools import synth
 
     g, co = synth.hex_graph(160, 160), synth.hex_coords(160, 160)
-    xy = (co - co.min(0)) / np.ptp(co, axis=0)
-    vals = np.stack([np.exp(-((xy[:, 0] - 0.5) ** 2 + (xy[:, 1] - 0.4) ** 2) / 0.02), np.random.default_rng(0).random(len(xy))], axis=1)
+    rng = np.random.default_rng(0)
+    vals = np.stack([rng.random(len(co)) * (1 + q) + (q == 2) * rng.poisson(0.2, len(co)) for q in range(3)], axis=1)
     sat, sat_idx, unsat, unsat_idx = _compute_idxs(g, co, 6)
-    a = sepal_scores(vals, sat, sat_idx, unsat, unsat_idx, max_neighs=6, n_iter=4000)
-    b = sepal_scores(vals, sat, sat_idx, unsat, unsat_idx, max_neighs=6, n_iter=4000)
-    np.testing.assert_array_equal(a, b)
-    assert np.isfinite(a[1]) and (np.isnan(a[0]) or a[0] > a[1])  # noise diffuses to equilibrium faster than structure
+    a = sepal_scores(vals, sat, sat_idx, unsat, unsat_idx, max_neighs=6, n_iter=1500)
+    np.testing.assert_array_equal(a, sepal_scores(vals, sat, sat_idx, unsat, unsat_idx, max_neighs=6, n_iter=1500))
+    exp = np.array([ref.sepal_score(vals[:, q], True, 1500, sat, sat_idx, unsat, unsat_idx) for q in range(3)])
+    assert np.array_equal(np.isnan(a), np.isnan(exp)) and np.isfinite(exp).any()
+    ok = np.isfinite(exp)
+    assert (np.abs(a[ok] - exp[ok]) / DT <= 2.5).all()

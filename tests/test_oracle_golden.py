@@ -142,3 +142,20 @@ def test_ligrec_restatement_matches_reference_golden():
         valid = ~np.isnan(gold[f"{name}_pvalues"])
         counts = ref.ligrec_counts(x, cl, n_cls, ref.spawn_states(pseed, n_perms), inv, mean_obs, inter, cpairs, valid)
         np.testing.assert_array_equal(counts[valid] / n_perms, gold[f"{name}_pvalues"][valid])
+
+
+def test_sepal_restatement_matches_reference_golden():
+    """oracle.ref.sepal_score (numpy, no fastmath) against scores of the reference's numba kernel (tests/golden/sepal.npz)."""
+    import os
+
+    from squidpy_b200.gr._sepal import _compute_idxs
+    from tests.golden.make_golden_sepal import make_case
+
+    gold = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "sepal.npz"), allow_pickle=False))
+    g, co, k, vals = make_case("square")
+    sat, si, un, ui = _compute_idxs(g, co, k)
+    np.testing.assert_array_equal(si, gold["square_sat_idx"])
+    np.testing.assert_array_equal(ui, gold["square_unsat_idx"])
+    for q in (10, 11, 13, 14, 15):  # the quickly converging genes (the loop is interpreted)
+        got = ref.sepal_score(vals[:, q], False, 30000, sat, si, un, ui)
+        assert abs(got - gold["square_score"][q]) <= 2.5e-3, (q, got, gold["square_score"][q])
