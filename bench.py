@@ -596,6 +596,41 @@ def main():
         t_f, _ = time_api("philox")
         fast["e2e"] = {"value": ws * P / t_f, "unit": "permutations/s", "seconds_per_call": t_f, "h2d_bytes_per_step": int(h2d - states.nbytes), "d2h_bytes_per_step": d2h}
 
+    # ---- configs[4] nhood part: 300 000 MERFISH-shaped cells, kNN(6) graph (built on the GPU), n_perms = 10 000 IN TOTAL,
+    # sharded over the ranks (strong scaling; 1 250 permutations per GPU at N = 8)
+    cfg5 = None
+    try:
+        from squidpy_b200.gr import KNNBuilder
+
+        P5 = 10000
+        pts5 = synth.thomas_points(300_000, seed=5)
+        lab5 = synth.dirichlet_labels(300_000, 12, seed=5).cat.codes.to_numpy().astype(np.uint32)
+        t0 = time.perf_counter()
+        adj5, _ = KNNBuilder(n_neighs=6, ctx=ctx).build(pts5)
+        t_graph = time.perf_counter() - t0
+        lo5, hi5 = rank * -(-P5 // ws), min(P5, (rank + 1) * -(-P5 // ws))
+        plan5 = NhoodPlan(adj5.indptr, adj5.indices, 12, ctx)
+        plan5.set_base(lab5)
+        plan5.upload(spawn_states(CFG2["seed"], P5, lo5, hi5))
+
+        def step5():
+            plan5.run_async()
+            if ws == 1:
+                plan5.stats_dev(stat5[0].data_ptr(), stat5[1].data_ptr())
+            else:
+                sequential_stats_device(plan5, P5, True)
+
+        stat5 = torch.empty((2, 144), dtype=torch.float64, device="cuda")
+        step5()
+        ms5 = _timed_steps(step5, max(1, min(args.steps, 3)), flush, ws)
+        cfg5 = {"metric": "nhood_enrichment permutations/s (configs[4]: 300k cells, 12 clusters, kNN k=6 directed graph, n_perms=10000 in total)",
+                "value": P5 / (ms5 / 1e3), "unit": "permutations/s", "ms_per_step": ms5, "scaling": "strong", "perms_per_rank": hi5 - lo5,
+                "graph_build_seconds": t_graph, "nnz": int(adj5.nnz),
+                "note": "kNN graph built with sqb_knn_2d; directed graph -> full-CSR count kernel (no symmetric shortcut); step = kernels + statistics (+ collective)"}
+        plan5.close()
+    except Exception as e:  # pragma: no cover
+        cfg5 = {"error": repr(e)}
+
     moran = cooc = rip = None
     if not args.skip_moran:
         try:
@@ -625,7 +660,7 @@ def main():
                 "config": dict(CONFIG, shuffle_algo=args.shuffle_algo) if args.shuffle_algo != -1 else CONFIG,
                 "collective": None if ws == 1 else "NCCL all_reduce(int64[C*C] sums) + send/recv chain + broadcast of float64[C*C] (inside the timed step)",
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "fast": fast, "roofline_fast": roofline_fast, "moran": moran, "co_occurrence": cooc, "ripley_L": rip}
+                "fast": fast, "roofline_fast": roofline_fast, "nhood_cfg5_strong": cfg5, "moran": moran, "co_occurrence": cooc, "ripley_L": rip}
         print(json.dumps(line), flush=True)
     plan.close()
     if ws > 1:

@@ -2166,11 +2166,11 @@ __device__ __forceinline__ void sqb_fe2(uint32_t& L, uint32_t& R, uint32_t k0, u
     for (int j = 0; j < 6; ++j) {
         const uint32_t kj = k0 + (uint32_t)j * k1;
         if ((j & 1) == 0) {
-            L += __umulhi(sqb_fe2_hash(R ^ kj), a);
-            L -= L >= a ? a : 0u;
+            L += __umulhi(sqb_fe2_hash(R ^ kj), a);  // < 2a
+            L = min(L, L - a);                       // mod a: L - a wraps to a huge value when L < a
         } else {
             R += __umulhi(sqb_fe2_hash(L ^ kj), b);
-            R -= R >= b ? b : 0u;
+            R = min(R, R - b);
         }
     }
 }

@@ -376,3 +376,18 @@ def test_full_size_1m_spots():
     lab = plan.shuffled_labels(40, 42)
     np.testing.assert_array_equal(np.sort(lab, axis=1), np.sort(np.broadcast_to(base, lab.shape), axis=1))  # a permutation
     np.testing.assert_array_equal(lab, ref.shuffle_labels(base, st[40:42]))
+
+
+def test_buffered_generator_states_are_rejected():
+    """A generator that already handed out half of a 64-bit draw (has_uint32 = 1) cannot be replayed from (state, inc) alone:
+    the C ABI refuses it instead of producing different permutations."""
+    g = synth.hex_graph(9, 9)
+    plan = NhoodPlan(g.indptr, g.indices, 3)
+    plan.set_base(np.random.default_rng(0).integers(0, 3, g.shape[0]).astype(np.uint32))
+    st = spawn_states(1, 4)
+    st[2, 4] = 1
+    with pytest.raises(NotImplementedError, match="has_uint32"):
+        plan.upload(st)
+    plan.upload(spawn_states(1, 4))  # the handle stays usable
+    assert plan.permute(spawn_states(1, 4)).shape == (4, 3, 3)
+    plan.close()

@@ -120,3 +120,21 @@ def test_api_ripley_golden(golden_dummy, dummy_adata, mode):
     np.testing.assert_allclose(res["sims_stat"]["stats"].to_numpy(), golden_dummy[f"ripley_{mode}_sims"], rtol=1e-12, atol=1e-15)
     np.testing.assert_array_equal(res["pvalues"], golden_dummy[f"ripley_{mode}_pvalues"])
     assert res[f"{mode}_stat"]["stats"].iloc[0] == 0.0
+
+
+def test_api_co_occurrence_unused_category_in_the_middle(dummy_adata):
+    """the reference sizes its output by the PRESENT categories but addresses it with raw codes (undefined behaviour
+    when a category in the middle is unused).  Here present codes are remapped: the result must equal the one obtained after
+    dropping the unused category, and the `occ` axis has one entry per present category."""
+    import pandas as pd
+
+    ad = dummy_adata
+    codes = np.asarray(ad.obs["cluster"].cat.codes).copy()
+    codes[codes == 1] = 2  # category '1' stays declared but unused
+    ad.obs["cluster"] = pd.Categorical.from_codes(codes, categories=["0", "1", "2"])
+    occ, iv = sq.gr.co_occurrence(ad, "cluster", interval=12, copy=True)
+    assert occ.shape == (2, 2, 11)
+    ad.obs["cluster"] = ad.obs["cluster"].cat.remove_unused_categories()
+    occ2, iv2 = sq.gr.co_occurrence(ad, "cluster", interval=12, copy=True)
+    np.testing.assert_array_equal(occ, occ2)
+    np.testing.assert_array_equal(iv, iv2)
