@@ -30,6 +30,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <thread>
 
@@ -494,12 +496,12 @@ __device__ __forceinline__ void ac_block_reduce(double (&q)[NQ], double (*s_red)
 
 // FMT 0: packed rows, 8 lanes per row (<= 8 entries);  FMT 1: packed rows, 16 lanes per row (<= 16 entries);
 // FMT 2: CSR rows, 8 lanes per row (any length; float64 weights).
-template <typename XT, int MODE, int FMT, bool PERM>
-__global__ void __launch_bounds__(AC_T, 4) ac_sparse_kernel(const __grid_constant__ AcSparseParams p) {
+template <typename XT, int MODE, int FMT, bool PERM, int GRP>
+__global__ void __launch_bounds__(AC_T, GRP == 8 ? 3 : 4) ac_sparse_kernel(const __grid_constant__ AcSparseParams p) {
     constexpr int LPR = FMT == 1 ? 16 : 8;
     constexpr int RPW = 32 / LPR;        // rows per warp step
     constexpr int NSUB = 32 / RPW;       // warp steps per block of 32 entries
-    constexpr int GRP = 4;               // warp steps handled together: 4 independent row loads / lookups / value loads in flight
+    // GRP = warp steps handled together: GRP independent row loads / look-ups / value loads in flight per warp
     extern __shared__ __align__(16) unsigned char ac_smem[];
     __shared__ double s_red[6][AC_NW];
     __shared__ double s_mean;
@@ -523,6 +525,7 @@ __global__ void __launch_bounds__(AC_T, 4) ac_sparse_kernel(const __grid_constan
         const int len4 = (len + 3) >> 2;
         // ---- phase 1: mark the stored observations, rank of the first one of every word, sum of the values ----
         double q[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
         for (int v = threadIdx.x; v < len4; v += AC_T) {
             const int4 iv = __ldg(reinterpret_cast<const int4*>(xi) + v);
             const int prev = v > 0 ? __ldg(xi + 4 * v - 1) : -1;
@@ -569,6 +572,7 @@ __global__ void __launch_bounds__(AC_T, 4) ac_sparse_kernel(const __grid_constan
             m = s_mean;
             q[0] = 0.0;
             // ---- phase 1b (unpermuted pass only): the column-sum terms D = sum c z, E = sum c, sum z^2, Geary's sum c x^2 ----
+#pragma unroll 2
             for (int v = threadIdx.x; v < len4; v += AC_T) {
                 const int4 iv = __ldg(reinterpret_cast<const int4*>(xi) + v);
                 const int ii[4] = {iv.x, iv.y, iv.z, iv.w};
@@ -742,6 +746,7 @@ __global__ void __launch_bounds__(AC_T, 4) ac_sparse_kernel(const __grid_constan
         }
         if (PERM) __syncthreads();  // s_red is reused by the next permutation of the batch
         }  // permutations of the batch
+#pragma unroll 4
         for (int v = threadIdx.x; v < len4; v += AC_T) {
             const int4 iv = __ldg(reinterpret_cast<const int4*>(xi) + v);
             if (iv.x >= 0) S[iv.x >> 5] = make_uint2(0u, 0u);
@@ -815,10 +820,10 @@ static int ac_geometry(sqb_autocorr* h, const void* kernel, AcGeom* g) {
     return SQB_OK;
 }
 
-template <typename XT, int MODE, int FMT, bool PERM>
-static int ac_sparse_launch(sqb_autocorr* h, const AcSparseParams& base) {
+template <typename XT, int MODE, int FMT, bool PERM, int GRP>
+static int ac_sparse_launch_g(sqb_autocorr* h, const AcSparseParams& base) {
     sqb_ctx* c = h->ctx;
-    const void* kernel = (const void*)ac_sparse_kernel<XT, MODE, FMT, PERM>;
+    const void* kernel = (const void*)ac_sparse_kernel<XT, MODE, FMT, PERM, GRP>;
     AcGeom geo;
     SQB_TRY(ac_geometry(h, kernel, &geo));
     AcSparseParams p = base;
@@ -828,9 +833,19 @@ static int ac_sparse_launch(sqb_autocorr* h, const AcSparseParams& base) {
     if (ctas > h->n_feat) ctas = h->n_feat;
     SQB_CUDA(cudaMemsetAsync(h->d_flags.p + 1, 0, sizeof(int), c->stream));
     SqbLaunchScope scope(c, SQB_K_AUTOCORR_MAIN);
-    ac_sparse_kernel<XT, MODE, FMT, PERM><<<(unsigned)ctas, AC_T, geo.smem, c->stream>>>(p);
+    ac_sparse_kernel<XT, MODE, FMT, PERM, GRP><<<(unsigned)ctas, AC_T, geo.smem, c->stream>>>(p);
     SQB_POST_LAUNCH();
     return SQB_OK;
+}
+
+template <typename XT, int MODE, int FMT, bool PERM>
+static int ac_sparse_launch(sqb_autocorr* h, const AcSparseParams& base) {
+    static const int grp = []() {
+        const char* e = getenv("SQB_AC_GRP");  // tuning knob: row groups per warp pass (4 or 8)
+        return e && atoi(e) == 4 ? 4 : 8;  // measured at configs[2]: 8 -> 7.15 ms, 4 -> 8.7 ms
+    }();
+    if (grp == 8 && FMT != 2) return ac_sparse_launch_g<XT, MODE, FMT, PERM, 8>(h, base);
+    return ac_sparse_launch_g<XT, MODE, FMT, PERM, 4>(h, base);
 }
 
 template <typename XT, int MODE, bool PERM>
@@ -1048,6 +1063,8 @@ static int ac_load_csr_typed(sqb_autocorr* h, const int64_t* h_xp, const int32_t
     DevBuf<uint8_t> r_val, t_val;
     DevBuf<unsigned int> cnt;
     DevBuf<unsigned long long> cursor;
+    r_ptr.bind(c->stream), t_ptr.bind(c->stream), pad.bind(c->stream), r_idx.bind(c->stream), t_idx.bind(c->stream);
+    r_val.bind(c->stream), t_val.bind(c->stream), cnt.bind(c->stream), cursor.bind(c->stream);
     auto cleanup = [&]() {
         r_ptr.release(), t_ptr.release(), pad.release(), r_idx.release(), t_idx.release(), r_val.release(), t_val.release();
         cnt.release(), cursor.release();
@@ -1162,6 +1179,14 @@ int sqb_autocorr_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const int32_t* w_i
     SQB_CUDA(cudaSetDevice(ctx->device));
     sqb_autocorr* h = new sqb_autocorr();
     h->ctx = ctx;
+    {  // stream-ordered allocation from the device pool: a handle is created and destroyed per API call, and GB-sized
+       // cudaMalloc / cudaFree pairs would synchronise the device every time
+        cudaStream_t st = ctx->stream;
+        h->d_wp.bind(st), h->d_wi.bind(st), h->d_wd.bind(st), h->d_csum.bind(st), h->d_rows.bind(st), h->d_x.bind(st), h->d_xp.bind(st);
+        h->d_xi.bind(st), h->d_len.bind(st), h->d_order.bind(st), h->d_tile.bind(st), h->d_sums.bind(st), h->d_partial.bind(st);
+        h->d_pnum.bind(st), h->d_pden.bind(st), h->d_out.bind(st), h->d_aux.bind(st), h->d_out_perms.bind(st), h->d_perm.bind(st);
+        h->d_perm32.bind(st), h->d_seen.bind(st), h->d_bitmap.bind(st), h->d_flags.bind(st);
+    }
     h->n = n;
     h->nnz = nnz;
     h->s0 = s0;

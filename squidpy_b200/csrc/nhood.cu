@@ -2434,6 +2434,39 @@ __global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __res
     }
 }
 
+// observed count (ONE label vector, uint32 as handed over by the host): a warp per CSR row, per-CTA C x C histogram in shared
+// memory (global atomics when it does not fit).  The batched kernel above would zero and flush 32 histogram columns per CTA
+// for a single permutation (13 ms at 1M spots); this one takes ~0.1 ms.
+__global__ void __launch_bounds__(256) nhood_count_single_kernel(const uint32_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
+                                                                 const uint32_t* __restrict__ labels, int64_t n, int C, int hist_smem,
+                                                                 uint32_t* __restrict__ counts) {
+    extern __shared__ uint32_t hist[];
+    const int CC = C * C;
+    if (hist_smem) {
+        for (int i = threadIdx.x; i < CC; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; i < n; i += nw) {
+        const uint32_t b = indptr[i], e = indptr[i + 1];
+        const uint32_t ra = labels[i] * (uint32_t)C;
+        for (uint32_t k = b + lane; k < e; k += 32) {
+            const uint32_t bin = ra + labels[indices[k]];
+            if (hist_smem)
+                atomicAdd(&hist[bin], 1u);
+            else
+                atomicAdd(&counts[bin], 1u);
+        }
+    }
+    if (!hist_smem) return;
+    __syncthreads();
+    for (int i = threadIdx.x; i < CC; i += blockDim.x) {
+        const uint32_t v = hist[i];
+        if (v) atomicAdd(&counts[i], v);
+    }
+}
+
 // fallback for very large n_cls: global atomics, lane = permutation
 template <typename LT>
 __global__ void nhood_count_global_kernel(const uint32_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
@@ -2502,6 +2535,7 @@ struct sqb_nhood {
     int shuffle_threads = 512;
     int64_t perm_chunk = 0;  // 0 = auto
     int count_algo = 0;
+    int count_single = 1;  // sqb_nhood_count: 1 = dedicated single-vector kernel, 0 = the batched kernels (test hook)
     int64_t shuffle_ctas = 0;          // persistent CTAs of the shuffle kernel (0 = occupancy x SM count)
     int shuffle_wfactor_x100 = 400;    // window = min(i/4, wfactor * sqrt(i)) raw values
 };
@@ -2907,6 +2941,62 @@ static int run_chunk_philox(sqb_nhood* h, int64_t p0, int64_t np) {
     return launch_count<LT>(h, labT, PB, (int)np, h->d_counts.p + p0 * (int64_t)h->n_cls * h->n_cls);
 }
 
+// observed count through the BATCHED kernels (lane = permutation, symmetric shortcut): test hook, option count_single = 0
+static int nhood_count_batched_path(sqb_nhood* h, const uint32_t* labels, uint32_t* out) {
+    SQB_CHECK(h && labels && out, SQB_ERR_INVALID, "sqb_nhood_count: null argument");
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    for (int64_t i = 0; i < h->n; ++i)
+        SQB_CHECK(labels[i] < (uint32_t)h->n_cls, SQB_ERR_INVALID, "sqb_nhood_count: labels[%lld]=%u >= n_cls=%d",
+                  (long long)i, labels[i], h->n_cls);
+    const int64_t CC = (int64_t)h->n_cls * h->n_cls;
+    DevBuf<uint8_t> labT;
+    DevBuf<uint32_t> cnt;
+    labT.bind(c->stream);
+    cnt.bind(c->stream);
+    int rc = SQB_OK;
+    if ((rc = h->d_tmp_u32.alloc(h->n)) != SQB_OK) return rc;
+    if ((rc = labT.alloc((size_t)h->n * 32 * h->lt_bytes)) != SQB_OK) return rc;
+    if ((rc = cnt.alloc(CC)) != SQB_OK) {
+        labT.release();
+        return rc;
+    }
+    auto cleanup = [&]() {
+        labT.release();
+        cnt.release();
+    };
+    cudaError_t e;
+    e = cudaMemcpyAsync(h->d_tmp_u32.p, labels, h->n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(labT.p, 0, (size_t)h->n * 32 * h->lt_bytes, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(cnt.p, 0, CC * sizeof(uint32_t), c->stream);
+    if (e != cudaSuccess) {
+        cleanup();
+        sqb_set_error("sqb_nhood_count: %s", cudaGetErrorString(e));
+        return SQB_ERR_CUDA;
+    }
+    {
+        SqbLaunchScope scope(c, SQB_K_MISC);
+        unsigned g = (unsigned)ceil_div64(h->n, 256);
+        if (h->lt_bytes == 1)
+            nhood_single_to_T_kernel<uint8_t><<<g, 256, 0, c->stream>>>(h->d_tmp_u32.p, labT.p, h->n);
+        else
+            nhood_single_to_T_kernel<uint16_t><<<g, 256, 0, c->stream>>>(h->d_tmp_u32.p, reinterpret_cast<uint16_t*>(labT.p), h->n);
+    }
+    rc = (h->lt_bytes == 1) ? launch_count<uint8_t>(h, labT.p, 32, 1, cnt.p)
+                            : launch_count<uint16_t>(h, reinterpret_cast<uint16_t*>(labT.p), 32, 1, cnt.p);
+    if (rc == SQB_OK) {
+        e = cudaMemcpyAsync(out, cnt.p, CC * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            sqb_set_error("sqb_nhood_count: %s", cudaGetErrorString(e));
+            rc = SQB_ERR_CUDA;
+        }
+    }
+    cleanup();
+    return rc;
+}
+
+
 static int ensure_buffers(sqb_nhood* h, int64_t chunk) {
     SQB_TRY(h->ctx->scratch[0].alloc((size_t)chunk * h->stride * h->lt_bytes));
     SQB_TRY(h->ctx->scratch[1].alloc((size_t)h->n * chunk * h->lt_bytes));
@@ -2943,6 +3033,8 @@ int sqb_nhood_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const uint32_t* indpt
     h->d_states.bind(ctx->stream);
     h->d_counts.bind(ctx->stream);
     h->d_tmp_u32.bind(ctx->stream);
+    h->d_cum.bind(ctx->stream);
+    h->d_bkt.bind(ctx->stream);
     h->n = n;
     h->nnz = nnz;
     h->n_cls = n_cls;
@@ -3048,6 +3140,8 @@ int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "count_un")) {
         SQB_CHECK(value == 4 || value == 6 || value == 8 || value == 12, SQB_ERR_INVALID, "count_un must be 4, 6, 8 or 12");
         h->count_un = (int)value;
+    } else if (!strcmp(key, "count_single")) {
+        h->count_single = value != 0;
     } else if (!strcmp(key, "count_sym")) {
         SQB_CHECK(value == -1 || value == 0, SQB_ERR_INVALID, "count_sym must be -1 (auto) or 0 (full CSR)");
         h->count_sym = (int)value;
@@ -3099,51 +3193,38 @@ int sqb_nhood_count(sqb_nhood* h, const uint32_t* labels, uint32_t* out) {
     for (int64_t i = 0; i < h->n; ++i)
         SQB_CHECK(labels[i] < (uint32_t)h->n_cls, SQB_ERR_INVALID, "sqb_nhood_count: labels[%lld]=%u >= n_cls=%d",
                   (long long)i, labels[i], h->n_cls);
+    if (!h->count_single) return nhood_count_batched_path(h, labels, out);
     const int64_t CC = (int64_t)h->n_cls * h->n_cls;
-    DevBuf<uint8_t> labT;
     DevBuf<uint32_t> cnt;
-    labT.bind(c->stream);
     cnt.bind(c->stream);
     int rc = SQB_OK;
     if ((rc = h->d_tmp_u32.alloc(h->n)) != SQB_OK) return rc;
-    if ((rc = labT.alloc((size_t)h->n * 32 * h->lt_bytes)) != SQB_OK) return rc;
-    if ((rc = cnt.alloc(CC)) != SQB_OK) {
-        labT.release();
-        return rc;
-    }
-    auto cleanup = [&]() {
-        labT.release();
-        cnt.release();
-    };
-    cudaError_t e;
-    e = cudaMemcpyAsync(h->d_tmp_u32.p, labels, h->n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(labT.p, 0, (size_t)h->n * 32 * h->lt_bytes, c->stream);
+    if ((rc = cnt.alloc(CC)) != SQB_OK) return rc;
+    cudaError_t e = cudaMemcpyAsync(h->d_tmp_u32.p, labels, h->n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(cnt.p, 0, CC * sizeof(uint32_t), c->stream);
+    if (e == cudaSuccess) {
+        const size_t smem = (size_t)CC * sizeof(uint32_t);
+        const int hist_smem = smem <= 160 * 1024 ? 1 : 0;
+        if (hist_smem && smem > 48 * 1024) e = cudaFuncSetAttribute(nhood_count_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            SqbLaunchScope scope(c, SQB_K_NHOOD_COUNT);
+            int64_t ctas = ceil_div64(h->n, 8 * 16);  // >= 16 rows per warp
+            const int64_t cap = (int64_t)c->sm_count * (smem > 32 * 1024 ? 2 : 8);
+            if (ctas > cap) ctas = cap;
+            if (ctas < 1) ctas = 1;
+            nhood_count_single_kernel<<<(unsigned)ctas, 256, hist_smem ? smem : 0, c->stream>>>(h->d_indptr.p, h->d_indices.p, h->d_tmp_u32.p, h->n,
+                                                                                                 h->n_cls, hist_smem, cnt.p);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, cnt.p, CC * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cnt.release();
     if (e != cudaSuccess) {
-        cleanup();
         sqb_set_error("sqb_nhood_count: %s", cudaGetErrorString(e));
         return SQB_ERR_CUDA;
     }
-    {
-        SqbLaunchScope scope(c, SQB_K_MISC);
-        unsigned g = (unsigned)ceil_div64(h->n, 256);
-        if (h->lt_bytes == 1)
-            nhood_single_to_T_kernel<uint8_t><<<g, 256, 0, c->stream>>>(h->d_tmp_u32.p, labT.p, h->n);
-        else
-            nhood_single_to_T_kernel<uint16_t><<<g, 256, 0, c->stream>>>(h->d_tmp_u32.p, reinterpret_cast<uint16_t*>(labT.p), h->n);
-    }
-    rc = (h->lt_bytes == 1) ? launch_count<uint8_t>(h, labT.p, 32, 1, cnt.p)
-                            : launch_count<uint16_t>(h, reinterpret_cast<uint16_t*>(labT.p), 32, 1, cnt.p);
-    if (rc == SQB_OK) {
-        e = cudaMemcpyAsync(out, cnt.p, CC * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) {
-            sqb_set_error("sqb_nhood_count: %s", cudaGetErrorString(e));
-            rc = SQB_ERR_CUDA;
-        }
-    }
-    cleanup();
-    return rc;
+    return SQB_OK;
 }
 
 int sqb_nhood_set_base(sqb_nhood* h, const uint32_t* base_labels, const int32_t* lib_codes, int n_libs) {
@@ -3236,8 +3317,9 @@ int sqb_nhood_set_base(sqb_nhood* h, const uint32_t* base_labels, const int32_t*
         }
         SQB_TRY(h->d_cum.alloc(cum.size()));
         SQB_TRY(h->d_bkt.alloc(bkt.size() > 0 ? bkt.size() : 1));
-        SQB_CUDA(cudaMemcpy(h->d_cum.p, cum.data(), cum.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        SQB_CUDA(cudaMemcpy(h->d_bkt.p, bkt.data(), bkt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        SQB_CUDA(cudaMemcpyAsync(h->d_cum.p, cum.data(), cum.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        SQB_CUDA(cudaMemcpyAsync(h->d_bkt.p, bkt.data(), bkt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        SQB_CUDA(cudaStreamSynchronize(c->stream));  // cum / bkt are locals
     }
     SQB_TRY(h->d_seg_start.alloc(h->nseg));
     SQB_TRY(h->d_seg_len.alloc(h->nseg));

@@ -28,12 +28,15 @@ def test_kat1_count():
 
 
 @pytest.mark.parametrize("n_cls", [2, 3, 10, 30, 45, 70, 120, 230, 300])
-def test_count_vs_oracle(n_cls):
-    # n_cls sweeps every histogram layout: 32/16/8/2 permutations per CTA in shared memory, global atomics (230),
-    # uint16 labels (300)
+@pytest.mark.parametrize("single", [1, 0])
+def test_count_vs_oracle(n_cls, single):
+    # batched path (single=0): n_cls sweeps every histogram layout: 32/16/8/2 permutations per CTA in shared memory, global
+    # atomics (230), uint16 labels (300); single=1: the dedicated observed-count kernel (shared histogram up to C=202, else global)
     g = synth.hex_graph(61, 53)
     lab = np.random.default_rng(n_cls).integers(0, n_cls, g.shape[0]).astype(np.uint32)
-    np.testing.assert_array_equal(_plan(g, n_cls).count(lab), ref.nhood_count(g.indptr, g.indices, lab, n_cls))
+    plan = _plan(g, n_cls)
+    plan.set_option("count_single", single)
+    np.testing.assert_array_equal(plan.count(lab), ref.nhood_count(g.indptr, g.indices, lab, n_cls))
 
 
 def test_count_directed_selfloops_empty_rows():
@@ -90,6 +93,8 @@ def test_count_symmetric_shortcut(kind):
     for count_sym in (-1, 0):
         plan = _plan(g, n_cls)
         plan.set_option("count_sym", count_sym)
+        np.testing.assert_array_equal(plan.count(lab), exp)  # dedicated single-vector kernel
+        plan.set_option("count_single", 0)                    # the batched kernels, which the shortcut belongs to
         np.testing.assert_array_equal(plan.count(lab), exp)
         plan.set_base(lab)
         np.testing.assert_array_equal(plan.permute(st), exp_perm)
