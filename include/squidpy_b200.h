@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SQB_ABI_VERSION 1
+#define SQB_ABI_VERSION 2
 
 typedef enum {
     SQB_OK = 0,

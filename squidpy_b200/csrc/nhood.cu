@@ -2520,6 +2520,8 @@ struct sqb_nhood {
     DevBuf<uint32_t> d_cum;  // [nseg][n_cls + 1] class offsets of every segment's sorted labels (fast mode)
     DevBuf<uint32_t> d_bkt;  // per segment: class at the first value of every bucket (fast mode class lookup)
     std::vector<int64_t> h_seg_start, h_seg_len, h_bkt_off;
+    std::vector<uint32_t> h_grouped;  // base labels in library-grouped order (host copy for the fast-mode tables)
+    bool philox_ready = false;
     std::vector<PhiloxSeg> h_pseg;
     // label matrices [chunk][stride] and [n][PB] live in ctx->scratch[0..1]
     DevBuf<uint32_t> d_counts;  // [P][C*C]
@@ -2941,6 +2943,69 @@ static int run_chunk_philox(sqb_nhood* h, int64_t p0, int64_t np) {
     return launch_count<LT>(h, labT, PB, (int)np, h->d_counts.p + p0 * (int64_t)h->n_cls * h->n_cls);
 }
 
+// fast RNG mode tables (built lazily: the exact mode never needs them)
+static int philox_prepare(sqb_nhood* h) {
+    if (h->philox_ready) return SQB_OK;
+    sqb_ctx* c = h->ctx;
+    const std::vector<int64_t>& seg_start = h->h_seg_start;
+    const std::vector<int64_t>& seg_len = h->h_seg_len;
+    const std::vector<uint32_t>& grouped = h->h_grouped;
+    {  // fast RNG mode: per segment the class offsets of its labels sorted by class, the Feistel radices and a bucket table
+       // (class at the first value of every bucket of 2^shift values) that shortens the class search to `steps` bisections
+        const int64_t C1 = (int64_t)h->n_cls + 1;
+        std::vector<uint32_t> cum((size_t)h->nseg * C1, 0u), bkt;
+        h->h_pseg.assign(h->nseg, PhiloxSeg());
+        h->h_bkt_off.assign(h->nseg, 0);
+        for (int sgm = 0; sgm < h->nseg; ++sgm) {
+            uint32_t* row = cum.data() + (size_t)sgm * C1;
+            const int64_t m = seg_len[sgm];
+            for (int64_t k = seg_start[sgm]; k < seg_start[sgm] + m; ++k) row[grouped[k] + 1]++;
+            for (int64_t cc = 0; cc < h->n_cls; ++cc) row[cc + 1] += row[cc];
+            PhiloxSeg& ps = h->h_pseg[sgm];
+            ps.start = seg_start[sgm];
+            ps.len = m;
+            ps.seg = sgm;
+            uint64_t a = (uint64_t)sqrt((double)(m > 0 ? m : 1));
+            while (a * a < (uint64_t)m) ++a;
+            while (a > 1 && (a - 1) * (a - 1) >= (uint64_t)m) --a;
+            if (a < 1) a = 1;
+            ps.a = (uint32_t)a;
+            ps.b = (uint32_t)((m + (int64_t)a - 1) / (int64_t)a);
+            if (ps.b < 1) ps.b = 1;
+            int bits = 0;
+            while (bits < 32 && ((uint64_t)(m > 0 ? m - 1 : 0) >> bits) != 0) ++bits;
+            ps.shift = bits > 11 ? bits - 11 : 0;  // <= 2048 buckets
+            ps.tsize = (int)((((uint64_t)(m > 0 ? m - 1 : 0)) >> ps.shift) + 1);
+            h->h_bkt_off[sgm] = (int64_t)bkt.size();
+            auto class_of = [&](uint64_t v) {  // last c in [0, n_cls) with row[c] <= v
+                int lo = 0, hi = h->n_cls - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if ((uint64_t)row[mid] <= v) lo = mid; else hi = mid - 1;
+                }
+                return (uint32_t)lo;
+            };
+            for (int t = 0; t <= ps.tsize; ++t) bkt.push_back(class_of((uint64_t)t << ps.shift));
+            // the kernel searches [table[bucket], table[bucket + 1]] (class at the first value of this / of the next bucket)
+            uint32_t maxrange = 0;
+            for (int t = 0; t < ps.tsize; ++t) {
+                const uint32_t d = bkt[h->h_bkt_off[sgm] + t + 1] - bkt[h->h_bkt_off[sgm] + t];
+                if (d > maxrange) maxrange = d;
+            }
+            int steps = 0;
+            while ((1u << steps) < maxrange + 1u) ++steps;
+            ps.steps = steps;
+        }
+        SQB_TRY(h->d_cum.alloc(cum.size()));
+        SQB_TRY(h->d_bkt.alloc(bkt.size() > 0 ? bkt.size() : 1));
+        SQB_CUDA(cudaMemcpyAsync(h->d_cum.p, cum.data(), cum.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        SQB_CUDA(cudaMemcpyAsync(h->d_bkt.p, bkt.data(), bkt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        SQB_CUDA(cudaStreamSynchronize(c->stream));  // cum / bkt are locals
+    }
+    h->philox_ready = true;
+    return SQB_OK;
+}
+
 // observed count through the BATCHED kernels (lane = permutation, symmetric shortcut): test hook, option count_single = 0
 static int nhood_count_batched_path(sqb_nhood* h, const uint32_t* labels, uint32_t* out) {
     SQB_CHECK(h && labels && out, SQB_ERR_INVALID, "sqb_nhood_count: null argument");
@@ -3269,58 +3334,8 @@ int sqb_nhood_set_base(sqb_nhood* h, const uint32_t* base_labels, const int32_t*
     h->nseg = (int)seg_start.size();
     h->h_seg_start = seg_start;
     h->h_seg_len = seg_len;
-    {  // fast RNG mode: per segment the class offsets of its labels sorted by class, the Feistel radices and a bucket table
-       // (class at the first value of every bucket of 2^shift values) that shortens the class search to `steps` bisections
-        const int64_t C1 = (int64_t)h->n_cls + 1;
-        std::vector<uint32_t> cum((size_t)h->nseg * C1, 0u), bkt;
-        h->h_pseg.assign(h->nseg, PhiloxSeg());
-        h->h_bkt_off.assign(h->nseg, 0);
-        for (int sgm = 0; sgm < h->nseg; ++sgm) {
-            uint32_t* row = cum.data() + (size_t)sgm * C1;
-            const int64_t m = seg_len[sgm];
-            for (int64_t k = seg_start[sgm]; k < seg_start[sgm] + m; ++k) row[grouped[k] + 1]++;
-            for (int64_t cc = 0; cc < h->n_cls; ++cc) row[cc + 1] += row[cc];
-            PhiloxSeg& ps = h->h_pseg[sgm];
-            ps.start = seg_start[sgm];
-            ps.len = m;
-            ps.seg = sgm;
-            uint64_t a = (uint64_t)sqrt((double)(m > 0 ? m : 1));
-            while (a * a < (uint64_t)m) ++a;
-            while (a > 1 && (a - 1) * (a - 1) >= (uint64_t)m) --a;
-            if (a < 1) a = 1;
-            ps.a = (uint32_t)a;
-            ps.b = (uint32_t)((m + (int64_t)a - 1) / (int64_t)a);
-            if (ps.b < 1) ps.b = 1;
-            int bits = 0;
-            while (bits < 32 && ((uint64_t)(m > 0 ? m - 1 : 0) >> bits) != 0) ++bits;
-            ps.shift = bits > 11 ? bits - 11 : 0;  // <= 2048 buckets
-            ps.tsize = (int)((((uint64_t)(m > 0 ? m - 1 : 0)) >> ps.shift) + 1);
-            h->h_bkt_off[sgm] = (int64_t)bkt.size();
-            auto class_of = [&](uint64_t v) {  // last c in [0, n_cls) with row[c] <= v
-                int lo = 0, hi = h->n_cls - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if ((uint64_t)row[mid] <= v) lo = mid; else hi = mid - 1;
-                }
-                return (uint32_t)lo;
-            };
-            for (int t = 0; t <= ps.tsize; ++t) bkt.push_back(class_of((uint64_t)t << ps.shift));
-            // the kernel searches [table[bucket], table[bucket + 1]] (class at the first value of this / of the next bucket)
-            uint32_t maxrange = 0;
-            for (int t = 0; t < ps.tsize; ++t) {
-                const uint32_t d = bkt[h->h_bkt_off[sgm] + t + 1] - bkt[h->h_bkt_off[sgm] + t];
-                if (d > maxrange) maxrange = d;
-            }
-            int steps = 0;
-            while ((1u << steps) < maxrange + 1u) ++steps;
-            ps.steps = steps;
-        }
-        SQB_TRY(h->d_cum.alloc(cum.size()));
-        SQB_TRY(h->d_bkt.alloc(bkt.size() > 0 ? bkt.size() : 1));
-        SQB_CUDA(cudaMemcpyAsync(h->d_cum.p, cum.data(), cum.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        SQB_CUDA(cudaMemcpyAsync(h->d_bkt.p, bkt.data(), bkt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        SQB_CUDA(cudaStreamSynchronize(c->stream));  // cum / bkt are locals
-    }
+    h->h_grouped = grouped;  // the fast RNG mode builds its class tables from these at its first upload
+    h->philox_ready = false;
     SQB_TRY(h->d_seg_start.alloc(h->nseg));
     SQB_TRY(h->d_seg_len.alloc(h->nseg));
     SQB_TRY(h->d_tmp_u32.alloc(n));
@@ -3380,6 +3395,7 @@ int sqb_nhood_permute_upload_philox(sqb_nhood* h, uint64_t seed, int64_t first_p
     SQB_CHECK(h->base_set, SQB_ERR_STATE, "sqb_nhood_permute_upload_philox: call sqb_nhood_set_base first");
     sqb_ctx* c = h->ctx;
     SQB_CUDA(cudaSetDevice(c->device));
+    SQB_TRY(philox_prepare(h));
     SQB_TRY(h->d_counts.alloc((size_t)n_perms * h->n_cls * h->n_cls));
     int64_t chunk = auto_chunk(h);
     if (chunk > ((n_perms + 31) / 32) * 32) chunk = ((n_perms + 31) / 32) * 32;
