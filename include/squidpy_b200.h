@@ -131,17 +131,19 @@ int sqb_nhood_shuffled_labels(sqb_nhood* h, int64_t p0, int64_t p1, uint32_t* ou
 
 /* Tuning / test options (all variants produce bit-identical results).
  *   "shuffle_algo"   -1 auto [default]: two-kernel list replay (7) for many permutations of large arrays, else 1 / 2;
- *                    0 one thread per permutation (serial replay); 1 CTA per permutation; 2 warp per permutation;
- *                    3 CTA per permutation with large windows; 4 two-warp pipeline; 5 two kernels with ordered replay;
- *                    6 CTA per permutation with list resolution; 7 two kernels (swap-target generation + list apply)
- *   "shuffle_threads" 128/256/512/1024 (algos 1, 3, 5, 6, 7), "shuffle_r" 2/4/8 steps or raw pairs per thread (3, 5, 6, 7),
- *   "shuffle_q"      1/2/4 PCG64 outputs per lane and batch (2, and the target generation of 5, 7),
- *   "shuffle_low"    elements of every label array kept in shared memory by the apply kernels of 5, 7 (-1 all that fits, 0 off),
+ *                    1 CTA per permutation; 2 warp per permutation; 7 two kernels (swap-target generation + list apply).
+ *                    0 (serial), 3 (large windows), 4 (two-warp pipeline), 5 (two kernels, ordered replay), 6 (fused list
+ *                    kernel) are superseded cross-check variants compiled into the TEST build only (make testvariants);
+ *                    the product library answers SQB_ERR_UNSUPPORTED for them.
+ *   "shuffle_threads" 128/256/512/1024 (algos 1, 7), "shuffle_r" 2/4/8 steps per thread (7),
+ *   "shuffle_q"      1/2/4/8 PCG64 outputs per lane and batch (2, and the target generation of 7),
+ *   "shuffle_low"    elements of every label array kept in shared memory by the apply kernel of 7 (-1 all that fits, 0 off),
  *   "shuffle_ctas"   persistent grid size = permutations in flight (0 = occupancy x SM count),
  *   "shuffle_stagger_us" start-up stagger of the persistent CTAs, "shuffle_wfactor_x100" window = min(i/4, f*sqrt(i)),
- *   "perm_chunk"     permutations resident at once, "count_algo" 0 auto / 1 shared-memory histograms / 2 global atomics,
- *   "count_sym"      -1 auto (count structurally symmetric graphs from the entries with j >= i) / 0 always the full CSR,
- *   "count_un"       CSR rows a warp walks at once in the symmetric count kernel (4 / 6 [default] / 8 / 12). */
+ *   "perm_chunk"     permutations resident at once (read at the next upload), "count_algo" 0 auto / 1 shared-memory histograms /
+ *                    2 global atomics, "count_sym" -1 auto (count structurally symmetric graphs from the entries with j >= i) /
+ *                    0 always the full CSR, "count_un" CSR rows a warp walks at once in the symmetric count kernel (4 / 6 / 8 / 12),
+ *   "count_single"   sqb_nhood_count: 1 dedicated single-vector kernel [default] / 0 the batched kernels (test hook). */
 int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value);
 /* algorithmic bytes per permutation, SURVEY.md 8(d): 4*nnz + 4*(n+1) + 8*n + 4*n_cls^2                   */
 int sqb_nhood_bytes_per_perm(sqb_nhood* h, int64_t* bytes);

@@ -840,12 +840,8 @@ static int ac_sparse_launch_g(sqb_autocorr* h, const AcSparseParams& base) {
 
 template <typename XT, int MODE, int FMT, bool PERM>
 static int ac_sparse_launch(sqb_autocorr* h, const AcSparseParams& base) {
-    static const int grp = []() {
-        const char* e = getenv("SQB_AC_GRP");  // tuning knob: row groups per warp pass (4 or 8)
-        return e && atoi(e) == 4 ? 4 : 8;  // measured at configs[2]: 8 -> 7.15 ms, 4 -> 8.7 ms
-    }();
-    if (grp == 8 && FMT != 2) return ac_sparse_launch_g<XT, MODE, FMT, PERM, 8>(h, base);
-    return ac_sparse_launch_g<XT, MODE, FMT, PERM, 4>(h, base);
+    // 8 row groups in flight per warp (measured at configs[2]: 7.15 ms; 4 groups: 8.7 ms)
+    return ac_sparse_launch_g<XT, MODE, FMT, PERM, 8>(h, base);
 }
 
 template <typename XT, int MODE, bool PERM>

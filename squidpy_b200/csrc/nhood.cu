@@ -119,6 +119,7 @@ __global__ void nhood_fill_kernel(uint4* __restrict__ dst, const uint4* __restri
     }
 }
 
+#ifdef SQB_TEST_VARIANTS  // superseded replay variant: compiled into the test build only (tests/native/libsquidpy_b200_testvariants.so)
 // ------------------------------------------------------------------------------------------------
 // 2a. reference-style serial replay: one thread per permutation (cross-check / fallback option)
 // ------------------------------------------------------------------------------------------------
@@ -145,6 +146,7 @@ __global__ void nhood_shuffle_serial_kernel(LT* __restrict__ labels, int64_t str
     }
 }
 
+#endif  // SQB_TEST_VARIANTS
 // ------------------------------------------------------------------------------------------------
 // 2b. CTA-parallel exact replay of numpy Generator.shuffle (see file header; validated step by step against
 //     numpy by the Python emulation tests/emu_shuffle.py).
@@ -645,6 +647,7 @@ __global__ void __launch_bounds__(128) nhood_shuffle_warp_kernel(LT* __restrict_
     }
 }
 
+#ifdef SQB_TEST_VARIANTS  // superseded replay variant: compiled into the test build only (tests/native/libsquidpy_b200_testvariants.so)
 // ------------------------------------------------------------------------------------------------
 // 2d. CTA per permutation, LARGE windows (default for big n).  ncu showed 2b/2c to be bound by the dependent
 //     instruction chain of a window (~600-1200 instructions per warp per window at IPC ~0.1-0.3), not by HBM or issue
@@ -924,6 +927,7 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_cta2_kernel(LT* __restrict__
     }
 }
 
+#endif  // SQB_TEST_VARIANTS
 // ------------------------------------------------------------------------------------------------
 // 2g. CTA-per-permutation replay WITHOUT a serial pass ("list" kernel, shuffle_algo 6).
 //     Measured on B200 (tools/micro/rmw_bench.cu): random byte swaps over label arrays that stay inside the 126 MB L2
@@ -981,6 +985,7 @@ __device__ __forceinline__ int sqb_list_latest_before(const uint16_t* __restrict
     return best;
 }
 
+#ifdef SQB_TEST_VARIANTS  // superseded replay variant: compiled into the test build only (tests/native/libsquidpy_b200_testvariants.so)
 template <typename LT, int NT, int R>
 __global__ void __launch_bounds__(NT) nhood_shuffle_list_kernel(LT* __restrict__ labels, int64_t stride,
                                                                 const uint64_t* __restrict__ states, int64_t n_perms,
@@ -1217,6 +1222,8 @@ __global__ void __launch_bounds__(NT) nhood_shuffle_list_kernel(LT* __restrict__
     }
 }
 
+#endif  // SQB_TEST_VARIANTS
+#ifdef SQB_TEST_VARIANTS  // superseded replay variant: compiled into the test build only (tests/native/libsquidpy_b200_testvariants.so)
 // ------------------------------------------------------------------------------------------------
 // 2e. TWO-WARP PIPELINE per permutation.  ncu: 2c spends ~9 500 cycles per 192-step window in ONE dependent chain
 //     (PCG64 multiply-adds -> ballots/prefix -> hash inserts -> global loads -> stores) at IPC ~0.12, with HBM and the
@@ -1498,6 +1505,7 @@ __global__ void __launch_bounds__(PIPE_TEAMS * 64) nhood_shuffle_pipe_kernel(LT*
     }
 }
 
+#endif  // SQB_TEST_VARIANTS
 // ------------------------------------------------------------------------------------------------
 // 2f. TWO-KERNEL replay (algo 5).  ncu showed every fused variant to be bound by random DRAM row activations (1000
 //     live 1 MB label arrays do not fit the 126 MB L2) and, with fewer permutations in flight, by the dependent
@@ -1628,6 +1636,7 @@ __global__ void __launch_bounds__(128) nhood_jgen_kernel(uint32_t* __restrict__ 
     }
 }
 
+#ifdef SQB_TEST_VARIANTS  // superseded replay variant: compiled into the test build only (tests/native/libsquidpy_b200_testvariants.so)
 template <typename LT, int NT, int SPT>
 __global__ void __launch_bounds__(NT) nhood_apply_kernel(LT* __restrict__ labels, const uint32_t* __restrict__ J,
                                                          int64_t stride, int64_t n_perms, int nseg,
@@ -1832,6 +1841,7 @@ __global__ void __launch_bounds__(NT) nhood_apply_kernel(LT* __restrict__ labels
     }
 }
 
+#endif  // SQB_TEST_VARIANTS
 // ------------------------------------------------------------------------------------------------
 // 2h. TWO-KERNEL replay with list-based conflict resolution (shuffle_algo 7): nhood_jgen_kernel (2f, a warp per
 //     permutation, warp-level synchronisation only) turns the PCG64 streams into the swap targets J[perm][i]; this kernel
@@ -2627,6 +2637,7 @@ static int launch_shuffle_nt(sqb_nhood* h, LT* lab, const uint64_t* states, int6
     return SQB_OK;
 }
 
+#ifdef SQB_TEST_VARIANTS  // superseded replay variant: compiled into the test build only (tests/native/libsquidpy_b200_testvariants.so)
 template <typename LT, int NT, int R>
 static int launch_shuffle_cta2(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np) {
     sqb_ctx* c = h->ctx;
@@ -2700,6 +2711,7 @@ static int launch_apply(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t np, fl
     return SQB_OK;
 }
 
+#endif  // SQB_TEST_VARIANTS
 template <typename LT, int NT, int SPT>
 static int launch_apply_list(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t np, int64_t low) {
     sqb_ctx* c = h->ctx;
@@ -2728,6 +2740,14 @@ static int launch_apply_list(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t n
                                                (uint64_t)h->shuffle_stagger_us * 1000ull, (int)low_cap);
     return SQB_OK;
 }
+
+#ifndef SQB_TEST_VARIANTS
+static int sqb_variant_unavailable(int algo) {
+    sqb_set_error("shuffle_algo %d is a superseded replay variant kept as a cross-check: it is compiled into the test build only "
+                  "(make -C squidpy_b200/csrc testvariants); the product library offers -1 (auto), 1, 2 and 7", algo);
+    return SQB_ERR_UNSUPPORTED;
+}
+#endif
 
 template <typename LT>
 static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np, int algo, int nt, int r,
@@ -2766,6 +2786,7 @@ static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* stat
         SQB_POST_LAUNCH();
         return SQB_OK;
     }
+#ifdef SQB_TEST_VARIANTS
     if (nt == 512 && r == 4) rc = launch_apply<LT, 512, 4>(h, lab, J, np, wf);
     else if (nt == 512 && r == 2) rc = launch_apply<LT, 512, 2>(h, lab, J, np, wf);
     else if (nt == 1024 && r == 2) rc = launch_apply<LT, 1024, 2>(h, lab, J, np, wf);
@@ -2776,6 +2797,11 @@ static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* stat
     SQB_TRY(rc);
     SQB_POST_LAUNCH();
     return SQB_OK;
+#else
+    (void)wf;
+    (void)rc;
+    return sqb_variant_unavailable(algo);
+#endif
 }
 
 template <typename LT>
@@ -2791,6 +2817,9 @@ static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t
         return launch_shuffle_two_kernel<LT>(h, lab, states, np, 7, 1024, 2, 98304);
     SqbLaunchScope scope(c, SQB_K_NHOOD_SHUFFLE);
     const int algo = h->shuffle_algo >= 0 ? h->shuffle_algo : (np <= 2 * (int64_t)c->sm_count ? 1 : 2);
+#ifndef SQB_TEST_VARIANTS
+    if (algo == 0 || algo == 3 || algo == 4 || algo == 6) return sqb_variant_unavailable(algo);
+#else
     if (algo == 0) {
         nhood_shuffle_serial_kernel<LT><<<(unsigned)ceil_div64(np, 32), 32, 0, c->stream>>>(
             lab, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p);
@@ -2824,7 +2853,9 @@ static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t
         if (ctas > ceil_div64(np, PIPE_TEAMS)) ctas = ceil_div64(np, PIPE_TEAMS);
         nhood_shuffle_pipe_kernel<LT><<<(unsigned)ctas, PIPE_TEAMS * 64, 0, c->stream>>>(
             lab, h->stride, states, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, (float)h->shuffle_wfactor_x100 / 100.0f);
-    } else if (algo == 2) {
+    } else
+#endif
+    if (algo == 2) {
         const float wf = (float)h->shuffle_wfactor_x100 / 100.0f;
         int64_t ctas = h->shuffle_ctas > 0 ? h->shuffle_ctas : (int64_t)c->sm_count * 8;
         if (ctas > ceil_div64(np, 4)) ctas = ceil_div64(np, 4);

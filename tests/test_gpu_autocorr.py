@@ -218,3 +218,36 @@ def test_api_obs_and_obsm(golden_dummy, dummy_adata):
     dummy_adata.obsm["emb"] = golden_dummy["X"][:, :4].copy()
     df = sq.gr.spatial_autocorr(dummy_adata, attr="obsm", layer="emb", copy=True)
     assert list(df.index.sort_values()) == [0, 1, 2, 3] and np.isfinite(df["I"]).all()
+
+
+@pytest.mark.parametrize("fmt", ["csr", "csc", "dense"])
+def test_feature_shard_equals_slice_of_the_full_run(fmt):
+    """Multi-GPU sharding loads a contiguous feature range per rank (`cols=`): for CSR-by-observation input the slice is cut
+    while the matrix is staged (`sqb_autocorr_load_csr_cols`); the scores must be the corresponding slice of the full run, bit
+    for bit, and an unsorted row must not lose entries."""
+    w = _w(45, 50)
+    n = w.shape[0]
+    x = sp.random(n, 210, density=0.12, format="csr", random_state=8, dtype=np.float32)
+    plan = AutocorrPlan(w)
+    plan.load(x, obs_major=True)
+    full_i, full_c = plan.score("moran"), plan.score("geary")
+    m = {"csr": x, "csc": x.tocsc(), "dense": x.toarray()}[fmt]
+    for lo, hi in ((0, 70), (70, 141), (141, 210), (5, 6)):
+        plan.load(m, obs_major=True, cols=(lo, hi))
+        assert plan.n_features == hi - lo
+        got_i, got_c = plan.score("moran"), plan.score("geary")
+        if fmt == "dense":
+            np.testing.assert_allclose(got_i, full_i[lo:hi], **TIGHT)
+            np.testing.assert_allclose(got_c, full_c[lo:hi], **TIGHT)
+        else:
+            np.testing.assert_array_equal(got_i, full_i[lo:hi])
+            np.testing.assert_array_equal(got_c, full_c[lo:hi])
+    # rows with descending column order: the wrapper sorts a copy before slicing
+    rev = sp.csr_matrix((x.data.copy(), x.indices.copy(), x.indptr.copy()), shape=x.shape)
+    for r in range(n):
+        a, b = rev.indptr[r], rev.indptr[r + 1]
+        rev.indices[a:b] = rev.indices[a:b][::-1]
+        rev.data[a:b] = rev.data[a:b][::-1]
+    rev.has_sorted_indices = False
+    plan.load(rev, obs_major=True, cols=(70, 141))
+    np.testing.assert_array_equal(plan.score("moran"), full_i[70:141])

@@ -2,6 +2,10 @@
 
 from __future__ import annotations
 
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pandas as pd
 import pytest
@@ -14,6 +18,18 @@ from squidpy_b200.gr import NhoodPlan
 from tools import synth
 
 pytestmark = pytest.mark.gpu
+
+# The product library offers the replay variants -1 (auto), 1, 2 and 7.  The superseded variants 0, 3, 4, 5, 6 are kept as
+# independent cross-checks in a TEST build of the same sources (tests/native/libsquidpy_b200_testvariants.so, `make testvariants`):
+# `test_superseded_replay_variants_cross_check` re-runs this file against that build in a subprocess with SQB_VARIANT_TESTS=1,
+# which flips the parametrisations below from the product variants to the superseded ones.
+VARIANT_RUN = os.environ.get("SQB_VARIANT_TESTS") == "1"
+PRODUCT_ALGOS = (-1, 1, 2, 7)
+
+
+def _algos(params):
+    return [q for q in params if ((q[0] if isinstance(q, tuple) else q) in PRODUCT_ALGOS) != VARIANT_RUN]
+
 
 
 def _plan(g, n_cls):
@@ -123,11 +139,11 @@ def test_create_errors():
         NhoodPlan(np.array([0, 1, 2]), np.array([1, -1], dtype=np.int64), 2)
 
 
-@pytest.mark.parametrize("algo,threads,q", [(0, 512, 4), (1, 128, 4), (1, 256, 4), (1, 512, 4), (1, 1024, 4), (2, 512, 1), (2, 512, 2), (2, 512, 4),
+@pytest.mark.parametrize("algo,threads,q", _algos([(0, 512, 4), (1, 128, 4), (1, 256, 4), (1, 512, 4), (1, 1024, 4), (2, 512, 1), (2, 512, 2), (2, 512, 4),
                                              (3, 128, 4), (3, 256, 4), (3, 256, 8), (3, 512, 2), (3, 512, 4), (3, 1024, 2), (3, 1024, 4), (4, 512, 4),
                                              (5, 256, 4), (5, 256, 8), (5, 512, 2), (5, 512, 4), (5, 1024, 2), (5, 1024, 4),
                                              (6, 128, 4), (6, 256, 4), (6, 256, 8), (6, 512, 2), (6, 512, 4), (6, 512, 8), (6, 1024, 2), (6, 1024, 4),
-                                             (7, 128, 4), (7, 256, 4), (7, 256, 8), (7, 512, 2), (7, 512, 4), (7, 512, 8), (7, 1024, 2), (7, 1024, 4)])
+                                             (7, 128, 4), (7, 256, 4), (7, 256, 8), (7, 512, 2), (7, 512, 4), (7, 512, 8), (7, 1024, 2), (7, 1024, 4)]))
 @pytest.mark.parametrize("n", [2, 3, 5, 33, 100, 1000, 1025, 5041, 70001])
 def test_shuffle_is_numpy_exact(algo, threads, q, n):
     """Shuffled label vectors equal numpy Generator.shuffle of the same spawned generators (oracle = exact replay,
@@ -149,7 +165,7 @@ def test_shuffle_is_numpy_exact(algo, threads, q, n):
     np.testing.assert_array_equal(got, ref.shuffle_labels(base, st))
 
 
-@pytest.mark.parametrize("algo,threads,r", [(1, 512, 4), (2, 512, 4), (3, 512, 4), (5, 512, 4), (6, 512, 4), (6, 1024, 2), (7, 1024, 2), (7, 512, 8), (-1, 512, 4)])
+@pytest.mark.parametrize("algo,threads,r", _algos([(1, 512, 4), (2, 512, 4), (3, 512, 4), (5, 512, 4), (6, 512, 4), (6, 1024, 2), (7, 1024, 2), (7, 512, 8), (-1, 512, 4)]))
 def test_shuffle_uint16_labels(algo, threads, r):
     """More than 256 categories: 16-bit label arrays through every replay variant (incl. the shared-memory low part of the
     default, which then holds half as many elements), with library segments."""
@@ -183,7 +199,7 @@ def test_target_generation_batch_sizes(q, n):
     base = (np.arange(n) % 113).astype(np.uint32)
     st = spawn_states(900 + n, 24)
     exp = ref.shuffle_labels(base, st)
-    for algo in (5, 7):
+    for algo in _algos([5, 7]):
         plan = _plan(g, 113)
         plan.set_option("shuffle_algo", algo)
         plan.set_option("shuffle_q", q)
@@ -192,6 +208,7 @@ def test_target_generation_batch_sizes(q, n):
         np.testing.assert_array_equal(plan.shuffled_labels(0, 24), exp)
 
 
+@pytest.mark.skipif(not VARIANT_RUN, reason="algo 6 lives in the test build (see test_superseded_replay_variants_cross_check)")
 @pytest.mark.parametrize("wf", [100, 400, 1600, 6400])
 @pytest.mark.parametrize("threads,r", [(256, 4), (512, 8), (1024, 4)])
 def test_list_replay_window_factor(wf, threads, r):
@@ -211,7 +228,7 @@ def test_list_replay_window_factor(wf, threads, r):
     np.testing.assert_array_equal(plan.shuffled_labels(0, 9), ref.shuffle_labels(base, st))
 
 
-@pytest.mark.parametrize("algo", [5, 7])
+@pytest.mark.parametrize("algo", _algos([5, 7]))
 @pytest.mark.parametrize("low", [0, 1024, 50000, -1])
 def test_two_kernel_replay_low_part(low, algo):
     """algos 5 and 7 can keep the first `low` positions of every label array in shared memory: same permutations for any split."""
@@ -231,7 +248,7 @@ def test_two_kernel_replay_low_part(low, algo):
     np.testing.assert_array_equal(plan.shuffled_labels(0, 5), ref.shuffle_labels(base, st, lib, 3))
 
 
-@pytest.mark.parametrize("algo", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("algo", _algos([0, 1, 2, 3, 4, 5, 6, 7]))
 def test_shuffle_library_groups(algo):
     n = 4000
     g = synth.hex_graph(40, 100)
@@ -396,3 +413,37 @@ def test_buffered_generator_states_are_rejected():
     plan.upload(spawn_states(1, 4))  # the handle stays usable
     assert plan.permute(spawn_states(1, 4)).shape == (4, 3, 3)
     plan.close()
+
+
+@pytest.mark.skipif(VARIANT_RUN, reason="already inside the cross-check run")
+def test_superseded_replay_variants_cross_check():
+    """The five superseded exact-replay variants (serial, large-window CTA, two-warp pipeline, ordered two-kernel, fused list
+    kernel) must produce numpy's permutations too: independent implementations of the same replay agreeing bit for bit is the
+    strongest check the product kernels have.  They are compiled into a test-only build, loaded here in a subprocess."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "tests", "native", "libsquidpy_b200_testvariants.so")
+    assert os.path.exists(lib), "build it with `make -C squidpy_b200/csrc testvariants` (done by __graft_entry__.build())"
+    env = dict(os.environ, SQB_LIB_PATH=lib, SQB_VARIANT_TESTS="1")
+    sel = "shuffle_is_numpy_exact or uint16_labels or target_generation or list_replay or low_part or library_groups"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-p", "no:cacheprovider", "-x", "-k", sel],
+                       env=env, capture_output=True, text=True, timeout=1700, cwd=root)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0, tail
+    import re
+
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert m and int(m.group(1)) >= 200, tail
+
+
+def test_product_library_rejects_superseded_variants():
+    if VARIANT_RUN:
+        pytest.skip("test build")
+    g = synth.hex_graph(12, 12)
+    plan = _plan(g, 4)
+    plan.set_base(np.random.default_rng(0).integers(0, 4, g.shape[0]).astype(np.uint32))
+    for algo in (0, 3, 4, 5, 6):
+        plan.set_option("shuffle_algo", algo)
+        with pytest.raises(NotImplementedError, match="test build"):
+            plan.permute(spawn_states(1, 3))
+    plan.set_option("shuffle_algo", -1)
+    assert plan.permute(spawn_states(1, 3)).shape == (3, 4, 4)

@@ -22,18 +22,29 @@ for st in $STAGES; do
       timeout 500 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_nhood.py -q -p no:cacheprovider -x -k "(shuffle_is_numpy_exact and 7-1024-2 and (70001 or 33)) or (library_groups and 7) or count_symmetric" > $OUT/sanitizer_memcheck2.log 2>&1; echo "memcheck nhood rc=$?" | tee -a $OUT/summary.txt
       tail -n 3 $OUT/sanitizer_memcheck.log $OUT/sanitizer_synccheck.log $OUT/sanitizer_memcheck2.log ;;
     bench)
-      timeout 1500 python bench.py --steps 5 --warmup 3 --all > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/summary.txt
+      timeout 1500 python bench.py --steps 20 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/summary.txt
       tail -c 6000 $OUT/bench.json; tail -n 20 $OUT/bench.err ;;
     ncu)
-      timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 1 --skip-cpu --skip-moran > $OUT/ncu_bench.log 2>&1; echo "ncu-list rc=$?" | tee -a $OUT/summary.txt ;;
+      timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 1 --skip-cpu --skip-moran --skip-pairs > $OUT/ncu_bench.log 2>&1; echo "ncu-list rc=$?" | tee -a $OUT/summary.txt ;;
     tune)
       timeout 900 python tools/tune_nhood.py 1000 > $OUT/tune_nhood.log 2>&1; echo "tune rc=$?" | tee -a $OUT/summary.txt
       cat $OUT/tune_nhood.log | tail -40 ;;
     ncufull)
-      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"nhood_apply_list|nhood_jgen|nhood_shuffle_warp|nhood_count_kernel|nhood_transpose" -c 4 -f -o $OUT/prof_nhood python bench.py --steps 1 --warmup 0 --perms 1000 --skip-cpu --skip-moran > $OUT/ncu_full.log 2>&1; echo "ncu-full nhood rc=$?" | tee -a $OUT/summary.txt
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ac_scatter_kernel|ac_main_kernel" -s 2 -c 2 -f -o $OUT/prof_moran python tools/prof_targets.py moran > $OUT/ncu_moran.log 2>&1; echo "ncu-full moran rc=$?" | tee -a $OUT/summary.txt
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"nhood_apply_list|nhood_jgen|nhood_count_kernel|nhood_transpose|nhood_philox_labels" -c 6 -f -o $OUT/prof_nhood python tools/philox_time.py 1000 > $OUT/ncu_full.log 2>&1; echo "ncu-full nhood rc=$?" | tee -a $OUT/summary.txt
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ac_sparse_kernel|ac_rank_sort|ac_coltranspose" -c 4 -f -o $OUT/prof_moran python tools/prof_targets.py moran > $OUT/ncu_moran.log 2>&1; echo "ncu-full moran rc=$?" | tee -a $OUT/summary.txt
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:"pairs_kernel" -c 1 -f -o $OUT/prof_cooc python tools/prof_targets.py cooc > $OUT/ncu_cooc.log 2>&1; echo "ncu-full cooc rc=$?" | tee -a $OUT/summary.txt
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"pairs_kernel" -c 1 -f -o $OUT/prof_ripley python tools/prof_targets.py ripley > $OUT/ncu_ripley.log 2>&1; echo "ncu-full ripley rc=$?" | tee -a $OUT/summary.txt ;;
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"pairs_kernel" -c 1 -f -o $OUT/prof_ripley python tools/prof_targets.py ripley > $OUT/ncu_ripley.log 2>&1; echo "ncu-full ripley rc=$?" | tee -a $OUT/summary.txt
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"graph_knn_kernel|sepal_kernel|ligrec_group_means" -c 3 -f -o $OUT/prof_misc python tools/prof_targets.py misc > $OUT/ncu_misc.log 2>&1; echo "ncu-full misc rc=$?" | tee -a $OUT/summary.txt
+      # the reports together exceed what gpurun brings back (64 MiB): summarise them HERE (ncu is on the box) and drop them
+      mkdir -p $OUT/profiles
+      python tools/summarize_profiles.py r02 gpurun_out/profiles > $OUT/summarize.log 2>&1
+      for k in nhood_apply_list nhood_jgen nhood_count_kernel nhood_philox_labels; do python tools/ncu_hotspots.py $OUT/prof_nhood.ncu-rep $k 25 > $OUT/profiles/r02_hotspots_$k.txt 2>&1; done
+      python tools/ncu_hotspots.py $OUT/prof_moran.ncu-rep ac_sparse_kernel 30 > $OUT/profiles/r02_hotspots_ac_sparse_kernel.txt 2>&1
+      python tools/ncu_hotspots.py $OUT/prof_cooc.ncu-rep pairs_kernel 20 > $OUT/profiles/r02_hotspots_pairs_kernel.txt 2>&1
+      python tools/ncu_hotspots.py $OUT/prof_misc.ncu-rep graph_knn_kernel 15 > $OUT/profiles/r02_hotspots_graph_knn_kernel.txt 2>&1
+      python tools/ncu_hotspots.py $OUT/prof_misc.ncu-rep sepal_kernel 15 > $OUT/profiles/r02_hotspots_sepal_kernel.txt 2>&1
+      rm -f $OUT/prof_nhood.ncu-rep $OUT/prof_cooc.ncu-rep $OUT/prof_ripley.ncu-rep $OUT/prof_misc.ncu-rep
+      ls -la $OUT/profiles ;;
   esac
 done
 cat $OUT/summary.txt

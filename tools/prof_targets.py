@@ -28,6 +28,21 @@ elif target == "ripley":
     sup = np.linspace(0, 7000, 50)
     c = pair_counts([pts[lab == k] for k in range(12)], sup, ctx=ctx)
     print("ripley ok", int(c[:, -1].sum()))
+elif target == "misc":
+    # one launch each of the kNN search (1M points, k=6), the sepal diffusion (71x71 lattice, 64 genes) and the ligrec group means
+    import pandas as pd
+    from squidpy_b200.gr import knn_2d, ligrec_analysis, sepal_scores
+    from squidpy_b200.gr._sepal import _compute_idxs
+    d, i = knn_2d(synth.hex_coords(1000, 1000), 6, ctx=ctx)
+    g = synth.hex_graph(71, 71); co = synth.hex_coords(71, 71)
+    rng = np.random.default_rng(0)
+    sat, sat_idx, unsat, unsat_idx = _compute_idxs(g, co, 6)
+    sc = sepal_scores(rng.random((g.shape[0], 64)) * rng.integers(1, 6, 64), sat, sat_idx, unsat, unsat_idx, max_neighs=6, n_iter=2000, ctx=ctx)
+    x = rng.poisson(0.8, (50000, 256)).astype(np.float64); cl = rng.integers(0, 12, 50000)
+    df = pd.DataFrame(x, columns=list(range(256))); df["clusters"] = pd.Categorical(cl, categories=list(range(12)))
+    inter = np.stack([rng.integers(0, 256, 500), rng.integers(0, 256, 500)], 1); cp = np.array([(a, b) for a in range(12) for b in range(12)])
+    r = ligrec_analysis(df, inter, cp, threshold=0.05, n_perms=200, seed=1, ctx=ctx)
+    print("misc ok", int(i.sum()), float(np.nanmean(sc)), float(np.nanmean(r.pvalues)))
 elif target == "shuffle":
     # nhood shuffle kernel alone at the headline shape: python tools/prof_targets.py shuffle P key=value ...
     from squidpy_b200._rng import spawn_states
