@@ -141,8 +141,8 @@ int sqb_nhood_shuffled_labels(sqb_nhood* h, int64_t p0, int64_t p1, uint32_t* ou
  *   "shuffle_ctas"   persistent grid size = permutations in flight (0 = occupancy x SM count),
  *   "shuffle_stagger_us" start-up stagger of the persistent CTAs, "shuffle_wfactor_x100" window = min(i/4, f*sqrt(i)),
  *   "perm_chunk"     permutations resident at once (read at the next upload), "count_algo" 0 auto / 1 shared-memory histograms /
- *                    2 global atomics, "count_sym" -1 auto (count structurally symmetric graphs from the entries with j >= i) /
- *                    0 always the full CSR, "count_un" CSR rows a warp walks at once in the symmetric count kernel (4 / 6 / 8 / 12),
+ *                    2 global atomics, "count_sym" -1 auto (row-record kernel; structurally symmetric graphs are counted from the entries with j >= i) /
+ *                    0 always the CSR-row kernel on the full CSR, "count_un" row records (three entries each) a warp takes per pass in the count kernel (1 / 2 / 3 / 4),
  *   "count_single"   sqb_nhood_count: 1 dedicated single-vector kernel [default] / 0 the batched kernels (test hook). */
 int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value);
 /* algorithmic bytes per permutation, SURVEY.md 8(d): 4*nnz + 4*(n+1) + 8*n + 4*n_cls^2                   */

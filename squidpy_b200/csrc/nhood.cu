@@ -13,7 +13,8 @@
 //                          per-position lists instead of an ordered replay of conflicting swaps, low part of the array in
 //                          shared memory, next window marked while the current one is resolved (sections 2f-2h; 2a-2e
 //                          are the earlier, bit-identical variants kept as options and cross-checks)
-//   3. nhood_transpose     [P][n] -> [n][PB] (permutation-minor) so that one warp lane = one permutation
+//   3. nhood_transpose     [P][n] -> [PB/32][n + 1][32] (groups of 32 permutations, permutation-minor inside a group) so that
+//                          one warp lane = one permutation and a CTA's labels of consecutive nodes are contiguous
 //   4. nhood_count         CSR neighbour-pair histogram: lane = permutation, warp walks the CSR once for 32
 //                          permutations; lane-private shared-memory histogram columns (bank = lane, no
 //                          conflicts), one flush per CTA; symmetric graphs are walked over j >= i only (3b).
@@ -2103,7 +2104,7 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// 3. transpose [P][stride] -> [n][PB]  (32 permutations x 256 nodes per CTA), optional row scatter through
+// 3. transpose [P][stride] -> [PB/32][n + 1][32]  (32 permutations x 256 nodes per CTA), optional row scatter through
 //    `order` (library-grouped position k -> original node id)
 // ------------------------------------------------------------------------------------------------
 template <typename LT>
@@ -2129,7 +2130,7 @@ __global__ void __launch_bounds__(256) nhood_transpose_kernel(const LT* __restri
         } pack;
 #pragma unroll
         for (int pp = 0; pp < 32; ++pp) pack.e[pp] = tile[pp][tx];
-        uint4* dst = reinterpret_cast<uint4*>(labT + row * PB + pg);
+        uint4* dst = reinterpret_cast<uint4*>(labT + ((int64_t)(pg >> 5) * (n + 1) + row) * 32);  // group-major: [PB/32][n + 1][32]
 #pragma unroll
         for (int k = 0; k < NV; ++k) dst[k] = pack.v[k];
     }
@@ -2147,7 +2148,7 @@ __global__ void __launch_bounds__(256) nhood_transpose_kernel(const LT* __restri
 //     class_of(pi_p(r)) = the last c with cum[c] <= pi_p(r), found through a shared-memory bucket table + a fixed
 //     number of bisection steps instead of a random gather from a 1 MB array.  Shuffling the sorted vector has the same
 //     distribution as shuffling the original.  One lane evaluates 4 consecutive permutations of one position (4
-//     independent dependency chains) and stores 4 labels straight into the permutation-minor matrix labT[node][PB] the
+//     independent dependency chains) and stores 4 labels straight into the group-major matrix labT[PB/32][node][32] the
 //     count kernel reads: fill + target generation + apply + transpose (21 of the 25 ms of the exact mode at 1M x 1000)
 //     collapse into one streaming kernel.  tests/philox_ref.py is the executable specification (numpy, bit-identical);
 //     results are validated statistically against the exact mode.
@@ -2194,7 +2195,7 @@ struct PhiloxSeg {
 };
 
 template <typename LT>
-__global__ void __launch_bounds__(256) nhood_philox_labels_kernel(LT* __restrict__ labT, int PB, PhiloxSeg sg,
+__global__ void __launch_bounds__(256) nhood_philox_labels_kernel(LT* __restrict__ labT, int PB, int64_t n_nodes, PhiloxSeg sg,
                                                                   const uint32_t* __restrict__ cum, int C,
                                                                   const uint32_t* __restrict__ bucket,
                                                                   const uint32_t* __restrict__ order, uint64_t seed, int64_t perm0,
@@ -2252,7 +2253,7 @@ __global__ void __launch_bounds__(256) nhood_philox_labels_kernel(LT* __restrict
             }
             cls[q] = lo;
         }
-        LT* dst = labT + node * PB + p4;
+        LT* dst = labT + ((int64_t)(p4 >> 5) * (n_nodes + 1) + node) * 32 + (p4 & 31);
         if (sizeof(LT) == 1) {
             *reinterpret_cast<uint32_t*>(dst) = cls[0] | (cls[1] << 8) | (cls[2] << 16) | (cls[3] << 24);
         } else {
@@ -2339,12 +2340,49 @@ __global__ void nhood_upper_fill_kernel(const uint32_t* __restrict__ indptr, con
     }
 }
 
+// 3c. Row records for the count kernel: {i, j0, j1, j2} (16 bytes) = a row and up to three of its stored columns, unused
+//     slots = n; a row with more entries continues in further records.  One 16-byte load then serves three
+//     (pair x 32 permutations) units and the row label is fetched once per record.  Unused slots name node n: row n of every
+//     group of the label matrix holds the label n_cls, whose histogram column is a spare that is never flushed -- the
+//     kernel needs no predicate for them.  Built from the entries with j >= i of a
+//     symmetric graph (self loops stay in: they are over-counted by one in the symmetrised flush and taken off again by
+//     nhood_count_selfloops_kernel, which only runs for graphs that have any) or from all entries of any other graph.
+__global__ void nhood_rec_count_kernel(const uint32_t* __restrict__ ptr, int64_t n, uint32_t* __restrict__ cnt) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i > n) return;
+    cnt[i] = (i < n) ? (ptr[i + 1] - ptr[i] + 2u) / 3u : 0u;
+}
+
+__global__ void nhood_rec_fill_kernel(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ idx, int64_t n,
+                                      const uint32_t* __restrict__ rptr, uint4* __restrict__ recs, uint32_t* __restrict__ n_self) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t b = ptr[i], e = ptr[i + 1];
+    uint32_t w = rptr[i], self = 0;
+    for (uint32_t k = b; k < e; k += 3) {
+        uint4 r = make_uint4((uint32_t)i, idx[k], (uint32_t)n, (uint32_t)n);  // unused slot = the spare row n of the label matrix
+        if (k + 1 < e) r.z = idx[k + 1];
+        if (k + 2 < e) r.w = idx[k + 2];
+        self += (r.y == (uint32_t)i) + (r.z == (uint32_t)i) + (r.w == (uint32_t)i);
+        recs[w++] = r;
+    }
+    if (self) atomicAdd(n_self, self);
+}
+
+__global__ void nhood_self_fill_kernel(const uint32_t* __restrict__ uptr, const uint32_t* __restrict__ uidx, int64_t n,
+                                       uint32_t* __restrict__ selfnodes, uint32_t* __restrict__ cursor) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (uint32_t k = uptr[i]; k < uptr[i + 1]; ++k)
+        if (uidx[k] == (uint32_t)i) selfnodes[atomicAdd(cursor, 1u)] = (uint32_t)i;  // order is irrelevant (integer adds)
+}
+
 // ------------------------------------------------------------------------------------------------
 // 4. count: hist[(a*C+b)*G + perm_in_group] over the nodes of this CTA's chunk.
 //    G = permutations per CTA; lane = (edge slot = lane / G, perm = lane % G).  With G = 32 every lane owns
 //    its own histogram column (bank == lane): shared-memory atomics never conflict inside a warp.
 // ------------------------------------------------------------------------------------------------
-template <typename LT, int G, bool SYM, int UNROWS = 8>
+template <typename LT, int G, int UNROWS = 8>
 __global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
                                                            const LT* __restrict__ labT, int PB, int64_t n, int C,
                                                            int64_t nodes_per_cta, int P, uint32_t* __restrict__ counts) {
@@ -2363,14 +2401,14 @@ __global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __res
         // ~7 instructions per (edge x 32 permutations), memory-level parallelism UN per warp.
         constexpr int UN = UNROWS;
         const int perm = blockIdx.y * 32 + lane;
-        const LT* __restrict__ col = labT + perm;
-        // all element offsets are 32 x 32 -> 64 bit products (one IMAD.WIDE.U32 each): n < 2^31, PB < 2^31
-        const uint32_t PBu = (uint32_t)PB, Cu = (uint32_t)C;
+        const LT* __restrict__ col = labT + (int64_t)blockIdx.y * (n + 1) * 32 + lane;  // group-major label matrix [PB/32][n + 1][32]
+        // all element offsets are 32 x 32 -> 64 bit products (one IMAD.WIDE.U32 each): n < 2^31
+        const uint32_t PBu = 32u, Cu = (uint32_t)C;
+        (void)perm;
         const uint32_t nb32 = (uint32_t)node_begin, ne32 = (uint32_t)node_end;
         uint32_t* __restrict__ myhist = hist + lane;
         for (uint32_t i0 = nb32 + (uint32_t)warp * UN; i0 < ne32; i0 += (uint32_t)nwarps * UN) {
             uint32_t beg[UN], deg[UN], rowb[UN];
-            uint32_t rowa[UN];  // SYM: label of the row itself, for the mirrored increment (b, a)
             uint32_t maxdeg = 0, mindeg = 0xFFFFFFFFu;
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
@@ -2378,12 +2416,10 @@ __global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __res
                 beg[u] = 0;
                 deg[u] = 0;
                 rowb[u] = 0;
-                rowa[u] = 0;
                 if (i < ne32) {
                     beg[u] = indptr[i];
                     deg[u] = indptr[i + 1] - beg[u];
-                    rowa[u] = (uint32_t)col[(uint64_t)i * PBu];
-                    rowb[u] = rowa[u] * Cu;
+                    rowb[u] = (uint32_t)col[(uint64_t)i * PBu] * Cu;
                 }
                 maxdeg = deg[u] > maxdeg ? deg[u] : maxdeg;
                 mindeg = deg[u] < mindeg ? deg[u] : mindeg;
@@ -2399,11 +2435,6 @@ __global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __res
                 for (int u = 0; u < UN; ++u) bl[u] = (uint32_t)col[(uint64_t)j[u] * PBu];
 #pragma unroll
                 for (int u = 0; u < UN; ++u) atomicAdd(myhist + (rowb[u] + bl[u]) * 32u, 1u);
-                if (SYM) {  // mirrored entry of every j > i (j == i, a self loop, is stored once); the test is warp uniform
-#pragma unroll
-                    for (int u = 0; u < UN; ++u)
-                        if (j[u] != i0 + u) atomicAdd(myhist + (bl[u] * Cu + rowa[u]) * 32u, 1u);
-                }
             }
             for (; k < maxdeg; ++k) {
 #pragma unroll
@@ -2412,7 +2443,6 @@ __global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __res
                         const uint32_t j = indices[beg[u] + k];
                         const uint32_t bl = (uint32_t)col[(uint64_t)j * PBu];
                         atomicAdd(myhist + (rowb[u] + bl) * 32u, 1u);
-                        if (SYM && j != i0 + u) atomicAdd(myhist + (bl * Cu + rowa[u]) * 32u, 1u);
                     }
                 }
             }
@@ -2422,15 +2452,15 @@ __global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __res
         const int sub = lane / G, pl = lane % G;
         const int perm = blockIdx.y * G + pl;
         const bool valid = perm < P;
-        const LT* __restrict__ col = labT + perm;  // column of this lane's permutation (padded columns exist up to PB)
+        const LT* __restrict__ col = labT + (int64_t)(perm >> 5) * (n + 1) * 32 + (perm & 31);  // padded columns exist up to PB
         for (int64_t i = node_begin + warp; i < node_end; i += nwarps) {
             const uint32_t beg = indptr[i], end = indptr[i + 1];
-            const uint32_t a = (uint32_t)col[i * PB];
+            const uint32_t a = (uint32_t)col[i * 32];
             const uint32_t rowbase = a * (uint32_t)C;
 #pragma unroll 4
             for (uint32_t e = beg + sub; e < end; e += EPW) {
                 const uint32_t j = indices[e];
-                const uint32_t b = (uint32_t)col[(int64_t)j * PB];
+                const uint32_t b = (uint32_t)col[(int64_t)j * 32];
                 if (valid) atomicAdd(&hist[(rowbase + b) * G + pl], 1u);
             }
         }
@@ -2441,6 +2471,163 @@ __global__ void __launch_bounds__(1024) nhood_count_kernel(const uint32_t* __res
         const uint32_t v = hist[i];
         const int p = blockIdx.y * G + (i % G);
         if (v != 0 && p < P) atomicAdd(&counts[(int64_t)p * CC + (i / G)], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4b. count from the row records (3c).  Directed graphs: one increment (l_i, l_j) per stored entry (MIRROR = false).
+//     Structurally symmetric graphs (MIRROR = true): per unordered pair {i, j} the full count is +1 on (l_i, l_j) and +1 on
+//     (l_j, l_i): the kernel makes ONE increment, U[l_i][l_j], per stored entry with j >= i and adds the mirror when the
+//     histogram is flushed (counts += U + U^T; a self loop lands twice on the diagonal and is taken off once by
+//     nhood_count_selfloops_kernel).  lane = permutation, every lane owns its histogram column (bank == lane): the
+//     shared-memory reductions of a warp never conflict.
+//     What bounds it (tools/micro/smem_bench.cu, ncu): the SM's single load/store pipe takes ~1.85 cycles per warp
+//     instruction, global load or shared-memory reduction alike -- not the reduction itself (1.87 cycles) and not DRAM.  So the
+//     kernel minimises LSU instructions per (entry x 32 permutations): one 16-byte record load per three entries, the row
+//     label once per record, one label load and one reduction per entry = 2.67 (CSR-row kernel of rounds 1-2: 2 reductions,
+//     1.3 label loads and an index load per entry + a branch, 21 instructions, 4.2 ms at 1M spots x 1000 permutations;
+//     flat (i, j) pairs: 3.5).  A warp takes UN records per pass, software-pipelined three deep: while the reductions of
+//     group k issue, the label loads of group k+1 and the record loads of group k+2 are in flight (one CTA of 32 warps per
+//     SM: without the pipeline 67% of the stall samples were label addresses waiting for the index load).
+// ------------------------------------------------------------------------------------------------
+// label load straight into a 32-bit register (ld.u8 / ld.u16 zero-extend: no cvt + mask after the load); the address is one
+// 32 x 32 + 64 bit multiply-add (node_bytes is kept opaque by the caller so that it is not strength-reduced into two shifts)
+template <typename LT>
+__device__ __forceinline__ uint32_t sqb_ld_label_u32(unsigned long long base, uint32_t node, uint32_t node_bytes);
+template <>
+__device__ __forceinline__ uint32_t sqb_ld_label_u32<uint8_t>(unsigned long long base, uint32_t node, uint32_t node_bytes) {
+    uint32_t v;
+    asm volatile("{\n .reg .u64 a;\n mad.wide.u32 a, %1, %3, %2;\n ld.global.nc.u8 %0, [a];\n}" : "=r"(v) : "r"(node), "l"(base), "r"(node_bytes));
+    return v;
+}
+template <>
+__device__ __forceinline__ uint32_t sqb_ld_label_u32<uint16_t>(unsigned long long base, uint32_t node, uint32_t node_bytes) {
+    uint32_t v;
+    asm volatile("{\n .reg .u64 a;\n mad.wide.u32 a, %1, %3, %2;\n ld.global.nc.u16 %0, [a];\n}" : "=r"(v) : "r"(node), "l"(base), "r"(node_bytes));
+    return v;
+}
+// one reduction on this lane's counter of bin (l_i, l_j): rowaddr = l_i * bytes per histogram row + the lane's column.  The
+// histogram rows have C + 1 columns: unused record slots name the spare row of the label matrix, carry the label C and land
+// in the spare column, which is never flushed -- no predicate anywhere (ptxas wraps a predicated ATOMS into a four-instruction
+// convergence region).
+__device__ __forceinline__ void sqb_hist_inc(uint32_t rowaddr, uint32_t lb) {
+    asm volatile("{\n .reg .u32 a;\n mad.lo.u32 a, %1, 128, %0;\n red.shared.add.u32 [a], 1;\n}" ::"r"(rowaddr), "r"(lb));
+}
+
+template <typename LT, int UN, bool MIRROR>
+__global__ void __launch_bounds__(1024) nhood_count_recs_kernel(const uint4* __restrict__ recs, int64_t n_recs,
+                                                                const LT* __restrict__ labT, int64_t n, int C,
+                                                                int64_t recs_per_cta, int P, uint32_t* __restrict__ counts) {
+    extern __shared__ __align__(16) uint32_t hist[];
+    const int C1 = C + 1;  // one spare column per histogram row (see sqb_hist_inc)
+    const int nb = C * C1 * 32;
+    {
+        uint4* hz = reinterpret_cast<uint4*>(hist);
+        for (int i = threadIdx.x; i < nb / 4; i += blockDim.x) hz[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // lanes of padded permutations (blockIdx.y * 32 + lane >= P) count into columns nobody reads
+    unsigned long long colp = reinterpret_cast<unsigned long long>(labT + (int64_t)blockIdx.y * (n + 1) * 32 + lane);  // [PB/32][n + 1][32]
+    asm volatile("" : "+l"(colp));  // opaque: every label address stays ONE 32x32+64 multiply-add
+    uint32_t NB = 32u * (uint32_t)sizeof(LT);  // bytes between the labels of consecutive nodes
+    asm volatile("" : "+r"(NB));
+    const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(hist) + (uint32_t)lane * 4u;  // byte address of this lane's column
+    const uint32_t rowmul = (uint32_t)C1 * 128u;                                           // bytes per histogram row ((C + 1) bins x 32 lanes)
+    const int64_t r_begin = (int64_t)blockIdx.x * recs_per_cta;
+    int64_t r_end = r_begin + recs_per_cta;
+    if (r_end > n_recs) r_end = n_recs;
+    const int64_t r_full = r_begin + ((r_end - r_begin) / UN) * UN;  // whole groups of UN records
+    const int64_t step = (int64_t)nwarps * UN;
+    const int64_t r_first = r_begin + (int64_t)warp * UN;
+    const int n_it = r_first < r_full ? (int)((r_full - 1 - r_first) / step) + 1 : 0;  // groups of this warp
+    const uint4* __restrict__ pp = recs + r_first;                                     // the group being fetched
+    uint4 rc[UN];
+    uint32_t la[UN], lb[UN][3];
+    auto ld_recs = [&]() {
+#pragma unroll
+        for (int u = 0; u < UN; ++u)  // streamed once: keep the records out of L1, which holds the label sectors
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(rc[u].x), "=r"(rc[u].y), "=r"(rc[u].z), "=r"(rc[u].w)
+                         : "l"(pp + u));
+        pp += step;
+    };
+    auto ld_labels = [&](uint32_t(&xa)[UN], uint32_t(&xb)[UN][3]) {
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            xa[u] = sqb_ld_label_u32<LT>(colp, rc[u].x, NB);
+            xb[u][0] = sqb_ld_label_u32<LT>(colp, rc[u].y, NB);
+            xb[u][1] = sqb_ld_label_u32<LT>(colp, rc[u].z, NB);
+            xb[u][2] = sqb_ld_label_u32<LT>(colp, rc[u].w, NB);
+        }
+    };
+    auto reduce = [&](const uint32_t(&xa)[UN], const uint32_t(&xb)[UN][3]) {
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const uint32_t rowaddr = xa[u] * rowmul + hbase;
+            sqb_hist_inc(rowaddr, xb[u][0]);
+            sqb_hist_inc(rowaddr, xb[u][1]);
+            sqb_hist_inc(rowaddr, xb[u][2]);
+        }
+    };
+    if (n_it > 0) {
+        ld_recs();
+        ld_labels(la, lb);
+        if (n_it > 1) ld_recs();
+        // steady state: all three stages are live; unrolled by two so that the label registers of consecutive groups swap
+        // roles instead of being copied
+#pragma unroll 2
+        for (int k = 0; k < n_it - 2; ++k) {
+            uint32_t na[UN], nb2[UN][3];
+            ld_labels(na, nb2);  // group k+1
+            ld_recs();           // group k+2
+            reduce(la, lb);      // group k
+#pragma unroll
+            for (int u = 0; u < UN; ++u) la[u] = na[u], lb[u][0] = nb2[u][0], lb[u][1] = nb2[u][1], lb[u][2] = nb2[u][2];
+        }
+        if (n_it > 1) {
+            uint32_t na[UN], nb2[UN][3];
+            ld_labels(na, nb2);
+            reduce(la, lb);
+#pragma unroll
+            for (int u = 0; u < UN; ++u) la[u] = na[u], lb[u][0] = nb2[u][0], lb[u][1] = nb2[u][1], lb[u][2] = nb2[u][2];
+        }
+        reduce(la, lb);
+    }
+    for (int64_t r = r_full + warp; r < r_end; r += nwarps) {  // fewer than UN records are left
+        const uint4 v = __ldg(recs + r);
+        const uint32_t rowaddr = sqb_ld_label_u32<LT>(colp, v.x, NB) * rowmul + hbase;
+        sqb_hist_inc(rowaddr, sqb_ld_label_u32<LT>(colp, v.y, NB));
+        sqb_hist_inc(rowaddr, sqb_ld_label_u32<LT>(colp, v.z, NB));
+        sqb_hist_inc(rowaddr, sqb_ld_label_u32<LT>(colp, v.w, NB));
+    }
+    __syncthreads();
+    const int CC = C * C;
+    for (int i = threadIdx.x; i < CC * 32; i += blockDim.x) {
+        const int bin = i >> 5, l = i & 31;
+        const int a = bin / C, b = bin - a * C;
+        const uint32_t v = MIRROR ? hist[((a * C1 + b) << 5) + l] + hist[((b * C1 + a) << 5) + l] : hist[((a * C1 + b) << 5) + l];  // U[a][b] + U[b][a]
+        const int p = blockIdx.y * 32 + l;
+        if (v != 0 && p < P) atomicAdd(&counts[(int64_t)p * CC + bin], v);
+    }
+}
+
+// row n of every group of the label matrix = label n_cls ("no node": the unused slots of the row records point here)
+template <typename LT>
+__global__ void nhood_spare_row_kernel(LT* __restrict__ labT, int64_t n, int PB, int C) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < PB) labT[((int64_t)(p >> 5) * (n + 1) + n) * 32 + (p & 31)] = (LT)C;
+}
+
+// a self loop (i, i) is ONE stored entry: +1 on (l_i, l_i); the symmetrised flush above gave it 2
+template <typename LT>
+__global__ void nhood_count_selfloops_kernel(const uint32_t* __restrict__ selfnodes, uint32_t n_self, const LT* __restrict__ labT,
+                                             int64_t n, int C, int P, uint32_t* __restrict__ counts) {
+    const int p = blockIdx.y * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    for (uint32_t k = blockIdx.x; k < n_self; k += gridDim.x) {
+        const uint32_t a = (uint32_t)labT[((int64_t)(p >> 5) * (n + 1) + selfnodes[k]) * 32 + (p & 31)];
+        atomicAdd(&counts[(int64_t)p * C * C + a * C + a], 0xFFFFFFFFu);  // -1 (mod 2^32)
     }
 }
 
@@ -2488,13 +2675,13 @@ __global__ void nhood_count_global_kernel(const uint32_t* __restrict__ indptr, c
     const int64_t node_begin = (int64_t)blockIdx.x * nodes_per_cta;
     int64_t node_end = node_begin + nodes_per_cta;
     if (node_end > n) node_end = n;
-    const LT* __restrict__ col = labT + perm;
+    const LT* __restrict__ col = labT + (int64_t)blockIdx.y * (n + 1) * 32 + lane;  // group-major label matrix [PB/32][n + 1][32]
     const int64_t CC = (int64_t)C * C;
     for (int64_t i = node_begin + warp; i < node_end; i += nwarps) {
         const uint32_t beg = indptr[i], end = indptr[i + 1];
-        const uint32_t a = (uint32_t)col[i * PB];
+        const uint32_t a = (uint32_t)col[i * 32];
         for (uint32_t e = beg; e < end; ++e) {
-            const uint32_t b = (uint32_t)col[(int64_t)indices[e] * PB];
+            const uint32_t b = (uint32_t)col[(int64_t)indices[e] * 32];
             if (valid) atomicAdd(&counts[(int64_t)perm * CC + (int64_t)a * C + b], 1u);
         }
     }
@@ -2509,11 +2696,15 @@ struct sqb_nhood {
     int n_cls = 0;
     int lt_bytes = 1;  // 1: uint8 labels (n_cls <= 256), 2: uint16
     DevBuf<uint32_t> d_indptr, d_indices;
-    DevBuf<uint32_t> d_uptr, d_uidx;  // entries with j >= i of a symmetric graph (see 3b), else unused
+    DevBuf<uint32_t> d_uptr, d_uidx;  // entries with j >= i of a symmetric graph (see 3b): only while the pair list is built
+    DevBuf<uint4> d_recs;              // row records (3c) of those entries (symmetric graph) or of all entries: what the count kernel walks
+    DevBuf<uint32_t> d_selfnodes;      // nodes with a stored self loop (usually none)
+    int64_t n_recs = 0;
+    uint32_t n_self = 0;
     bool sym = false;
     int count_sym = -1;  // -1 auto (use the upper CSR when the graph is symmetric), 0 = always the full CSR
     int jgen_threads = 128;  // block size of the swap-target generation kernel (32 / 64 / 128: 1 / 2 / 4 permutations per block)
-    int count_un = 6;    // CSR rows a warp walks at once in the symmetric count kernel (4 / 6 / 8 / 12)
+    int count_un = 4;    // records (of three entries) a warp takes per pass in the count kernel (1 / 2 / 3 / 4)
     DevBuf<uint8_t> d_base;   // stride * lt_bytes, library-grouped order
     DevBuf<uint32_t> d_order;  // grouped position -> node id (only with libraries)
     bool has_order = false;
@@ -2533,7 +2724,7 @@ struct sqb_nhood {
     std::vector<uint32_t> h_grouped;  // base labels in library-grouped order (host copy for the fast-mode tables)
     bool philox_ready = false;
     std::vector<PhiloxSeg> h_pseg;
-    // label matrices [chunk][stride] and [n][PB] live in ctx->scratch[0..1]
+    // label matrices [chunk][stride] and [PB/32][n + 1][32] live in ctx->scratch[0..1]
     DevBuf<uint32_t> d_counts;  // [P][C*C]
     DevBuf<uint32_t> d_tmp_u32;
     std::vector<uint32_t> h_order;
@@ -2586,21 +2777,46 @@ static int launch_count(sqb_nhood* h, const LT* labT, int PB, int P, uint32_t* d
     const int threads = smem > 100 * 1024 ? 1024 : 512;
 #define SQB_COUNT_CASE(GV)                                                                                        \
     case GV: {                                                                                                    \
-        auto k = nhood_count_kernel<LT, GV, false>;                                                               \
+        auto k = nhood_count_kernel<LT, GV>;                                                                      \
         SQB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
         k<<<grid, threads, smem, c->stream>>>(h->d_indptr.p, h->d_indices.p, labT, PB, h->n, C, nodes_per_cta, P, \
                                               d_counts);                                                          \
     } break;
-    if (G == 32 && h->sym && h->count_sym != 0) {  // symmetric graph: walk the entries with j >= i only
-        // rows per warp pass, measured at 1M spots x 1000 permutations: 4 -> 5.9 ms, 6 -> 4.2 ms, 8 -> 4.6 ms, 12 -> 6.5 ms
-        void (*k)(const uint32_t*, const uint32_t*, const LT*, int, int64_t, int, int64_t, int, uint32_t*) =
-            nhood_count_kernel<LT, 32, true, 6>;
-        if (h->count_un == 4) k = nhood_count_kernel<LT, 32, true, 4>;
-        if (h->count_un == 8) k = nhood_count_kernel<LT, 32, true, 8>;
-        if (h->count_un == 12) k = nhood_count_kernel<LT, 32, true, 12>;
-        SQB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, threads, smem, c->stream>>>(h->d_uptr.p, h->d_uidx.p, labT, PB, h->n, C, nodes_per_cta, P, d_counts);
+    if (G == 32 && h->n_recs > 0 && h->count_sym != 0 && (size_t)C * (C + 1) * 128 <= smem_limit) {  // record kernel (4b): mirrored flush for symmetric graphs
+        void (*k)(const uint4*, int64_t, const LT*, int64_t, int, int64_t, int, uint32_t*) = nullptr;
+#define SQB_RECS_PICK(UNV) (h->sym ? nhood_count_recs_kernel<LT, UNV, true> : nhood_count_recs_kernel<LT, UNV, false>)
+        // records per warp pass, measured at 1M spots x 1000 permutations: 1 -> 2.38 ms, 2 -> 1.95, 3 -> 1.57, 4 -> 1.52
+        k = SQB_RECS_PICK(4);
+        if (h->count_un == 1) k = SQB_RECS_PICK(1);
+        if (h->count_un == 2) k = SQB_RECS_PICK(2);
+        if (h->count_un == 3) k = SQB_RECS_PICK(3);
+#undef SQB_RECS_PICK
+        // grid = pchunk x ngroups CTAs, one per SM at a time: aim at ~8 waves and, when a nearby pchunk makes the CTA count a
+        // multiple of the SM count, take it (608 CTAs = 4.1 waves cost a fifth round for 10% of the work)
+        int64_t pchunk = ((int64_t)8 * c->sm_count + ngroups / 2) / ngroups;
+        if (pchunk < 1) pchunk = 1;
+        for (int64_t q = pchunk; q <= 2 * pchunk; ++q)
+            if ((q * ngroups) % c->sm_count == 0) {
+                pchunk = q;
+                break;
+            }
+        const int64_t max_pchunk = ceil_div64(h->n_recs, 1024);
+        if (pchunk > max_pchunk) pchunk = max_pchunk;
+        if (pchunk < 1) pchunk = 1;
+        const int64_t recs_per_cta = ceil_div64(h->n_recs, pchunk);
+        pchunk = ceil_div64(h->n_recs, recs_per_cta);
+        if (pchunk < 1) pchunk = 1;
+        dim3 pgrid((unsigned)pchunk, (unsigned)ngroups);
+        const size_t rsmem = (size_t)C * (C + 1) * 128;  // one spare column per row
+        nhood_spare_row_kernel<LT><<<(unsigned)((PB + 255) / 256), 256, 0, c->stream>>>(const_cast<LT*>(labT), h->n, PB, C);
+        SQB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+        k<<<pgrid, threads, rsmem, c->stream>>>(h->d_recs.p, h->n_recs, labT, h->n, C, recs_per_cta, P, d_counts);
         SQB_POST_LAUNCH();
+        if (h->sym && h->n_self > 0) {
+            dim3 sgrid((unsigned)(h->n_self < 4096 ? h->n_self : 4096), (unsigned)((P + 127) / 128));
+            nhood_count_selfloops_kernel<LT><<<sgrid, 128, 0, c->stream>>>(h->d_selfnodes.p, h->n_self, labT, h->n, C, P, d_counts);
+            SQB_POST_LAUNCH();
+        }
         return SQB_OK;
     }
     switch (G) {
@@ -2937,7 +3153,7 @@ static int run_chunk(sqb_nhood* h, int64_t p0, int64_t np, bool do_count) {
     return SQB_OK;
 }
 
-// fast RNG mode: labels of permutations [p0, p0 + np) straight into labT[n][PB] (one launch per library segment)
+// fast RNG mode: labels of permutations [p0, p0 + np) straight into labT[PB/32][n + 1][32] (one launch per library segment)
 template <typename LT>
 static int philox_labels(sqb_nhood* h, int64_t p0, int64_t np, LT* labT, int PB) {
     sqb_ctx* c = h->ctx;
@@ -2958,7 +3174,7 @@ static int philox_labels(sqb_nhood* h, int64_t p0, int64_t np, LT* labT, int PB)
         gx = ceil_div64(m, pos_per_cta);
         SqbLaunchScope scope(c, SQB_K_NHOOD_SHUFFLE);
         nhood_philox_labels_kernel<LT><<<dim3((unsigned)gx, (unsigned)gy), 256, smem, c->stream>>>(
-            labT, PB, ps, h->d_cum.p + (size_t)sgm * (C + 1), C, h->d_bkt.p + h->h_bkt_off[sgm], h->has_order ? h->d_order.p : nullptr,
+            labT, PB, h->n, ps, h->d_cum.p + (size_t)sgm * (C + 1), C, h->d_bkt.p + h->h_bkt_off[sgm], h->has_order ? h->d_order.p : nullptr,
             h->philox_seed, h->perm_first + p0, pos_per_cta);
         SQB_POST_LAUNCH();
     }
@@ -3052,7 +3268,7 @@ static int nhood_count_batched_path(sqb_nhood* h, const uint32_t* labels, uint32
     cnt.bind(c->stream);
     int rc = SQB_OK;
     if ((rc = h->d_tmp_u32.alloc(h->n)) != SQB_OK) return rc;
-    if ((rc = labT.alloc((size_t)h->n * 32 * h->lt_bytes)) != SQB_OK) return rc;
+    if ((rc = labT.alloc((size_t)(h->n + 1) * 32 * h->lt_bytes)) != SQB_OK) return rc;
     if ((rc = cnt.alloc(CC)) != SQB_OK) {
         labT.release();
         return rc;
@@ -3063,7 +3279,7 @@ static int nhood_count_batched_path(sqb_nhood* h, const uint32_t* labels, uint32
     };
     cudaError_t e;
     e = cudaMemcpyAsync(h->d_tmp_u32.p, labels, h->n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(labT.p, 0, (size_t)h->n * 32 * h->lt_bytes, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(labT.p, 0, (size_t)(h->n + 1) * 32 * h->lt_bytes, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(cnt.p, 0, CC * sizeof(uint32_t), c->stream);
     if (e != cudaSuccess) {
         cleanup();
@@ -3095,7 +3311,45 @@ static int nhood_count_batched_path(sqb_nhood* h, const uint32_t* labels, uint32
 
 static int ensure_buffers(sqb_nhood* h, int64_t chunk) {
     SQB_TRY(h->ctx->scratch[0].alloc((size_t)chunk * h->stride * h->lt_bytes));
-    SQB_TRY(h->ctx->scratch[1].alloc((size_t)h->n * chunk * h->lt_bytes));
+    SQB_TRY(h->ctx->scratch[1].alloc((size_t)(h->n + 1) * chunk * h->lt_bytes));
+    return SQB_OK;
+}
+
+// row records (3c) of the CSR (ptr, idx) into h->d_recs; *n_self = number of stored (i, i) among them
+static int nhood_build_records(sqb_nhood* h, const uint32_t* ptr, const uint32_t* idx, uint32_t* n_self_out) {
+    sqb_ctx* ctx = h->ctx;
+    const int64_t n = h->n;
+    DevBuf<uint32_t> cnt, rptr, cnt_self;
+    DevBuf<uint8_t> tmp;
+    cnt.bind(ctx->stream), rptr.bind(ctx->stream), cnt_self.bind(ctx->stream), tmp.bind(ctx->stream);
+    auto cleanup = [&]() { cnt.release(), rptr.release(), cnt_self.release(), tmp.release(); };
+    int rc;
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)(n + 1), ctx->stream);
+    if ((rc = cnt.alloc(n + 1)) != SQB_OK || (rc = rptr.alloc(n + 1)) != SQB_OK || (rc = cnt_self.alloc(1)) != SQB_OK ||
+        (rc = tmp.alloc(tmp_bytes > 0 ? tmp_bytes : 1)) != SQB_OK) {
+        cleanup();
+        return rc;
+    }
+    nhood_rec_count_kernel<<<(unsigned)ceil_div64(n + 1, 256), 256, 0, ctx->stream>>>(ptr, n, cnt.p);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cnt.p, rptr.p, (int)(n + 1), ctx->stream);
+    uint32_t total = 0, h_self = 0;
+    cudaMemcpyAsync(&total, rptr.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && total > 0 && (rc = h->d_recs.alloc(total)) == SQB_OK) {
+        cudaMemsetAsync(cnt_self.p, 0, sizeof(uint32_t), ctx->stream);
+        nhood_rec_fill_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(ptr, idx, n, rptr.p, h->d_recs.p, cnt_self.p);
+        cudaMemcpyAsync(&h_self, cnt_self.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        e = cudaStreamSynchronize(ctx->stream);
+    }
+    cleanup();
+    if (e != cudaSuccess) {
+        sqb_set_error("sqb_nhood_create: building the row records failed: %s", cudaGetErrorString(e));
+        return SQB_ERR_CUDA;
+    }
+    if (rc != SQB_OK) return rc;
+    h->n_recs = total;
+    *n_self_out = h_self;
     return SQB_OK;
 }
 
@@ -3122,6 +3376,8 @@ int sqb_nhood_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const uint32_t* indpt
     h->d_indices.bind(ctx->stream);
     h->d_uptr.bind(ctx->stream);
     h->d_uidx.bind(ctx->stream);
+    h->d_recs.bind(ctx->stream);
+    h->d_selfnodes.bind(ctx->stream);
     h->d_base.bind(ctx->stream);
     h->d_order.bind(ctx->stream);
     h->d_seg_start.bind(ctx->stream);
@@ -3188,8 +3444,19 @@ int sqb_nhood_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const uint32_t* indpt
             if (e == cudaSuccess && (rc = h->d_uidx.alloc(total > 0 ? total : 1)) == SQB_OK) {
                 nhood_upper_fill_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(h->d_indptr.p, h->d_indices.p, n,
                                                                                               h->d_uptr.p, h->d_uidx.p);
+                // the same entries as row records (3c) + the nodes with a self loop
+                uint32_t h_self = 0;
                 e = cudaStreamSynchronize(ctx->stream);
-                h->sym = (e == cudaSuccess);
+                if (e == cudaSuccess && (rc = nhood_build_records(h, h->d_uptr.p, h->d_uidx.p, &h_self)) == SQB_OK) {
+                    if (h_self > 0 && (rc = h->d_selfnodes.alloc(h_self)) == SQB_OK) {
+                        cudaMemsetAsync(flag.p, 0, sizeof(uint32_t), ctx->stream);
+                        nhood_self_fill_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(h->d_uptr.p, h->d_uidx.p, n,
+                                                                                                     h->d_selfnodes.p, flag.p);
+                        e = cudaStreamSynchronize(ctx->stream);
+                    }
+                    h->n_self = h_self;
+                    h->sym = (e == cudaSuccess && rc == SQB_OK);
+                }
             }
         }
         cleanup();
@@ -3198,7 +3465,17 @@ int sqb_nhood_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const uint32_t* indpt
             sqb_nhood_destroy(h);
             return e != cudaSuccess ? SQB_ERR_CUDA : rc;
         }
-        if (!h->sym) h->d_uptr.release();
+        h->d_uptr.release();  // the count kernel walks the row records; the upper CSR was only their scaffolding
+        h->d_uidx.release();
+        const size_t smem_limit = ctx->smem_optin > 8192 ? ctx->smem_optin - 4096 : 40000;
+        if (!h->sym && (size_t)n_cls * n_cls * 128 <= smem_limit && nnz < ((int64_t)1 << 31)) {
+            // directed / irregular graph: row records of every stored entry, same kernel without the mirrored flush
+            uint32_t unused = 0;
+            if (nhood_build_records(h, h->d_indptr.p, h->d_indices.p, &unused) != SQB_OK) {
+                h->d_recs.release();  // not fatal: the CSR-row kernel counts without them
+                h->n_recs = 0;
+            }
+        }
     }
     SQB_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = h;
@@ -3212,6 +3489,8 @@ int sqb_nhood_destroy(sqb_nhood* h) {
     h->d_indices.release();
     h->d_uptr.release();
     h->d_uidx.release();
+    h->d_recs.release();
+    h->d_selfnodes.release();
     h->d_base.release();
     h->d_order.release();
     h->d_seg_start.release();
@@ -3234,7 +3513,7 @@ int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value) {
         SQB_CHECK(value == 32 || value == 64 || value == 128, SQB_ERR_INVALID, "jgen_threads must be 32, 64 or 128");
         h->jgen_threads = (int)value;
     } else if (!strcmp(key, "count_un")) {
-        SQB_CHECK(value == 4 || value == 6 || value == 8 || value == 12, SQB_ERR_INVALID, "count_un must be 4, 6, 8 or 12");
+        SQB_CHECK(value >= 1 && value <= 4, SQB_ERR_INVALID, "count_un must be 1, 2, 3 or 4");
         h->count_un = (int)value;
     } else if (!strcmp(key, "count_single")) {
         h->count_single = value != 0;
@@ -3430,7 +3709,7 @@ int sqb_nhood_permute_upload_philox(sqb_nhood* h, uint64_t seed, int64_t first_p
     SQB_TRY(h->d_counts.alloc((size_t)n_perms * h->n_cls * h->n_cls));
     int64_t chunk = auto_chunk(h);
     if (chunk > ((n_perms + 31) / 32) * 32) chunk = ((n_perms + 31) / 32) * 32;
-    SQB_TRY(c->scratch[1].alloc((size_t)h->n * chunk * h->lt_bytes));  // labT only: nothing permutation-major exists in this mode
+    SQB_TRY(c->scratch[1].alloc((size_t)(h->n + 1) * chunk * h->lt_bytes));  // labT only: nothing permutation-major exists in this mode
     h->n_perms = n_perms;
     h->chunk = chunk;
     h->rng_mode = 1;
@@ -3454,7 +3733,7 @@ int sqb_nhood_permute_run_async(sqb_nhood* h) {
     if (h->rng_mode == 0)
         SQB_TRY(ensure_buffers(h, chunk));
     else
-        SQB_TRY(c->scratch[1].alloc((size_t)h->n * chunk * h->lt_bytes));
+        SQB_TRY(c->scratch[1].alloc((size_t)(h->n + 1) * chunk * h->lt_bytes));
     for (int64_t p0 = 0; p0 < h->n_perms; p0 += chunk) {
         int64_t np = h->n_perms - p0 < chunk ? h->n_perms - p0 : chunk;
         if (h->rng_mode == 1) {
@@ -3799,8 +4078,8 @@ int sqb_nhood_shuffled_labels(sqb_nhood* h, int64_t p0, int64_t p1, uint32_t* ou
     sqb_ctx* c = h->ctx;
     SQB_CUDA(cudaSetDevice(c->device));
     if (h->rng_mode == 1) {  // fast mode: 32 permutations at a time through labT[n][32]
-        SQB_TRY(c->scratch[1].alloc((size_t)h->n * h->chunk * h->lt_bytes));
-        std::vector<uint8_t> host((size_t)h->n * 32 * h->lt_bytes);
+        SQB_TRY(c->scratch[1].alloc((size_t)(h->n + 1) * h->chunk * h->lt_bytes));
+        std::vector<uint8_t> host((size_t)h->n * 32 * h->lt_bytes);  // group 0 rows [0, n); row n is the spare row
         for (int64_t q0 = p0; q0 < p1; q0 += 32) {
             const int64_t np = p1 - q0 < 32 ? p1 - q0 : 32;
             if (h->lt_bytes == 1)
