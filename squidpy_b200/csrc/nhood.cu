@@ -2104,6 +2104,323 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2i. REGION replay (shuffle_algo 8): the apply step of the two-kernel replay with EVERY random access in shared memory.
+//     tools/micro/smem_bench.cu on B200: a random byte read + write costs 5.3 cycles per warp in the CTA's own shared
+//     memory, 135 in distributed shared memory of a cluster and 230 against an L2-resident global array -- the list kernel
+//     (2h) spends most of its time on the two thirds of its targets that miss its shared-memory low part.  A 1 MB label
+//     array does not fit one SM, but Fisher-Yates only ever moves a label DOWN-or-into a target j <= i, so the array can
+//     be processed one REGION [lo, hi) of <= ~160 K positions at a time, top region first, each step exactly once, in the
+//     pass of the region its target falls into:
+//       pass of region r:  slab <- a[lo, hi)                                    (coalesced)
+//         phase X  steps i = m-1 .. hi (tops above the region) whose target lies in [lo, hi): the J values are scanned
+//                  (coalesced), the matching steps compacted in step order into windows of <= W, and applied as
+//                  v = slab[j]; slab[j] = a[i]; a[i] = v.  a[i] still holds T(i), the value position i had just before
+//                  step i: the pass of i's own region left it there (below), and no pass in between touches it.
+//         phase Y  steps i = hi-1 .. lo (tops inside the region): windows of W consecutive steps exactly as in 2h (own-range
+//                  lists, duplicate filter, hash lists), every access in the slab.  A step whose target lies BELOW the
+//                  region is not applied here: it only leaves T(i) at its top for the pass that owns its target.
+//         a[lo, hi) <- slab                                                      (coalesced)
+//     Conflicts inside a window are resolved with the lists of 2g/2h (original values only, no ordered pass); in phase X
+//     tops are never targets, so only the duplicate-target lists remain.  Cost besides the resolution: the J row is
+//     re-scanned once per region above the target region, (R-1)/2 extra passes over J for R regions (streaming).
+// ------------------------------------------------------------------------------------------------
+template <typename LT, int NT, int SPT>
+__global__ void __launch_bounds__(NT, 1) nhood_apply_region_kernel(LT* __restrict__ labels, const uint32_t* __restrict__ J,
+                                                                   int64_t stride, int64_t n_perms, int nseg,
+                                                                   const int64_t* __restrict__ seg_start,
+                                                                   const int64_t* __restrict__ seg_len, uint32_t full_mask,
+                                                                   uint64_t stagger_ns, int region_cap) {
+    constexpr int W = NT * SPT;  // steps per window
+    constexpr int HS = W;        // hash slots: only steps of multiply-hit buckets are inserted
+    constexpr int NWB = 2 * W;   // filter words (16 buckets of 2 bits each)
+    constexpr int NWARP = NT / 32;
+    constexpr int KMAX = 8;      // phase X: J values scanned per thread and chunk
+    constexpr int LOG_HS = (HS == 512 ? 9 : HS == 1024 ? 10 : HS == 2048 ? 11 : HS == 4096 ? 12 : HS == 8192 ? 13 : 14);
+    static_assert(HS == (1 << LOG_HS), "HS must be a power of two");
+    static_assert(W < 0xFFFF, "step indices are stored in 16 bits");
+    static_assert(NWARP <= 32, "one warp scans the warp totals");
+    constexpr int HS_SHIFT = 32 - LOG_HS;
+    extern __shared__ __align__(16) unsigned char sqb_shuffle_smem[];
+    unsigned long long* s_tab = reinterpret_cast<unsigned long long*>(sqb_shuffle_smem);  // [HS] (target << 32) | list head
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_tab + HS);                            // [NWB] duplicate filter
+    uint32_t* s_ohead = s_bits + NWB;                                                      // [W] own-range list heads
+    uint32_t* s_qi = s_ohead + W;                                                          // [W] phase X: top position of a slot
+    uint32_t* s_qj = s_qi + W;                                                             // [W] phase X: target - lo of a slot
+    uint32_t* s_wsum = s_qj + W;                                                           // [64] matches per warp
+    uint16_t* s_next = reinterpret_cast<uint16_t*>(s_wsum + 64);                           // [W] list links
+    LT* s_otop = reinterpret_cast<LT*>(s_next + W);                                        // [W] original top values
+    LT* s_slab = s_otop + W;                                                               // [region_cap] the region
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int h = tid; h < HS; h += NT) s_tab[h] = SQB_EMPTY64;
+    for (int w = tid; w < NWB; w += NT) s_bits[w] = 0u;
+    for (int w = tid; w < W; w += NT) s_ohead[w] = SQB_NONE32;
+    sqb_stagger(stagger_ns * blockIdx.x / gridDim.x);
+    __syncthreads();
+
+    // duplicate filter: "seen" / "seen again" bits of the bucket of target jl (2h)
+    auto mark_target = [&](uint32_t jl) {
+        const uint32_t sh = (jl & 15u) * 2u;
+        uint32_t* wp = &s_bits[(jl >> 4) & (NWB - 1)];
+        const uint32_t old = atomicOr(wp, 1u << sh);
+        if ((old >> sh) & 1u) atomicOr(wp, 2u << sh);
+    };
+    auto seen_again = [&](uint32_t jl) -> bool { return (s_bits[(jl >> 4) & (NWB - 1)] >> ((jl & 15u) * 2u + 1u)) & 1u; };
+    // push step s on the list of target jl in the hash table; returns the table slot
+    auto hash_push = [&](uint32_t jl, int s) -> uint32_t {
+        uint32_t h = (jl * 2654435761u) >> HS_SHIFT;
+        const unsigned long long mine = ((unsigned long long)jl << 32) | (unsigned)s;
+        uint32_t nxt = SQB_NONE16;
+        while (true) {
+            const unsigned long long prev = atomicCAS(&s_tab[h], SQB_EMPTY64, mine);
+            if (prev == SQB_EMPTY64) break;
+            if ((uint32_t)(prev >> 32) == jl) {  // same target: push in front of the current head
+                if (atomicCAS(&s_tab[h], prev, mine) == prev) {
+                    nxt = (uint32_t)prev & 0xFFFFu;
+                    break;
+                }
+                continue;
+            }
+            h = (h + 1) & (HS - 1);
+        }
+        s_next[s] = (uint16_t)nxt;
+        return h;
+    };
+
+    for (int64_t perm = blockIdx.x; perm < n_perms; perm += gridDim.x) {
+        LT* __restrict__ a = labels + perm * stride;
+        const uint32_t* __restrict__ Jp = J + perm * stride;
+        for (int seg = 0; seg < nseg; ++seg) {
+            const int64_t base = seg_start[seg];
+            const int m = (int)seg_len[seg];  // n < 2^31
+            if (m < 2) continue;
+            const int R = (m + region_cap - 1) / region_cap;
+            const int B = (((m + R - 1) / R + 15) / 16) * 16;  // balanced regions, <= region_cap (a multiple of 16)
+            for (int r = (m - 1) / B; r >= 0; --r) {
+                const int lo = r * B;
+                const int len = min(B, m - lo);
+                const int hi = lo + len;
+                for (int x = tid; x < len; x += NT) s_slab[x] = a[base + lo + x];
+                __syncthreads();
+                // ---------------- phase X: tops above the region, targets inside ----------------
+                int i_cur = m - 1;
+                while (i_cur >= hi) {
+                    const int avail = i_cur - hi + 1;
+                    int K = KMAX;  // expected matches NT*K*len/(i_cur+1), kept 15% below W
+                    while (K > 1 && (int64_t)NT * K * len * 23 > (int64_t)W * ((int64_t)i_cur + 1) * 20) K >>= 1;
+                    uint32_t jv[KMAX], rk[KMAX];
+                    uint32_t mbits, total, wbase;
+                    int SC;
+                    while (true) {
+                        SC = min(NT * K, avail);
+                        uint32_t cnt = 0;
+                        mbits = 0;
+#pragma unroll
+                        for (int k = 0; k < KMAX; ++k) {
+                            jv[k] = 0, rk[k] = 0;
+                            if (k < K) {  // block-uniform
+                                const int s = warp * 32 * K + k * 32 + lane;
+                                const bool inb = s < SC;
+                                const uint32_t j = inb ? __ldcs(Jp + base + (i_cur - (inb ? s : 0))) : 0u;
+                                const bool mt = inb && (j - (uint32_t)lo) < (uint32_t)len;
+                                const uint32_t b = __ballot_sync(0xffffffffu, mt);
+                                rk[k] = cnt + __popc(b & lt_mask);
+                                cnt += __popc(b);
+                                jv[k] = j;
+                                mbits |= (mt ? 1u : 0u) << k;
+                            }
+                        }
+                        if (lane == 0) s_wsum[warp] = cnt;
+                        __syncthreads();
+                        uint32_t v = lane < NWARP ? s_wsum[lane] : 0u, incl = v;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                            if (lane >= d) incl += t;
+                        }
+                        total = __shfl_sync(0xffffffffu, incl, 31);
+                        wbase = __shfl_sync(0xffffffffu, incl - v, warp);
+                        if (total <= (uint32_t)W) break;
+                        K >>= 1;          // more matches than a window holds: scan half as many steps (K = 1 always fits)
+                        __syncthreads();  // s_wsum is rewritten
+                    }
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) {
+                        if ((mbits >> k) & 1u) {
+                            const uint32_t slot = wbase + rk[k];
+                            const uint32_t jl = jv[k] - (uint32_t)lo;
+                            s_qi[slot] = (uint32_t)(i_cur - (warp * 32 * K + k * 32 + lane));
+                            s_qj[slot] = jl;
+                            mark_target(jl);
+                        }
+                    }
+                    SQB_CONVERGE();
+                    __syncthreads();
+                    // ---- resolve the window of `total` compacted steps (slot order = step order) ----
+                    const int S = (int)total;
+                    uint32_t qi[SPT], qj[SPT], slotv[SPT];
+                    LT vt[SPT], vj[SPT];
+                    uint32_t actm = 0, slowm = 0;
+#pragma unroll
+                    for (int mm = 0; mm < SPT; ++mm) {
+                        const int s = tid + mm * NT;
+                        const bool ac = s < S;
+                        qi[mm] = ac ? s_qi[s] : 0u;
+                        qj[mm] = ac ? s_qj[s] : 0u;
+                        vt[mm] = ac ? ld_cg<LT>(a + base + qi[mm]) : (LT)0;  // T(i): left there by the pass of i's own region
+                        vj[mm] = ac ? s_slab[qj[mm]] : (LT)0;
+                        actm |= (ac ? 1u : 0u) << mm;
+                        slotv[mm] = 0;
+                    }
+#pragma unroll
+                    for (int mm = 0; mm < SPT; ++mm) {
+                        const int s = tid + mm * NT;
+                        if (((actm >> mm) & 1u) && seen_again(qj[mm])) {
+                            slowm |= 1u << mm;
+                            slotv[mm] = hash_push(qj[mm], s);
+                        }
+                    }
+#pragma unroll
+                    for (int mm = 0; mm < SPT; ++mm)
+                        if ((actm >> mm) & 1u) s_otop[tid + mm * NT] = vt[mm];
+                    SQB_CONVERGE();
+                    __syncthreads();
+#pragma unroll
+                    for (int mm = 0; mm < SPT; ++mm) {
+                        const int s = tid + mm * NT;
+                        if ((actm >> mm) & 1u) {
+                            LT val = vj[mm];
+                            bool last = true;  // the only (or the last) step of this window that targets position j
+                            if ((slowm >> mm) & 1u) {
+                                const uint32_t head = (uint32_t)s_tab[slotv[mm]] & 0xFFFFu;
+                                int mx;
+                                const int p = sqb_list_latest_before(s_next, head, s, &mx);
+                                if (p >= 0) val = s_otop[p];  // tops are never targets here: T(p) is p's original top value
+                                last = (mx == s);
+                            }
+                            if (last) s_slab[qj[mm]] = vt[mm];
+                            st_cs<LT>(a + base + qi[mm], val);  // final
+                        }
+                    }
+                    SQB_CONVERGE();
+                    __syncthreads();
+#pragma unroll
+                    for (int mm = 0; mm < SPT; ++mm)
+                        if ((slowm >> mm) & 1u) s_tab[slotv[mm]] = SQB_EMPTY64;
+                    {
+                        uint4* bz = reinterpret_cast<uint4*>(s_bits);
+#pragma unroll
+                        for (int x = tid; x < NWB / 4; x += NT) bz[x] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    __syncthreads();
+                    i_cur -= SC;
+                }
+                // ---------------- phase Y: tops inside the region ----------------
+                const int i_min = max(lo, 1);
+                i_cur = hi - 1;
+                while (i_cur >= i_min) {
+                    const int S = min(W, i_cur - i_min + 1);  // steps i_cur, i_cur-1, ..., i_cur-S+1
+                    const int own_lo = i_cur - S;
+                    uint32_t jv[SPT], slotv[SPT];
+                    LT vj[SPT];
+                    uint32_t inwm = 0, actm = 0, ownm = 0, slowm = 0;
+#pragma unroll
+                    for (int mm = 0; mm < SPT; ++mm) {
+                        const int s = tid + mm * NT;
+                        const bool inw = s < S;
+                        const uint32_t j = inw ? __ldcs(Jp + base + (i_cur - (inw ? s : 0))) : 0u;
+                        const bool ac = inw && (int)j >= lo;  // a target below the region belongs to a later pass
+                        const bool ow = ac && (int)j > own_lo;
+                        jv[mm] = j;
+                        slotv[mm] = 0;
+                        vj[mm] = (LT)0;
+                        inwm |= (inw ? 1u : 0u) << mm;
+                        actm |= (ac ? 1u : 0u) << mm;
+                        ownm |= (ow ? 1u : 0u) << mm;
+                        if (inw) s_otop[s] = s_slab[i_cur - s - lo];
+                        if (ac && !ow) {
+                            vj[mm] = s_slab[j - (uint32_t)lo];
+                            mark_target(j - (uint32_t)lo);
+                        }
+                        if (ow) {
+                            const int u = i_cur - (int)j;  // u >= s
+                            if (u != s) {
+                                const uint32_t prev = atomicExch(&s_ohead[u], (uint32_t)s);
+                                s_next[s] = (uint16_t)prev;  // NONE32 truncates to NONE16
+                            }
+                        }
+                    }
+                    SQB_CONVERGE();
+                    __syncthreads();
+#pragma unroll
+                    for (int mm = 0; mm < SPT; ++mm) {
+                        const int s = tid + mm * NT;
+                        if (((actm >> mm) & 1u) && !((ownm >> mm) & 1u) && seen_again(jv[mm] - (uint32_t)lo)) {
+                            slowm |= 1u << mm;
+                            slotv[mm] = hash_push(jv[mm] - (uint32_t)lo, s);
+                        }
+                    }
+                    SQB_CONVERGE();
+                    __syncthreads();
+#pragma unroll
+                    for (int mm = 0; mm < SPT; ++mm) {
+                        const int s = tid + mm * NT;
+                        if ((inwm >> mm) & 1u) {
+                            const int top_l = i_cur - s - lo;
+                            if ((actm >> mm) & 1u) {
+                                const uint32_t j = jv[mm];
+                                LT val;
+                                if ((ownm >> mm) & 1u) {
+                                    const int u = i_cur - (int)j;
+                                    if (u == s) {
+                                        val = sqb_list_T<LT>(s_ohead, s_next, s_otop, s);
+                                    } else {
+                                        int mx;
+                                        const int p = sqb_list_latest_before(s_next, s_ohead[u], s, &mx);
+                                        val = (p >= 0) ? sqb_list_T<LT>(s_ohead, s_next, s_otop, p) : s_otop[u];
+                                    }
+                                } else {
+                                    bool last = true;
+                                    val = vj[mm];
+                                    if ((slowm >> mm) & 1u) {
+                                        const uint32_t head = (uint32_t)s_tab[slotv[mm]] & 0xFFFFu;
+                                        int mx;
+                                        const int p = sqb_list_latest_before(s_next, head, s, &mx);
+                                        if (p >= 0) val = sqb_list_T<LT>(s_ohead, s_next, s_otop, p);
+                                        last = (mx == s);
+                                    }
+                                    if (last) s_slab[j - (uint32_t)lo] = sqb_list_T_own<LT>(s_ohead, s_next, s_otop, s, s_otop[s]);
+                                }
+                                s_slab[top_l] = val;  // final
+                            } else {
+                                // target below the region: leave T(s) at the top for the pass that owns the target
+                                s_slab[top_l] = sqb_list_T_own<LT>(s_ohead, s_next, s_otop, s, s_otop[s]);
+                            }
+                        }
+                    }
+                    SQB_CONVERGE();
+                    __syncthreads();
+#pragma unroll
+                    for (int mm = 0; mm < SPT; ++mm) {
+                        if ((ownm >> mm) & 1u) s_ohead[i_cur - (int)jv[mm]] = SQB_NONE32;
+                        if ((slowm >> mm) & 1u) s_tab[slotv[mm]] = SQB_EMPTY64;
+                    }
+                    {
+                        uint4* bz = reinterpret_cast<uint4*>(s_bits);
+#pragma unroll
+                        for (int x = tid; x < NWB / 4; x += NT) bz[x] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    __syncthreads();
+                    i_cur -= S;
+                }
+                for (int x = tid; x < len; x += NT) a[base + lo + x] = s_slab[x];
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 3. transpose [P][stride] -> [PB/32][n + 1][32]  (32 permutations x 256 nodes per CTA), optional row scatter through
 //    `order` (library-grouped position k -> original node id)
 // ------------------------------------------------------------------------------------------------
@@ -2734,6 +3051,7 @@ struct sqb_nhood {
     int shuffle_q = 4;     // algo 2: PCG64 outputs per lane per batch (window = 64*q raw values)
     int shuffle_r = 4;     // algo 3: PCG64 outputs per thread per batch (window = 2*r*threads raw values); algo 5: steps per thread
     int64_t shuffle_low = 0;   // algo 5: elements of every label array kept in shared memory (-1 = as much as fits, 0 = off)
+    int64_t shuffle_region = 0;  // algo 8: positions per region (0 = as many as shared memory holds; smaller values are a test hook)
     int64_t shuffle_stagger_us = 0;  // start-up stagger of the persistent shuffle CTAs / warps (see sqb_stagger)
     int shuffle_threads = 512;
     int64_t perm_chunk = 0;  // 0 = auto
@@ -2957,10 +3275,32 @@ static int launch_apply_list(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t n
     return SQB_OK;
 }
 
+template <typename LT, int NT, int SPT>
+static int launch_apply_region(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t np) {
+    sqb_ctx* c = h->ctx;
+    auto k = nhood_apply_region_kernel<LT, NT, SPT>;
+    constexpr size_t W = (size_t)NT * SPT, HS = W, NWB = 2 * W;
+    // [tab u64 x HS][bits u32 x NWB][ohead, qi, qj u32 x W][wsum u32 x 64][next u16 x W][otop LT x W][slab LT x cap]
+    const size_t tables = HS * 8 + NWB * 4 + 3 * W * 4 + 64 * 4 + W * 2 + W * sizeof(LT);
+    SQB_CHECK(tables + 16 * sizeof(LT) <= c->smem_optin, SQB_ERR_UNSUPPORTED, "shuffle_algo 8: %zu bytes of shared memory exceed the device limit", tables);
+    int64_t cap = ((int64_t)c->smem_optin - (int64_t)tables) / (int64_t)sizeof(LT);
+    if (h->shuffle_region > 0 && cap > h->shuffle_region) cap = h->shuffle_region;  // test hook: small regions
+    cap = (cap / 16) * 16;
+    if (cap < 16) cap = 16;
+    const size_t smem = tables + (size_t)cap * sizeof(LT);
+    SQB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = h->shuffle_ctas;
+    if (grid <= 0) grid = c->sm_count;  // one CTA per SM (launch bounds), persistent over the permutations
+    if (grid > np) grid = np;
+    k<<<(unsigned)grid, NT, smem, c->stream>>>(lab, J, h->stride, np, h->nseg, h->d_seg_start.p, h->d_seg_len.p, 0xFFFFFFFFu,
+                                               (uint64_t)h->shuffle_stagger_us * 1000ull, (int)cap);
+    return SQB_OK;
+}
+
 #ifndef SQB_TEST_VARIANTS
 static int sqb_variant_unavailable(int algo) {
     sqb_set_error("shuffle_algo %d is a superseded replay variant kept as a cross-check: it is compiled into the test build only "
-                  "(make -C squidpy_b200/csrc testvariants); the product library offers -1 (auto), 1, 2 and 7", algo);
+                  "(make -C squidpy_b200/csrc testvariants); the product library offers -1 (auto), 1, 2, 7 and 8", algo);
     return SQB_ERR_UNSUPPORTED;
 }
 #endif
@@ -2988,6 +3328,16 @@ static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* stat
     }
     SqbLaunchScope scope(c, SQB_K_NHOOD_SHUFFLE);
     int rc = SQB_ERR_INVALID;
+    if (algo == 8) {
+        if (nt == 1024 && r == 2) rc = launch_apply_region<LT, 1024, 2>(h, lab, J, np);
+        else if (nt == 512 && r == 4) rc = launch_apply_region<LT, 512, 4>(h, lab, J, np);
+        else if (nt == 512 && r == 2) rc = launch_apply_region<LT, 512, 2>(h, lab, J, np);
+        else if (nt == 256 && r == 4) rc = launch_apply_region<LT, 256, 4>(h, lab, J, np);
+        else sqb_set_error("shuffle_algo 8: unsupported (shuffle_threads, shuffle_r) = (%d, %d)", nt, r);
+        SQB_TRY(rc);
+        SQB_POST_LAUNCH();
+        return SQB_OK;
+    }
     if (algo == 7) {
         if (nt == 1024 && r == 4) rc = launch_apply_list<LT, 1024, 4>(h, lab, J, np, low);
         else if (nt == 1024 && r == 2) rc = launch_apply_list<LT, 1024, 2>(h, lab, J, np, low);
@@ -3023,7 +3373,7 @@ static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* stat
 template <typename LT>
 static int launch_shuffle(sqb_nhood* h, LT* lab, const uint64_t* states, int64_t np) {
     sqb_ctx* c = h->ctx;
-    if (h->shuffle_algo == 5 || h->shuffle_algo == 7)
+    if (h->shuffle_algo == 5 || h->shuffle_algo == 7 || h->shuffle_algo == 8)
         return launch_shuffle_two_kernel<LT>(h, lab, states, np, h->shuffle_algo, h->shuffle_threads, h->shuffle_r, h->shuffle_low);
     // auto (measured on B200, 1000 x 1M: two-kernel list replay 23 ms, warp per permutation 39 ms, CTA per permutation
     // 42 ms): many permutations of large arrays -> J generation + list apply with the tuned shape (1024 threads, 2048-step
@@ -3507,7 +3857,7 @@ int sqb_nhood_destroy(sqb_nhood* h) {
 int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value) {
     SQB_CHECK(h && key, SQB_ERR_INVALID, "sqb_nhood_set_option: null argument");
     if (!strcmp(key, "shuffle_algo")) {
-        SQB_CHECK(value >= -1 && value <= 7, SQB_ERR_INVALID, "shuffle_algo must be -1 (auto) or 0..7");
+        SQB_CHECK(value >= -1 && value <= 8, SQB_ERR_INVALID, "shuffle_algo must be -1 (auto) or 0..8");
         h->shuffle_algo = (int)value;
     } else if (!strcmp(key, "jgen_threads")) {
         SQB_CHECK(value == 32 || value == 64 || value == 128, SQB_ERR_INVALID, "jgen_threads must be 32, 64 or 128");
@@ -3526,6 +3876,9 @@ int sqb_nhood_set_option(sqb_nhood* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "shuffle_low")) {
         SQB_CHECK(value >= -1, SQB_ERR_INVALID, "shuffle_low must be >= -1");
         h->shuffle_low = value;
+    } else if (!strcmp(key, "shuffle_region")) {
+        SQB_CHECK(value >= 0, SQB_ERR_INVALID, "shuffle_region must be >= 0");
+        h->shuffle_region = value;
     } else if (!strcmp(key, "shuffle_r")) {
         SQB_CHECK(value == 2 || value == 4 || value == 8, SQB_ERR_INVALID, "shuffle_r must be 2, 4 or 8");
         h->shuffle_r = (int)value;

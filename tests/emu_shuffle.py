@@ -322,3 +322,95 @@ def serial_targets(state, inc, segs):
                     break
             out[(base, i)] = v
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Region replay (shuffle_algo 8, nhood_apply_region_kernel): executable specification
+# ------------------------------------------------------------------------------------------------
+def _resolve_general_window(slab, a, lo, hi, tops, tgts, rng):
+    """One window of the region replay: compacted steps in step order (slot s: top position tops[s], strictly descending;
+    target tgts[s] inside the region [lo, hi)).  A top lies above the region (its value T is read from / its final value is
+    written to `a`) or inside it (slab).  Every step derives what it writes from per-POSITION lists and original values only:
+      targeters[p] = steps with target p (and top != p), owner[p] = the step whose top is p (if it is in this window);
+      T(x) = value of x's top just before step x = T(latest targeter of that top) or its original value;
+      step s writes  top_s <- value of its target just before s = T(latest earlier targeter of it) or the original;
+      the last targeter of p deposits T(itself) at p unless p's owner is in the window (the owner then overwrites p anyway and
+      has taken the deposit through T)."""
+    S = len(tops)
+    otop = [a[tops[s]] if tops[s] >= hi else slab[tops[s] - lo] for s in range(S)]
+    targeters, owner = {}, {}
+    order = list(range(S))
+    rng.shuffle(order)
+    for s in order:
+        if tops[s] < hi:
+            owner[tops[s]] = s
+        if tgts[s] != tops[s]:
+            targeters.setdefault(tgts[s], []).append(s)
+    orig = {p: slab[p - lo] for p in targeters}
+
+    def T(x):
+        while targeters.get(tops[x]):
+            x = max(targeters[tops[x]])
+        return otop[x]
+
+    wa, ws = [], []
+    for s in order:
+        top, p = tops[s], tgts[s]
+        if p == top:
+            val = T(s)
+        else:
+            lst = targeters[p]
+            c = [e for e in lst if e < s]
+            val = T(max(c)) if c else orig[p]
+            if s == max(lst) and p not in owner:
+                ws.append((p - lo, T(s)))
+        if top >= hi:
+            wa.append((top, val))
+        else:
+            ws.append((top - lo, val))
+    for pos, v in wa:
+        a[pos] = v
+    for pos, v in ws:
+        slab[pos] = v
+
+
+def region_replay(arr, J, cap, NT=8, SPT=2, KMAX=8, rng=None, stats=None):
+    """Applies the Fisher-Yates steps i = m-1 .. 1 (swap positions i and J[i] <= i) to a copy of `arr`, one region of at most
+    `cap` positions at a time, top region first (see nhood.cu 2i): the pass of region [lo, hi) scans all steps i >= lo and
+    applies those whose TARGET lies in the region (a step whose target lies below is left to a later pass: its top then
+    still holds T(step), the value it had just before the step).  Mirrors the kernel's chunking: NT*K steps are scanned per
+    window (K halved when more than W = NT*SPT of them match)."""
+    rng = rng or random.Random(0)
+    a = list(arr)
+    m = len(a)
+    if m < 2:
+        return a
+    W = NT * SPT
+    R = (m + cap - 1) // cap
+    B = (((m + R - 1) // R + 15) // 16) * 16
+    for r in range((m - 1) // B, -1, -1):
+        lo = r * B
+        ln = min(B, m - lo)
+        hi = lo + ln
+        slab = a[lo:hi]
+        i_min = max(lo, 1)
+        i_cur = m - 1
+        while i_cur >= i_min:
+            avail = i_cur - i_min + 1
+            K = KMAX
+            while K > 1 and NT * K > W and NT * K * min(ln, i_cur - lo + 1) * 23 > W * (i_cur + 1) * 20:
+                K >>= 1
+            while True:
+                SC = min(NT * K, avail)
+                steps = [i_cur - s for s in range(SC) if lo <= J[i_cur - s] < hi]
+                if len(steps) <= W:
+                    break
+                K >>= 1
+                if stats is not None:
+                    stats["overflow"] = stats.get("overflow", 0) + 1
+            _resolve_general_window(slab, a, lo, hi, steps, [J[i] for i in steps], rng)
+            if stats is not None:
+                stats["xwin"] = stats.get("xwin", 0) + 1
+            i_cur -= SC
+        a[lo:hi] = slab
+    return a

@@ -19,12 +19,12 @@ from tools import synth
 
 pytestmark = pytest.mark.gpu
 
-# The product library offers the replay variants -1 (auto), 1, 2 and 7.  The superseded variants 0, 3, 4, 5, 6 are kept as
+# The product library offers the replay variants -1 (auto), 1, 2, 7 and 8.  The superseded variants 0, 3, 4, 5, 6 are kept as
 # independent cross-checks in a TEST build of the same sources (tests/native/libsquidpy_b200_testvariants.so, `make testvariants`):
 # `test_superseded_replay_variants_cross_check` re-runs this file against that build in a subprocess with SQB_VARIANT_TESTS=1,
 # which flips the parametrisations below from the product variants to the superseded ones.
 VARIANT_RUN = os.environ.get("SQB_VARIANT_TESTS") == "1"
-PRODUCT_ALGOS = (-1, 1, 2, 7)
+PRODUCT_ALGOS = (-1, 1, 2, 7, 8)
 
 
 def _algos(params):
@@ -143,7 +143,8 @@ def test_create_errors():
                                              (3, 128, 4), (3, 256, 4), (3, 256, 8), (3, 512, 2), (3, 512, 4), (3, 1024, 2), (3, 1024, 4), (4, 512, 4),
                                              (5, 256, 4), (5, 256, 8), (5, 512, 2), (5, 512, 4), (5, 1024, 2), (5, 1024, 4),
                                              (6, 128, 4), (6, 256, 4), (6, 256, 8), (6, 512, 2), (6, 512, 4), (6, 512, 8), (6, 1024, 2), (6, 1024, 4),
-                                             (7, 128, 4), (7, 256, 4), (7, 256, 8), (7, 512, 2), (7, 512, 4), (7, 512, 8), (7, 1024, 2), (7, 1024, 4)]))
+                                             (7, 128, 4), (7, 256, 4), (7, 256, 8), (7, 512, 2), (7, 512, 4), (7, 512, 8), (7, 1024, 2), (7, 1024, 4),
+                                             (8, 256, 4), (8, 512, 2), (8, 512, 4), (8, 1024, 2)]))
 @pytest.mark.parametrize("n", [2, 3, 5, 33, 100, 1000, 1025, 5041, 70001])
 def test_shuffle_is_numpy_exact(algo, threads, q, n):
     """Shuffled label vectors equal numpy Generator.shuffle of the same spawned generators (oracle = exact replay,
@@ -156,7 +157,7 @@ def test_shuffle_is_numpy_exact(algo, threads, q, n):
     plan = _plan(g, n_cls)
     plan.set_option("shuffle_algo", algo)
     plan.set_option("shuffle_threads", threads)
-    plan.set_option("shuffle_r" if algo in (3, 5, 6, 7) else "shuffle_q", q)
+    plan.set_option("shuffle_r" if algo in (3, 5, 6, 7, 8) else "shuffle_q", q)
     plan.set_base(base)
     P = 7
     st = spawn_states(1234 + n, P)
@@ -165,7 +166,7 @@ def test_shuffle_is_numpy_exact(algo, threads, q, n):
     np.testing.assert_array_equal(got, ref.shuffle_labels(base, st))
 
 
-@pytest.mark.parametrize("algo,threads,r", _algos([(1, 512, 4), (2, 512, 4), (3, 512, 4), (5, 512, 4), (6, 512, 4), (6, 1024, 2), (7, 1024, 2), (7, 512, 8), (-1, 512, 4)]))
+@pytest.mark.parametrize("algo,threads,r", _algos([(1, 512, 4), (2, 512, 4), (3, 512, 4), (5, 512, 4), (6, 512, 4), (6, 1024, 2), (7, 1024, 2), (7, 512, 8), (8, 1024, 2), (8, 512, 4), (-1, 512, 4)]))
 def test_shuffle_uint16_labels(algo, threads, r):
     """More than 256 categories: 16-bit label arrays through every replay variant (incl. the shared-memory low part of the
     default, which then holds half as many elements), with library segments."""
@@ -177,9 +178,11 @@ def test_shuffle_uint16_labels(algo, threads, r):
     plan = _plan(g, n_cls)
     plan.set_option("shuffle_algo", algo)
     plan.set_option("shuffle_threads", threads)
-    plan.set_option("shuffle_r" if algo in (3, 5, 6, 7) else "shuffle_q", r)
+    plan.set_option("shuffle_r" if algo in (3, 5, 6, 7, 8) else "shuffle_q", r)
     if algo == 7:
         plan.set_option("shuffle_low", -1)
+    if algo == 8:
+        plan.set_option("shuffle_region", 20000)  # several regions per segment
     P = 300 if algo == -1 else 5  # auto picks the two-kernel list replay only for more than 2 x SM permutations
     st = spawn_states(11, P)
     plan.set_base(base)
@@ -199,7 +202,7 @@ def test_target_generation_batch_sizes(q, n):
     base = (np.arange(n) % 113).astype(np.uint32)
     st = spawn_states(900 + n, 24)
     exp = ref.shuffle_labels(base, st)
-    for algo in _algos([5, 7]):
+    for algo in _algos([5, 7, 8]):
         plan = _plan(g, 113)
         plan.set_option("shuffle_algo", algo)
         plan.set_option("shuffle_q", q)
@@ -228,6 +231,38 @@ def test_list_replay_window_factor(wf, threads, r):
     np.testing.assert_array_equal(plan.shuffled_labels(0, 9), ref.shuffle_labels(base, st))
 
 
+@pytest.mark.skipif(VARIANT_RUN, reason="product variant")
+@pytest.mark.parametrize("region", [16, 48, 1000, 4096, 30000, 65536, 0])
+@pytest.mark.parametrize("threads,r", [(1024, 2), (256, 4)])
+def test_region_replay_region_sizes(region, threads, r):
+    """algo 8 replays one region of the label array at a time in shared memory (tops above the region: compacted windows;
+    tops inside: consecutive windows; targets below: deferred to the pass that owns them).  Any region size must give numpy's
+    permutation: tiny regions make every step cross regions and the compaction windows sparse, region sizes around the window
+    length exercise the own-range lists next to deferred steps, 0 = everything shared memory holds."""
+    if region in (16, 48):
+        ns = [2, 17, 100, 3001]
+    else:
+        ns = [5041, 70001, 200003]
+    for n in ns:
+        g = sp.csr_matrix((np.ones(n - 1, np.float32), (np.arange(n - 1), np.arange(1, n))), shape=(n, n))
+        base = (np.arange(n) * 13 % 241).astype(np.uint32)
+        plan = _plan(g, 241)
+        plan.set_option("shuffle_algo", 8)
+        plan.set_option("shuffle_threads", threads)
+        plan.set_option("shuffle_r", r)
+        plan.set_option("shuffle_region", region)
+        plan.set_base(base)
+        st = spawn_states(555 + n + region, 4)
+        plan.upload(st)
+        np.testing.assert_array_equal(plan.shuffled_labels(0, 4), ref.shuffle_labels(base, st))
+        if n > 5000:
+            lib = (np.arange(n) % 3).astype(np.int32)
+            plan.set_base(base, lib, 3)
+            plan.upload(st)
+            np.testing.assert_array_equal(plan.shuffled_labels(0, 2), ref.shuffle_labels(base, st[:2], lib, 3))
+        plan.close()
+
+
 @pytest.mark.parametrize("algo", _algos([5, 7]))
 @pytest.mark.parametrize("low", [0, 1024, 50000, -1])
 def test_two_kernel_replay_low_part(low, algo):
@@ -248,7 +283,7 @@ def test_two_kernel_replay_low_part(low, algo):
     np.testing.assert_array_equal(plan.shuffled_labels(0, 5), ref.shuffle_labels(base, st, lib, 3))
 
 
-@pytest.mark.parametrize("algo", _algos([0, 1, 2, 3, 4, 5, 6, 7]))
+@pytest.mark.parametrize("algo", _algos([0, 1, 2, 3, 4, 5, 6, 7, 8]))
 def test_shuffle_library_groups(algo):
     n = 4000
     g = synth.hex_graph(40, 100)
@@ -390,7 +425,7 @@ def test_full_size_1m_spots():
     assert (got.reshape(P, -1).sum(axis=1, dtype=np.int64) == g.nnz).all()  # every stored entry counted once
     np.testing.assert_array_equal(got, got.transpose(0, 2, 1))  # symmetric graph -> symmetric counts
     # every replay variant at full size, incl. several permutations per CTA / team (the superseded ones in the test build)
-    for algo in ((3, 4, 5, 6) if VARIANT_RUN else (1, 2, 7)):
+    for algo in ((3, 4, 5, 6) if VARIANT_RUN else (1, 2, 7, 8)):
         plan.set_option("shuffle_algo", algo)
         plan.set_option("shuffle_ctas", 16)
         np.testing.assert_array_equal(plan.permute(st), got)
