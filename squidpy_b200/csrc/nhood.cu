@@ -2108,74 +2108,88 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict_
 //     tools/micro/smem_bench.cu on B200: a random byte read + write costs 5.3 cycles per warp in the CTA's own shared
 //     memory, 135 in distributed shared memory of a cluster and 230 against an L2-resident global array -- the list kernel
 //     (2h) spends most of its time on the two thirds of its targets that miss its shared-memory low part.  A 1 MB label
-//     array does not fit one SM, but Fisher-Yates only ever moves a label DOWN-or-into a target j <= i, so the array can
-//     be processed one REGION [lo, hi) of <= ~160 K positions at a time, top region first, each step exactly once, in the
-//     pass of the region its target falls into:
-//       pass of region r:  slab <- a[lo, hi)                                    (coalesced)
-//         phase X  steps i = m-1 .. hi (tops above the region) whose target lies in [lo, hi): the J values are scanned
-//                  (coalesced), the matching steps compacted in step order into windows of <= W, and applied as
-//                  v = slab[j]; slab[j] = a[i]; a[i] = v.  a[i] still holds T(i), the value position i had just before
-//                  step i: the pass of i's own region left it there (below), and no pass in between touches it.
-//         phase Y  steps i = hi-1 .. lo (tops inside the region): windows of W consecutive steps exactly as in 2h (own-range
-//                  lists, duplicate filter, hash lists), every access in the slab.  A step whose target lies BELOW the
-//                  region is not applied here: it only leaves T(i) at its top for the pass that owns its target.
-//         a[lo, hi) <- slab                                                      (coalesced)
-//     Conflicts inside a window are resolved with the lists of 2g/2h (original values only, no ordered pass); in phase X
-//     tops are never targets, so only the duplicate-target lists remain.  Cost besides the resolution: the J row is
-//     re-scanned once per region above the target region, (R-1)/2 extra passes over J for R regions (streaming).
+//     array does not fit one SM, but Fisher-Yates only ever exchanges a top i with a target j <= i, so the array can be
+//     processed one REGION [lo, hi) of <= ~165 K positions at a time, top region first, every step exactly once, in the
+//     pass of the region its TARGET falls into:
+//       pass of region r:  slab <- a[lo, hi)                                                  (coalesced)
+//         scan the steps i = m-1 .. max(lo, 1) (J row, coalesced, prefetched one chunk ahead); the steps whose target lies
+//         in [lo, hi) are compacted IN STEP ORDER into windows of <= W slots and applied: v = slab[j]; slab[j] = top;
+//         top = v, where the top is a[i] for a step above the region (a[i] still holds T(i), the value position i had just
+//         before step i: the pass of i's own region left it there and no pass in between touches it) or slab[i - lo] for a
+//         step inside it.  A step whose target lies BELOW the region is simply not in any window of this pass: whatever
+//         earlier steps deposited at its top stays there as T(i) for the pass that owns its target.
+//         a[lo, hi) <- slab                                                                    (coalesced)
+//     Conflicts inside a window are resolved as in 2g/2h from immutable lists and original values only (no ordered pass),
+//     now keyed by POSITION (tests/emu_shuffle.py::_resolve_general_window is the executable specification): targeters[p] =
+//     slots with target p, owner[p] = the slot whose top is p; T(x) = T(latest targeter of x's top) or its original value;
+//     slot s writes top_s <- T(latest earlier targeter of its target) or the target's original value; the last targeter of p
+//     deposits T(itself) at p unless p's owner is in the window.  Only positions whose filter bucket was marked twice (a few
+//     percent) touch the hash tables at all.
+//     Cost besides the resolution: the J row is re-scanned once per region above the target region, (R-1)/2 extra passes
+//     over J for R regions (streaming, 6 regions at 1M spots).
 // ------------------------------------------------------------------------------------------------
-template <typename LT, int NT, int SPT>
+template <typename LT, int NT>
 __global__ void __launch_bounds__(NT, 1) nhood_apply_region_kernel(LT* __restrict__ labels, const uint32_t* __restrict__ J,
                                                                    int64_t stride, int64_t n_perms, int nseg,
                                                                    const int64_t* __restrict__ seg_start,
                                                                    const int64_t* __restrict__ seg_len, uint32_t full_mask,
                                                                    uint64_t stagger_ns, int region_cap) {
-    constexpr int W = NT * SPT;  // steps per window
-    constexpr int HS = W;        // hash slots: only steps of multiply-hit buckets are inserted
-    constexpr int NWB = 2 * W;   // filter words (16 buckets of 2 bits each)
+    // Work distribution inside a window.  A chunk of NT*K consecutive steps is scanned, warp w takes the w-th run of 32*K of
+    // them: it compacts ITS matches in step order into its own segment of the slot arrays (ids w*CAPW + r: id order = step
+    // order) with nothing but ballots, and then processes them 32 at a time with full lanes.  Slots on multiply-marked
+    // positions (a few percent) are compacted once more per warp and resolved by lanes 0..n-1 of the warp in one pass per
+    // phase, so the list code never runs with one or two live lanes per iteration.  Three block barriers per window:
+    // filter marks complete / lists complete / writes complete.
     constexpr int NWARP = NT / 32;
-    constexpr int KMAX = 8;      // phase X: J values scanned per thread and chunk
-    constexpr int LOG_HS = (HS == 512 ? 9 : HS == 1024 ? 10 : HS == 2048 ? 11 : HS == 4096 ? 12 : HS == 8192 ? 13 : 14);
+    constexpr int KMAX = 16;          // J values scanned per thread and chunk, at most
+    constexpr int CAPW = 96;          // slot ids per warp
+    constexpr int ITMAX = CAPW / 32;  // dense iterations per warp and window, at most
+    constexpr int NID = NWARP * CAPW;
+    constexpr int HS = 2 * NT;        // slots per window, at most = hash slots per table
+    constexpr int NWB = 2 * HS;       // filter words (16 buckets of 2 bits each)
+    constexpr int QSH = 18;           // slot entry = (chunk offset << 18) | (target - lo)
+    constexpr int ETGT = 56;          // expected matches per warp a chunk is sized for (CAPW is 5 sigma above)
+    constexpr int LOG_HS = (HS == 512 ? 9 : HS == 1024 ? 10 : HS == 2048 ? 11 : HS == 4096 ? 12 : 13);
     static_assert(HS == (1 << LOG_HS), "HS must be a power of two");
-    static_assert(W < 0xFFFF, "step indices are stored in 16 bits");
-    static_assert(NWARP <= 32, "one warp scans the warp totals");
+    static_assert(NID < 0xFFFF, "slot ids are stored in 16 bits");
+    static_assert(NT * KMAX <= (1 << (32 - QSH)), "chunk offsets must fit the slot entry");
+    static_assert(NT * 2 <= HS && 64 <= CAPW, "two steps per thread must always fit a window");
     constexpr int HS_SHIFT = 32 - LOG_HS;
     extern __shared__ __align__(16) unsigned char sqb_shuffle_smem[];
-    unsigned long long* s_tab = reinterpret_cast<unsigned long long*>(sqb_shuffle_smem);  // [HS] (target << 32) | list head
-    uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_tab + HS);                            // [NWB] duplicate filter
-    uint32_t* s_ohead = s_bits + NWB;                                                      // [W] own-range list heads
-    uint32_t* s_qi = s_ohead + W;                                                          // [W] phase X: top position of a slot
-    uint32_t* s_qj = s_qi + W;                                                             // [W] phase X: target - lo of a slot
-    uint32_t* s_wsum = s_qj + W;                                                           // [64] matches per warp
-    uint16_t* s_next = reinterpret_cast<uint16_t*>(s_wsum + 64);                           // [W] list links
-    LT* s_otop = reinterpret_cast<LT*>(s_next + W);                                        // [W] original top values
-    LT* s_slab = s_otop + W;                                                               // [region_cap] the region
+    unsigned long long* s_tabT = reinterpret_cast<unsigned long long*>(sqb_shuffle_smem);  // [HS] (position << 32) | head of its targeter list
+    unsigned long long* s_tabO = s_tabT + HS;                                              // [HS] (position << 32) | slot whose top it is
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_tabO + HS);                            // [NWB] duplicate filter
+    uint32_t* s_q = s_bits + NWB;                                                           // [NID] the window's slots
+    uint32_t* s_cnt = s_q + NID;                                                            // [64] slots per warp
+    uint16_t* s_next = reinterpret_cast<uint16_t*>(s_cnt + 64);                             // [NID] list links
+    uint16_t* s_slow = s_next + NID;                                                        // [NWARP][32] slots of multiply-marked positions
+    LT* s_otop = reinterpret_cast<LT*>(s_slow + NWARP * 32);                                // [NID] original top values
+    LT* s_slab = s_otop + NID;                                                              // [region_cap] the region
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    for (int h = tid; h < HS; h += NT) s_tab[h] = SQB_EMPTY64;
+    for (int h = tid; h < 2 * HS; h += NT) s_tabT[h] = SQB_EMPTY64;  // both tables
     for (int w = tid; w < NWB; w += NT) s_bits[w] = 0u;
-    for (int w = tid; w < W; w += NT) s_ohead[w] = SQB_NONE32;
     sqb_stagger(stagger_ns * blockIdx.x / gridDim.x);
     __syncthreads();
 
-    // duplicate filter: "seen" / "seen again" bits of the bucket of target jl (2h)
-    auto mark_target = [&](uint32_t jl) {
-        const uint32_t sh = (jl & 15u) * 2u;
-        uint32_t* wp = &s_bits[(jl >> 4) & (NWB - 1)];
+    // duplicate filter: "marked" / "marked again" bits of the bucket of position pl (2h)
+    auto mark_pos = [&](uint32_t pl) {
+        const uint32_t sh = (pl & 15u) * 2u;
+        uint32_t* wp = &s_bits[(pl >> 4) & (NWB - 1)];
         const uint32_t old = atomicOr(wp, 1u << sh);
         if ((old >> sh) & 1u) atomicOr(wp, 2u << sh);
     };
-    auto seen_again = [&](uint32_t jl) -> bool { return (s_bits[(jl >> 4) & (NWB - 1)] >> ((jl & 15u) * 2u + 1u)) & 1u; };
-    // push step s on the list of target jl in the hash table; returns the table slot
-    auto hash_push = [&](uint32_t jl, int s) -> uint32_t {
-        uint32_t h = (jl * 2654435761u) >> HS_SHIFT;
-        const unsigned long long mine = ((unsigned long long)jl << 32) | (unsigned)s;
+    auto marked_again = [&](uint32_t pl) -> bool { return (s_bits[(pl >> 4) & (NWB - 1)] >> ((pl & 15u) * 2u + 1u)) & 1u; };
+    // push slot id on the targeter list of position pl; returns the table slot
+    auto push_targeter = [&](uint32_t pl, int id) -> uint32_t {
+        uint32_t h = (pl * 2654435761u) >> HS_SHIFT;
+        const unsigned long long mine = ((unsigned long long)pl << 32) | (unsigned)id;
         uint32_t nxt = SQB_NONE16;
         while (true) {
-            const unsigned long long prev = atomicCAS(&s_tab[h], SQB_EMPTY64, mine);
+            const unsigned long long prev = atomicCAS(&s_tabT[h], SQB_EMPTY64, mine);
             if (prev == SQB_EMPTY64) break;
-            if ((uint32_t)(prev >> 32) == jl) {  // same target: push in front of the current head
-                if (atomicCAS(&s_tab[h], prev, mine) == prev) {
+            if ((uint32_t)(prev >> 32) == pl) {  // same position: push in front of the current head
+                if (atomicCAS(&s_tabT[h], prev, mine) == prev) {
                     nxt = (uint32_t)prev & 0xFFFFu;
                     break;
                 }
@@ -2183,237 +2197,333 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_region_kernel(LT* __restric
             }
             h = (h + 1) & (HS - 1);
         }
-        s_next[s] = (uint16_t)nxt;
+        s_next[id] = (uint16_t)nxt;
         return h;
+    };
+    auto insert_owner = [&](uint32_t pl, int id) -> uint32_t {  // tops are distinct: plain insertion
+        uint32_t h = (pl * 2654435761u) >> HS_SHIFT;
+        const unsigned long long mine = ((unsigned long long)pl << 32) | (unsigned)id;
+        while (atomicCAS(&s_tabO[h], SQB_EMPTY64, mine) != SQB_EMPTY64) h = (h + 1) & (HS - 1);
+        return h;
+    };
+    auto find_key = [&](const unsigned long long* tab, uint32_t pl) -> int {  // table slot of position pl, or -1
+        uint32_t h = (pl * 2654435761u) >> HS_SHIFT;
+        for (int probes = 0; probes < HS; ++probes) {
+            const unsigned long long e = tab[h];
+            if (e == SQB_EMPTY64) return -1;
+            if ((uint32_t)(e >> 32) == pl) return (int)h;
+            h = (h + 1) & (HS - 1);
+        }
+        return -1;
     };
 
     for (int64_t perm = blockIdx.x; perm < n_perms; perm += gridDim.x) {
-        LT* __restrict__ a = labels + perm * stride;
-        const uint32_t* __restrict__ Jp = J + perm * stride;
         for (int seg = 0; seg < nseg; ++seg) {
             const int64_t base = seg_start[seg];
             const int m = (int)seg_len[seg];  // n < 2^31
             if (m < 2) continue;
+            LT* __restrict__ a0 = labels + perm * stride + base;
+            const uint32_t* __restrict__ Jb = J + perm * stride + base;
             const int R = (m + region_cap - 1) / region_cap;
             const int B = (((m + R - 1) / R + 15) / 16) * 16;  // balanced regions, <= region_cap (a multiple of 16)
             for (int r = (m - 1) / B; r >= 0; --r) {
                 const int lo = r * B;
                 const int len = min(B, m - lo);
                 const int hi = lo + len;
-                for (int x = tid; x < len; x += NT) s_slab[x] = a[base + lo + x];
+                {  // slab <- a[lo, hi)
+                    const LT* __restrict__ src = a0 + lo;
+                    int x0 = 0;
+                    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+                        constexpr int EPV = 16 / (int)sizeof(LT);
+                        const int nv = len / EPV;
+                        const uint4* __restrict__ sv = reinterpret_cast<const uint4*>(src);
+                        uint4* dv = reinterpret_cast<uint4*>(s_slab);
+                        for (int x = tid; x < nv; x += NT) dv[x] = __ldcg(sv + x);
+                        x0 = nv * EPV;
+                    }
+                    for (int x = x0 + tid; x < len; x += NT) s_slab[x] = ld_cg<LT>(src + x);
+                }
                 __syncthreads();
-                // ---------------- phase X: tops above the region, targets inside ----------------
-                int i_cur = m - 1;
-                while (i_cur >= hi) {
-                    const int avail = i_cur - hi + 1;
-                    int K = KMAX;  // expected matches NT*K*len/(i_cur+1), kept 15% below W
-                    while (K > 1 && (int64_t)NT * K * len * 23 > (int64_t)W * ((int64_t)i_cur + 1) * 20) K >>= 1;
-                    uint32_t jv[KMAX], rk[KMAX];
-                    uint32_t mbits, total, wbase;
-                    int SC;
-                    while (true) {
-                        SC = min(NT * K, avail);
-                        uint32_t cnt = 0;
-                        mbits = 0;
+                const int i_min = max(lo, 1);
+                // chunk = NT*K consecutive steps from i_cur down, sized for ETGT expected matches per warp (two steps per thread
+                // always fit)
+                // (single precision is plenty: any block-uniform K is correct, this only sizes the windows).  K >= 4 is a multiple of
+                // 4: the scan then takes four consecutive J values per lane with one 16-byte load.
+                // (a first chunk of < 4 steps makes J[i_cur + 1] 16-byte aligned at every later chunk start: chunk lengths are
+                //  multiples of 4)
+                const int misalign = (int)((((uintptr_t)Jb >> 2) + (uintptr_t)m) & 3u);
+                constexpr bool vec_ok = true;
+                auto pick_k = [&](int i) -> int {
+                    const float num = (float)min(len, i - lo + 1);
+                    int k = (int)(((float)ETGT * ((float)i + 1.0f)) / (32.0f * num));
+                    k = k < 2 ? 2 : (k > KMAX ? KMAX : k);
+                    if (k >= 4) k &= ~3;
+                    return k;
+                };
+                // Scan layouts.  vector (K % 4 == 0 and vec_ok): step offset s = ((warp*K/4 + g)*32 + lane)*4 + e, jv[4g + e] = J[i_top - s]
+                // (one 16-byte load per g); scalar: s = (warp*K + k)*32 + lane, jv[k] = J[i_top - s].  Either way warp w scans the w-th
+                // run of 32*K steps and its (k, lane) resp. (g, lane, e) order is step order.
+                uint32_t jv[KMAX];
+                auto load_chunk = [&](int i_top, int K, int SC) {
+                    if ((K & 3) == 0 && vec_ok) {
+#pragma unroll
+                        for (int g = 0; g < KMAX / 4; ++g) {
+                            jv[4 * g] = jv[4 * g + 1] = jv[4 * g + 2] = jv[4 * g + 3] = 0u;
+                            if (4 * g < K) {  // block-uniform
+                                const int s0 = ((warp * (K >> 2) + g) * 32 + lane) * 4;
+                                if (s0 + 3 < SC) {
+                                    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(Jb + (i_top - s0 - 3)));
+                                    jv[4 * g] = v.w, jv[4 * g + 1] = v.z, jv[4 * g + 2] = v.y, jv[4 * g + 3] = v.x;
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e)
+                                        if (s0 + e < SC) jv[4 * g + e] = __ldcs(Jb + (i_top - s0 - e));
+                                }
+                            }
+                        }
+                    } else {
 #pragma unroll
                         for (int k = 0; k < KMAX; ++k) {
-                            jv[k] = 0, rk[k] = 0;
+                            jv[k] = 0u;
                             if (k < K) {  // block-uniform
-                                const int s = warp * 32 * K + k * 32 + lane;
-                                const bool inb = s < SC;
-                                const uint32_t j = inb ? __ldcs(Jp + base + (i_cur - (inb ? s : 0))) : 0u;
-                                const bool mt = inb && (j - (uint32_t)lo) < (uint32_t)len;
-                                const uint32_t b = __ballot_sync(0xffffffffu, mt);
-                                rk[k] = cnt + __popc(b & lt_mask);
-                                cnt += __popc(b);
-                                jv[k] = j;
-                                mbits |= (mt ? 1u : 0u) << k;
+                                const int s = (warp * K + k) * 32 + lane;
+                                if (s < SC) jv[k] = __ldcs(Jb + (i_top - s));
                             }
                         }
-                        if (lane == 0) s_wsum[warp] = cnt;
-                        __syncthreads();
-                        uint32_t v = lane < NWARP ? s_wsum[lane] : 0u, incl = v;
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-                            if (lane >= d) incl += t;
-                        }
-                        total = __shfl_sync(0xffffffffu, incl, 31);
-                        wbase = __shfl_sync(0xffffffffu, incl - v, warp);
-                        if (total <= (uint32_t)W) break;
-                        K >>= 1;          // more matches than a window holds: scan half as many steps (K = 1 always fits)
-                        __syncthreads();  // s_wsum is rewritten
                     }
-#pragma unroll
-                    for (int k = 0; k < KMAX; ++k) {
-                        if ((mbits >> k) & 1u) {
-                            const uint32_t slot = wbase + rk[k];
-                            const uint32_t jl = jv[k] - (uint32_t)lo;
-                            s_qi[slot] = (uint32_t)(i_cur - (warp * 32 * K + k * 32 + lane));
-                            s_qj[slot] = jl;
-                            mark_target(jl);
-                        }
-                    }
-                    SQB_CONVERGE();
-                    __syncthreads();
-                    // ---- resolve the window of `total` compacted steps (slot order = step order) ----
-                    const int S = (int)total;
-                    uint32_t qi[SPT], qj[SPT], slotv[SPT];
-                    LT vt[SPT], vj[SPT];
-                    uint32_t actm = 0, slowm = 0;
-#pragma unroll
-                    for (int mm = 0; mm < SPT; ++mm) {
-                        const int s = tid + mm * NT;
-                        const bool ac = s < S;
-                        qi[mm] = ac ? s_qi[s] : 0u;
-                        qj[mm] = ac ? s_qj[s] : 0u;
-                        vt[mm] = ac ? ld_cg<LT>(a + base + qi[mm]) : (LT)0;  // T(i): left there by the pass of i's own region
-                        vj[mm] = ac ? s_slab[qj[mm]] : (LT)0;
-                        actm |= (ac ? 1u : 0u) << mm;
-                        slotv[mm] = 0;
-                    }
-#pragma unroll
-                    for (int mm = 0; mm < SPT; ++mm) {
-                        const int s = tid + mm * NT;
-                        if (((actm >> mm) & 1u) && seen_again(qj[mm])) {
-                            slowm |= 1u << mm;
-                            slotv[mm] = hash_push(qj[mm], s);
-                        }
-                    }
-#pragma unroll
-                    for (int mm = 0; mm < SPT; ++mm)
-                        if ((actm >> mm) & 1u) s_otop[tid + mm * NT] = vt[mm];
-                    SQB_CONVERGE();
-                    __syncthreads();
-#pragma unroll
-                    for (int mm = 0; mm < SPT; ++mm) {
-                        const int s = tid + mm * NT;
-                        if ((actm >> mm) & 1u) {
-                            LT val = vj[mm];
-                            bool last = true;  // the only (or the last) step of this window that targets position j
-                            if ((slowm >> mm) & 1u) {
-                                const uint32_t head = (uint32_t)s_tab[slotv[mm]] & 0xFFFFu;
-                                int mx;
-                                const int p = sqb_list_latest_before(s_next, head, s, &mx);
-                                if (p >= 0) val = s_otop[p];  // tops are never targets here: T(p) is p's original top value
-                                last = (mx == s);
-                            }
-                            if (last) s_slab[qj[mm]] = vt[mm];
-                            st_cs<LT>(a + base + qi[mm], val);  // final
-                        }
-                    }
-                    SQB_CONVERGE();
-                    __syncthreads();
-#pragma unroll
-                    for (int mm = 0; mm < SPT; ++mm)
-                        if ((slowm >> mm) & 1u) s_tab[slotv[mm]] = SQB_EMPTY64;
-                    {
-                        uint4* bz = reinterpret_cast<uint4*>(s_bits);
-#pragma unroll
-                        for (int x = tid; x < NWB / 4; x += NT) bz[x] = make_uint4(0u, 0u, 0u, 0u);
-                    }
-                    __syncthreads();
-                    i_cur -= SC;
-                }
-                // ---------------- phase Y: tops inside the region ----------------
-                const int i_min = max(lo, 1);
-                i_cur = hi - 1;
+                };
+                int i_cur = m - 1;
+                int K = pick_k(i_cur);
+                int SC = min(NT * K, i_cur - i_min + 1);
+                if (misalign) K = 2, SC = min(misalign, SC);
+                load_chunk(i_cur, K, SC);
                 while (i_cur >= i_min) {
-                    const int S = min(W, i_cur - i_min + 1);  // steps i_cur, i_cur-1, ..., i_cur-S+1
-                    const int own_lo = i_cur - S;
-                    uint32_t jv[SPT], slotv[SPT];
-                    LT vj[SPT];
-                    uint32_t inwm = 0, actm = 0, ownm = 0, slowm = 0;
+                    // ---- S1: the warp compacts its matches, in step order, into its segment of the slot array ----
+                    const int idb = warp * CAPW;
+                    uint32_t cnt = 0;
+                    if ((K & 3) == 0 && vec_ok) {
 #pragma unroll
-                    for (int mm = 0; mm < SPT; ++mm) {
-                        const int s = tid + mm * NT;
-                        const bool inw = s < S;
-                        const uint32_t j = inw ? __ldcs(Jp + base + (i_cur - (inw ? s : 0))) : 0u;
-                        const bool ac = inw && (int)j >= lo;  // a target below the region belongs to a later pass
-                        const bool ow = ac && (int)j > own_lo;
-                        jv[mm] = j;
-                        slotv[mm] = 0;
-                        vj[mm] = (LT)0;
-                        inwm |= (inw ? 1u : 0u) << mm;
-                        actm |= (ac ? 1u : 0u) << mm;
-                        ownm |= (ow ? 1u : 0u) << mm;
-                        if (inw) s_otop[s] = s_slab[i_cur - s - lo];
-                        if (ac && !ow) {
-                            vj[mm] = s_slab[j - (uint32_t)lo];
-                            mark_target(j - (uint32_t)lo);
-                        }
-                        if (ow) {
-                            const int u = i_cur - (int)j;  // u >= s
-                            if (u != s) {
-                                const uint32_t prev = atomicExch(&s_ohead[u], (uint32_t)s);
-                                s_next[s] = (uint16_t)prev;  // NONE32 truncates to NONE16
-                            }
-                        }
-                    }
-                    SQB_CONVERGE();
-                    __syncthreads();
+                        for (int g = 0; g < KMAX / 4; ++g) {
+                            if (4 * g < K) {
+                                const int s0 = ((warp * (K >> 2) + g) * 32 + lane) * 4;
+                                uint32_t jl[4], bb[4];
+                                bool mt[4];
 #pragma unroll
-                    for (int mm = 0; mm < SPT; ++mm) {
-                        const int s = tid + mm * NT;
-                        if (((actm >> mm) & 1u) && !((ownm >> mm) & 1u) && seen_again(jv[mm] - (uint32_t)lo)) {
-                            slowm |= 1u << mm;
-                            slotv[mm] = hash_push(jv[mm] - (uint32_t)lo, s);
-                        }
-                    }
-                    SQB_CONVERGE();
-                    __syncthreads();
-#pragma unroll
-                    for (int mm = 0; mm < SPT; ++mm) {
-                        const int s = tid + mm * NT;
-                        if ((inwm >> mm) & 1u) {
-                            const int top_l = i_cur - s - lo;
-                            if ((actm >> mm) & 1u) {
-                                const uint32_t j = jv[mm];
-                                LT val;
-                                if ((ownm >> mm) & 1u) {
-                                    const int u = i_cur - (int)j;
-                                    if (u == s) {
-                                        val = sqb_list_T<LT>(s_ohead, s_next, s_otop, s);
-                                    } else {
-                                        int mx;
-                                        const int p = sqb_list_latest_before(s_next, s_ohead[u], s, &mx);
-                                        val = (p >= 0) ? sqb_list_T<LT>(s_ohead, s_next, s_otop, p) : s_otop[u];
-                                    }
-                                } else {
-                                    bool last = true;
-                                    val = vj[mm];
-                                    if ((slowm >> mm) & 1u) {
-                                        const uint32_t head = (uint32_t)s_tab[slotv[mm]] & 0xFFFFu;
-                                        int mx;
-                                        const int p = sqb_list_latest_before(s_next, head, s, &mx);
-                                        if (p >= 0) val = sqb_list_T<LT>(s_ohead, s_next, s_otop, p);
-                                        last = (mx == s);
-                                    }
-                                    if (last) s_slab[j - (uint32_t)lo] = sqb_list_T_own<LT>(s_ohead, s_next, s_otop, s, s_otop[s]);
+                                for (int e = 0; e < 4; ++e) {
+                                    jl[e] = jv[4 * g + e] - (uint32_t)lo;
+                                    mt[e] = (s0 + e < SC) && jl[e] < (uint32_t)len;
+                                    bb[e] = __ballot_sync(0xffffffffu, mt[e]);
                                 }
-                                s_slab[top_l] = val;  // final
-                            } else {
-                                // target below the region: leave T(s) at the top for the pass that owns the target
-                                s_slab[top_l] = sqb_list_T_own<LT>(s_ohead, s_next, s_otop, s, s_otop[s]);
+                                // slots in (lane, e) order: everything of the lower lanes first
+                                uint32_t rr = cnt + __popc(bb[0] & lt_mask) + __popc(bb[1] & lt_mask) + __popc(bb[2] & lt_mask) + __popc(bb[3] & lt_mask);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    if (mt[e] && rr < (uint32_t)CAPW) s_q[idb + rr] = ((uint32_t)(s0 + e) << QSH) | jl[e];
+                                    rr += mt[e] ? 1u : 0u;
+                                }
+                                cnt += __popc(bb[0]) + __popc(bb[1]) + __popc(bb[2]) + __popc(bb[3]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < KMAX; ++k) {
+                            if (k < K) {
+                                const int s = (warp * K + k) * 32 + lane;
+                                const uint32_t jl = jv[k] - (uint32_t)lo;
+                                const bool mt = (s < SC) && jl < (uint32_t)len;
+                                const uint32_t b = __ballot_sync(0xffffffffu, mt);
+                                const uint32_t rr = cnt + __popc(b & lt_mask);
+                                if (mt && rr < (uint32_t)CAPW) s_q[idb + rr] = ((uint32_t)s << QSH) | jl;
+                                cnt += __popc(b);
                             }
                         }
                     }
-                    SQB_CONVERGE();
-                    __syncthreads();
-#pragma unroll
-                    for (int mm = 0; mm < SPT; ++mm) {
-                        if ((ownm >> mm) & 1u) s_ohead[i_cur - (int)jv[mm]] = SQB_NONE32;
-                        if ((slowm >> mm) & 1u) s_tab[slotv[mm]] = SQB_EMPTY64;
+                    const bool ovf = cnt > (uint32_t)CAPW;
+                    if (ovf) cnt = CAPW;
+                    if (lane == 0) s_cnt[warp] = cnt;
+                    // the J values of the next chunk (the registers are free now)
+                    const int i_next = i_cur - SC;
+                    int K_next = 2, SC_next = 0;
+                    if (i_next >= i_min) {
+                        K_next = pick_k(i_next);
+                        SC_next = min(NT * K_next, i_next - i_min + 1);
+                        load_chunk(i_next, K_next, SC_next);
                     }
-                    {
+                    __syncwarp();
+                    // ---- S2: originals of the warp's slots (32 at a time), filter marks ----
+                    uint32_t q_[ITMAX];
+                    LT vt[ITMAX], vj[ITMAX];
+#pragma unroll
+                    for (int it = 0; it < ITMAX; ++it) {  // all loads first (the tops above the region come from global memory)
+                        q_[it] = 0xFFFFFFFFu;             // no slot
+                        vt[it] = (LT)0, vj[it] = (LT)0;
+                        const int rr = it * 32 + lane;
+                        if (rr < (int)cnt) {
+                            const uint32_t q = s_q[idb + rr];
+                            const uint32_t jl = q & ((1u << QSH) - 1u);
+                            const int i = i_cur - (int)(q >> QSH);
+                            q_[it] = q;
+                            vj[it] = s_slab[jl];
+                            vt[it] = (i < hi) ? s_slab[i - lo] : ld_cg<LT>(a0 + i);  // T(i): left there by the pass of i's own region
+                        }
+                    }
+#pragma unroll
+                    for (int it = 0; it < ITMAX; ++it) {
+                        if (q_[it] != 0xFFFFFFFFu) {
+                            const uint32_t jl = q_[it] & ((1u << QSH) - 1u);
+                            const int i = i_cur - (int)(q_[it] >> QSH);
+                            mark_pos(jl);
+                            if (i < hi) mark_pos((uint32_t)(i - lo));
+                            s_otop[idb + it * 32 + lane] = vt[it];
+                        }
+                    }
+                    SQB_CONVERGE();
+                    const int any_ovf = __syncthreads_or(ovf ? 1 : 0);
+                    uint32_t total = lane < NWARP ? s_cnt[lane] : 0u;
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+                    if (any_ovf || total > (uint32_t)HS) {
+                        // more matches than a warp segment or a window holds: forget the marks, scan half as many steps
                         uint4* bz = reinterpret_cast<uint4*>(s_bits);
+                        for (int x = tid; x < NWB / 4; x += NT) bz[x] = make_uint4(0u, 0u, 0u, 0u);
+                        __syncthreads();
+                        K = max(2, K >> 1);
+                        SC = min(NT * K, i_cur - i_min + 1);
+                        load_chunk(i_cur, K, SC);
+                        continue;
+                    }
+                    // ---- S3: slots on multiply-marked positions: compacted per warp, registered in the tables ----
+                    uint32_t fastm = 0;  // bit it: this lane's slot of iteration it takes the plain swap
+                    uint32_t nslow = 0;
+#pragma unroll
+                    for (int it = 0; it < ITMAX; ++it) {
+                        if (it * 32 < (int)cnt) {
+                            bool fl = false;
+                            const bool ac = q_[it] != 0xFFFFFFFFu;
+                            if (ac) {
+                                const uint32_t jl = q_[it] & ((1u << QSH) - 1u);
+                                const int i = i_cur - (int)(q_[it] >> QSH);
+                                fl = marked_again(jl) || (i < hi && marked_again((uint32_t)(i - lo)));
+                            }
+                            const uint32_t fb = __ballot_sync(0xffffffffu, fl);
+                            if (fl) s_slow[warp * 32 + ((nslow + __popc(fb & lt_mask)) & 31u)] = (uint16_t)(idb + it * 32 + lane);
+                            nslow += __popc(fb);
+                            fastm |= ((ac && !fl) ? 1u : 0u) << it;
+                        }
+                    }
+                    // (more than 32 such slots in one warp: only tiny or adversarial segments; handled like an overflow)
+                    const bool sovf = nslow > 32u;
+                    __syncwarp();
+                    int sid = -1;
+                    uint32_t sjl = 0, slotT = 0, slotO = 0;
+                    int stop = 0;
+                    bool stfl = false, sofl = false, sself = false;
+                    LT svt = (LT)0, svj = (LT)0;
+                    if (!sovf && lane < (int)nslow) {
+                        sid = s_slow[warp * 32 + lane];
+                        const uint32_t q = s_q[sid];
+                        sjl = q & ((1u << QSH) - 1u);
+                        stop = i_cur - (int)(q >> QSH);
+                        const bool inreg = stop < hi;
+                        sself = inreg && (uint32_t)(stop - lo) == sjl;
+                        stfl = marked_again(sjl);
+                        sofl = inreg && marked_again((uint32_t)(stop - lo));
+                        svt = s_otop[sid];
+                        svj = s_slab[sjl];
+                        if (stfl && !sself) slotT = push_targeter(sjl, sid);
+                        if (sofl) slotO = insert_owner((uint32_t)(stop - lo), sid);
+                    }
+                    SQB_CONVERGE();
+                    const int any_sovf = __syncthreads_or(sovf ? 1 : 0);
+                    if (any_sovf) {
+                        // undo the registrations of the other warps, then retry with half the steps
+                        if (sid >= 0) {
+                            if (stfl && !sself) s_tabT[slotT] = SQB_EMPTY64;
+                            if (sofl) s_tabO[slotO] = SQB_EMPTY64;
+                        }
+                        uint4* bz = reinterpret_cast<uint4*>(s_bits);
+                        for (int x = tid; x < NWB / 4; x += NT) bz[x] = make_uint4(0u, 0u, 0u, 0u);
+                        __syncthreads();
+                        K = max(1, K >> 1);  // K = 1: at most 32 slots per warp
+                        SC = min(NT * K, i_cur - i_min + 1);
+                        load_chunk(i_cur, K, SC);
+                        continue;
+                    }
+                    // ---- S4: writes.  Plain swaps by the lanes that hold them, everything else by the warp's resolver lanes
+                    //      from the (now immutable) lists and original values ----
+                    {
+                        uint4* bz = reinterpret_cast<uint4*>(s_bits);  // nobody reads the filter any more
 #pragma unroll
                         for (int x = tid; x < NWB / 4; x += NT) bz[x] = make_uint4(0u, 0u, 0u, 0u);
                     }
+#pragma unroll
+                    for (int it = 0; it < ITMAX; ++it) {
+                        if ((fastm >> it) & 1u) {
+                            const uint32_t jl = q_[it] & ((1u << QSH) - 1u);
+                            const int i = i_cur - (int)(q_[it] >> QSH);
+                            s_slab[jl] = vt[it];
+                            if (i < hi) s_slab[i - lo] = vj[it];
+                            else st_cs<LT>(a0 + i, vj[it]);  // final
+                        }
+                    }
+                    if (sid >= 0) {
+                        // T(x): value of slot x's top just before step x
+                        auto T_of = [&](int x) -> LT {
+                            while (true) {
+                                const int ix = i_cur - (int)(s_q[x] >> QSH);
+                                if (ix >= hi) break;  // tops above the region are never targets
+                                const int h = find_key(s_tabT, (uint32_t)(ix - lo));
+                                if (h < 0) break;
+                                int mx = -1;
+                                for (uint32_t e = (uint32_t)s_tabT[h] & 0xFFFFu; e != SQB_NONE16; e = s_next[e]) mx = max(mx, (int)e);
+                                x = mx;  // the latest targeter of x's top (every targeter of a top precedes its step)
+                            }
+                            return s_otop[x];
+                        };
+                        const LT Ts = sofl ? T_of(sid) : svt;
+                        LT val = svj;
+                        if (sself) {
+                            val = Ts;
+                        } else {
+                            bool last = true;  // the only (or the last) slot of this window that targets the position
+                            if (stfl) {
+                                const uint32_t head = (uint32_t)s_tabT[slotT] & 0xFFFFu;
+                                int mx;
+                                const int p = sqb_list_latest_before(s_next, head, sid, &mx);
+                                if (p >= 0) val = T_of(p);
+                                last = (mx == sid);
+                            }
+                            if (last && !(stfl && find_key(s_tabO, sjl) >= 0)) s_slab[sjl] = Ts;
+                        }
+                        if (stop < hi) s_slab[stop - lo] = val;
+                        else st_cs<LT>(a0 + stop, val);  // final
+                    }
+                    SQB_CONVERGE();
                     __syncthreads();
-                    i_cur -= S;
+                    // ---- S5: the resolver lanes clear their table entries (ordered before the next window's pushes by its
+                    //      first barrier; the filter was cleared above) ----
+                    if (sid >= 0) {
+                        if (stfl && !sself) s_tabT[slotT] = SQB_EMPTY64;
+                        if (sofl) s_tabO[slotO] = SQB_EMPTY64;
+                    }
+                    i_cur = i_next;
+                    K = K_next;
+                    SC = SC_next;
                 }
-                for (int x = tid; x < len; x += NT) a[base + lo + x] = s_slab[x];
+                __syncthreads();
+                {  // a[lo, hi) <- slab
+                    LT* __restrict__ dst = a0 + lo;
+                    int x0 = 0;
+                    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+                        constexpr int EPV = 16 / (int)sizeof(LT);
+                        const int nv = len / EPV;
+                        uint4* dv = reinterpret_cast<uint4*>(dst);
+                        const uint4* sv = reinterpret_cast<const uint4*>(s_slab);
+                        for (int x = tid; x < nv; x += NT) dv[x] = sv[x];
+                        x0 = nv * EPV;
+                    }
+                    for (int x = x0 + tid; x < len; x += NT) dst[x] = s_slab[x];
+                }
                 __syncthreads();
             }
         }
@@ -3275,15 +3385,16 @@ static int launch_apply_list(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t n
     return SQB_OK;
 }
 
-template <typename LT, int NT, int SPT>
+template <typename LT, int NT>
 static int launch_apply_region(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t np) {
     sqb_ctx* c = h->ctx;
-    auto k = nhood_apply_region_kernel<LT, NT, SPT>;
-    constexpr size_t W = (size_t)NT * SPT, HS = W, NWB = 2 * W;
-    // [tab u64 x HS][bits u32 x NWB][ohead, qi, qj u32 x W][wsum u32 x 64][next u16 x W][otop LT x W][slab LT x cap]
-    const size_t tables = HS * 8 + NWB * 4 + 3 * W * 4 + 64 * 4 + W * 2 + W * sizeof(LT);
+    auto k = nhood_apply_region_kernel<LT, NT>;
+    constexpr size_t NWARP = NT / 32, NID = NWARP * 96, HS = 2 * NT, NWB = 2 * HS;
+    // [tabT, tabO u64 x HS][bits u32 x NWB][q u32 x NID][cnt u32 x 64][next u16 x NID][slow u16 x 32 NWARP][otop LT x NID][slab LT x cap]
+    const size_t tables = 2 * HS * 8 + NWB * 4 + NID * 4 + 64 * 4 + NID * 2 + NWARP * 32 * 2 + NID * sizeof(LT);
     SQB_CHECK(tables + 16 * sizeof(LT) <= c->smem_optin, SQB_ERR_UNSUPPORTED, "shuffle_algo 8: %zu bytes of shared memory exceed the device limit", tables);
     int64_t cap = ((int64_t)c->smem_optin - (int64_t)tables) / (int64_t)sizeof(LT);
+    if (cap > (1 << 18) - 16) cap = (1 << 18) - 16;                                 // targets are stored in 18 bits (all ones = no slot)
     if (h->shuffle_region > 0 && cap > h->shuffle_region) cap = h->shuffle_region;  // test hook: small regions
     cap = (cap / 16) * 16;
     if (cap < 16) cap = 16;
@@ -3328,12 +3439,11 @@ static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* stat
     }
     SqbLaunchScope scope(c, SQB_K_NHOOD_SHUFFLE);
     int rc = SQB_ERR_INVALID;
-    if (algo == 8) {
-        if (nt == 1024 && r == 2) rc = launch_apply_region<LT, 1024, 2>(h, lab, J, np);
-        else if (nt == 512 && r == 4) rc = launch_apply_region<LT, 512, 4>(h, lab, J, np);
-        else if (nt == 512 && r == 2) rc = launch_apply_region<LT, 512, 2>(h, lab, J, np);
-        else if (nt == 256 && r == 4) rc = launch_apply_region<LT, 256, 4>(h, lab, J, np);
-        else sqb_set_error("shuffle_algo 8: unsupported (shuffle_threads, shuffle_r) = (%d, %d)", nt, r);
+    if (algo == 8) {  // (shuffle_r is not used by this variant)
+        if (nt == 1024) rc = launch_apply_region<LT, 1024>(h, lab, J, np);
+        else if (nt == 512) rc = launch_apply_region<LT, 512>(h, lab, J, np);
+        else if (nt == 256) rc = launch_apply_region<LT, 256>(h, lab, J, np);
+        else sqb_set_error("shuffle_algo 8: unsupported shuffle_threads = %d", nt);
         SQB_TRY(rc);
         SQB_POST_LAUNCH();
         return SQB_OK;

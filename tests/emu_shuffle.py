@@ -374,18 +374,21 @@ def _resolve_general_window(slab, a, lo, hi, tops, tgts, rng):
         slab[pos] = v
 
 
-def region_replay(arr, J, cap, NT=8, SPT=2, KMAX=8, rng=None, stats=None):
+def region_replay(arr, J, cap, NT=8, WL=4, CAPW=12, KMAX=16, rng=None, stats=None):
     """Applies the Fisher-Yates steps i = m-1 .. 1 (swap positions i and J[i] <= i) to a copy of `arr`, one region of at most
     `cap` positions at a time, top region first (see nhood.cu 2i): the pass of region [lo, hi) scans all steps i >= lo and
     applies those whose TARGET lies in the region (a step whose target lies below is left to a later pass: its top then
     still holds T(step), the value it had just before the step).  Mirrors the kernel's chunking: NT*K steps are scanned per
-    window (K halved when more than W = NT*SPT of them match)."""
+    window, "warp" w (WL lanes) takes the w-th run of WL*K of them; K is sized for ~0.58 CAPW expected matches per warp and
+    halved when a warp finds more than CAPW or the window more than HS = 2*NT."""
     rng = rng or random.Random(0)
     a = list(arr)
     m = len(a)
     if m < 2:
         return a
-    W = NT * SPT
+    HS = 2 * NT
+    ETGT = max(1, (CAPW * 56) // 96)
+    assert 2 * WL <= CAPW
     R = (m + cap - 1) // cap
     B = (((m + R - 1) // R + 15) // 16) * 16
     for r in range((m - 1) // B, -1, -1):
@@ -397,17 +400,17 @@ def region_replay(arr, J, cap, NT=8, SPT=2, KMAX=8, rng=None, stats=None):
         i_cur = m - 1
         while i_cur >= i_min:
             avail = i_cur - i_min + 1
-            K = KMAX
-            while K > 1 and NT * K > W and NT * K * min(ln, i_cur - lo + 1) * 23 > W * (i_cur + 1) * 20:
-                K >>= 1
+            K = min(KMAX, max(2, (ETGT * (i_cur + 1)) // (WL * min(ln, i_cur - lo + 1))))
             while True:
                 SC = min(NT * K, avail)
-                steps = [i_cur - s for s in range(SC) if lo <= J[i_cur - s] < hi]
-                if len(steps) <= W:
+                match = [lo <= J[i_cur - s] < hi for s in range(SC)]
+                per_warp = [sum(match[w * WL * K:(w + 1) * WL * K]) for w in range(NT // WL)]
+                if max(per_warp) <= CAPW and sum(per_warp) <= HS:
                     break
-                K >>= 1
+                K = max(2, K >> 1)
                 if stats is not None:
                     stats["overflow"] = stats.get("overflow", 0) + 1
+            steps = [i_cur - s for s in range(SC) if match[s]]
             _resolve_general_window(slab, a, lo, hi, steps, [J[i] for i in steps], rng)
             if stats is not None:
                 stats["xwin"] = stats.get("xwin", 0) + 1

@@ -170,7 +170,7 @@ def test_region_replay_equals_fisher_yates():
                 J[i] = rnd.randrange(min(i + 1, 6))
         arr = [rnd.randrange(1000) for _ in range(m)]
         cap = rnd.choice([16, 32, 48, 64, 128, 1024])
-        nt = rnd.choice([2, 4, 8, 16])
-        got = region_replay(arr, J, cap, NT=nt, SPT=rnd.choice([1, 2, 4]), KMAX=rnd.choice([2, 8]), rng=rnd, stats=stats)
+        nt = rnd.choice([4, 8, 16])
+        got = region_replay(arr, J, cap, NT=nt, WL=rnd.choice([2, 4]), CAPW=rnd.choice([8, 12]), KMAX=rnd.choice([2, 16]), rng=rnd, stats=stats)
         assert got == _fisher_yates(arr, J), (trial, m, cap, nt, mode)
     assert stats.get("xwin", 0) > 1000 and stats.get("overflow", 0) > 0  # compacted windows and the halving path were exercised
