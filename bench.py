@@ -563,7 +563,7 @@ def main():
                                         "bound": "SURVEY 8(d): |d mean| < 4 sigma/sqrt(P), |d std|/std < 4/sqrt(2P) per bin; both arms are P-sample estimates, so the difference of two has sqrt(2) of that spread and the maximum over 900 bins reaches ~4.5-5"},
                 "note": "NOT the reference's permutations: same null distribution, different draws; z-scores agree to O(P^-1/2)"}
         roofline_fast = {"bound": "hbm", "achieved": gbs_f, "peak": peak, "unit": "GB/s", "frac": gbs_f / peak, "algorithmic_bytes_per_perm": int(bpp),
-                         "kernel": "nhood_philox_labels_kernel + nhood_count_kernel + stats", "kernel_ms": kms_f,
+                         "kernel": "nhood_philox_labels_kernel + nhood_count_recs_kernel + stats", "kernel_ms": kms_f,
                          "note": "algorithmic bytes use the reference dtypes (u32 labels written + read per permutation); the kernels move u8 labels, so the effective figure can exceed the DRAM peak"}
         plan.upload(states)
 

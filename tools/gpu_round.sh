@@ -30,7 +30,7 @@ for st in $STAGES; do
       timeout 900 python tools/tune_nhood.py 1000 > $OUT/tune_nhood.log 2>&1; echo "tune rc=$?" | tee -a $OUT/summary.txt
       cat $OUT/tune_nhood.log | tail -40 ;;
     ncufull)
-      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"nhood_apply_list|nhood_jgen|nhood_count_kernel|nhood_transpose|nhood_philox_labels" -c 6 -f -o $OUT/prof_nhood python tools/philox_time.py 1000 > $OUT/ncu_full.log 2>&1; echo "ncu-full nhood rc=$?" | tee -a $OUT/summary.txt
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"nhood_apply_list|nhood_jgen|nhood_count_recs|nhood_transpose|nhood_philox_labels" -c 6 -f -o $OUT/prof_nhood python tools/philox_time.py 1000 > $OUT/ncu_full.log 2>&1; echo "ncu-full nhood rc=$?" | tee -a $OUT/summary.txt
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ac_sparse_kernel|ac_rank_sort|ac_coltranspose" -c 4 -f -o $OUT/prof_moran python tools/prof_targets.py moran > $OUT/ncu_moran.log 2>&1; echo "ncu-full moran rc=$?" | tee -a $OUT/summary.txt
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:"pairs_kernel" -c 1 -f -o $OUT/prof_cooc python tools/prof_targets.py cooc > $OUT/ncu_cooc.log 2>&1; echo "ncu-full cooc rc=$?" | tee -a $OUT/summary.txt
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:"pairs_kernel" -c 1 -f -o $OUT/prof_ripley python tools/prof_targets.py ripley > $OUT/ncu_ripley.log 2>&1; echo "ncu-full ripley rc=$?" | tee -a $OUT/summary.txt
@@ -38,7 +38,7 @@ for st in $STAGES; do
       # the reports together exceed what gpurun brings back (64 MiB): summarise them HERE (ncu is on the box) and drop them
       mkdir -p $OUT/profiles
       python tools/summarize_profiles.py r02 gpurun_out/profiles > $OUT/summarize.log 2>&1
-      for k in nhood_apply_list nhood_jgen nhood_count_kernel nhood_philox_labels; do python tools/ncu_hotspots.py $OUT/prof_nhood.ncu-rep $k 25 > $OUT/profiles/r02_hotspots_$k.txt 2>&1; done
+      for k in nhood_apply_list nhood_jgen nhood_count_recs nhood_philox_labels; do python tools/ncu_hotspots.py $OUT/prof_nhood.ncu-rep $k 25 > $OUT/profiles/r02_hotspots_$k.txt 2>&1; done
       python tools/ncu_hotspots.py $OUT/prof_moran.ncu-rep ac_sparse_kernel 30 > $OUT/profiles/r02_hotspots_ac_sparse_kernel.txt 2>&1
       python tools/ncu_hotspots.py $OUT/prof_cooc.ncu-rep pairs_kernel 20 > $OUT/profiles/r02_hotspots_pairs_kernel.txt 2>&1
       python tools/ncu_hotspots.py $OUT/prof_misc.ncu-rep graph_knn_kernel 15 > $OUT/profiles/r02_hotspots_graph_knn_kernel.txt 2>&1
