@@ -2104,7 +2104,12 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// 2i. REGION replay (shuffle_algo 8): the apply step of the two-kernel replay with EVERY random access in shared memory.
+// 2i. REGION replay (shuffle_algo 8; compiled into the TEST build only, like the other superseded variants): the apply step of
+//     the two-kernel replay with EVERY random access in shared memory.  Measured at 1M spots x 1000 permutations: 22.9 ms against
+//     16.0 ms for the list kernel 2h -- with the memory system out of the way the replay is bound by instruction issue
+//     (17 G warp instructions: the J row is re-scanned (R+1)/2 = 4 times, and every window pays for compaction, filter and
+//     three block barriers), see DESIGN.md 3.1.  Kept as an independent cross-check of 2h: a different decomposition of the
+//     same Fisher-Yates sweep that must produce the same permutations.
 //     tools/micro/smem_bench.cu on B200: a random byte read + write costs 5.3 cycles per warp in the CTA's own shared
 //     memory, 135 in distributed shared memory of a cluster and 230 against an L2-resident global array -- the list kernel
 //     (2h) spends most of its time on the two thirds of its targets that miss its shared-memory low part.  A 1 MB label
@@ -2128,6 +2133,7 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_list_kernel(LT* __restrict_
 //     Cost besides the resolution: the J row is re-scanned once per region above the target region, (R-1)/2 extra passes
 //     over J for R regions (streaming, 6 regions at 1M spots).
 // ------------------------------------------------------------------------------------------------
+#ifdef SQB_TEST_VARIANTS
 template <typename LT, int NT>
 __global__ void __launch_bounds__(NT, 1) nhood_apply_region_kernel(LT* __restrict__ labels, const uint32_t* __restrict__ J,
                                                                    int64_t stride, int64_t n_perms, int nseg,
@@ -2529,6 +2535,7 @@ __global__ void __launch_bounds__(NT, 1) nhood_apply_region_kernel(LT* __restric
         }
     }
 }
+#endif  // SQB_TEST_VARIANTS
 
 // ------------------------------------------------------------------------------------------------
 // 3. transpose [P][stride] -> [PB/32][n + 1][32]  (32 permutations x 256 nodes per CTA), optional row scatter through
@@ -3385,6 +3392,7 @@ static int launch_apply_list(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t n
     return SQB_OK;
 }
 
+#ifdef SQB_TEST_VARIANTS
 template <typename LT, int NT>
 static int launch_apply_region(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t np) {
     sqb_ctx* c = h->ctx;
@@ -3407,11 +3415,12 @@ static int launch_apply_region(sqb_nhood* h, LT* lab, const uint32_t* J, int64_t
                                                (uint64_t)h->shuffle_stagger_us * 1000ull, (int)cap);
     return SQB_OK;
 }
+#endif  // SQB_TEST_VARIANTS
 
 #ifndef SQB_TEST_VARIANTS
 static int sqb_variant_unavailable(int algo) {
     sqb_set_error("shuffle_algo %d is a superseded replay variant kept as a cross-check: it is compiled into the test build only "
-                  "(make -C squidpy_b200/csrc testvariants); the product library offers -1 (auto), 1, 2, 7 and 8", algo);
+                  "(make -C squidpy_b200/csrc testvariants); the product library offers -1 (auto), 1, 2 and 7", algo);
     return SQB_ERR_UNSUPPORTED;
 }
 #endif
@@ -3440,6 +3449,7 @@ static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* stat
     SqbLaunchScope scope(c, SQB_K_NHOOD_SHUFFLE);
     int rc = SQB_ERR_INVALID;
     if (algo == 8) {  // (shuffle_r is not used by this variant)
+#ifdef SQB_TEST_VARIANTS
         if (nt == 1024) rc = launch_apply_region<LT, 1024>(h, lab, J, np);
         else if (nt == 512) rc = launch_apply_region<LT, 512>(h, lab, J, np);
         else if (nt == 256) rc = launch_apply_region<LT, 256>(h, lab, J, np);
@@ -3447,6 +3457,9 @@ static int launch_shuffle_two_kernel(sqb_nhood* h, LT* lab, const uint64_t* stat
         SQB_TRY(rc);
         SQB_POST_LAUNCH();
         return SQB_OK;
+#else
+        return sqb_variant_unavailable(algo);
+#endif
     }
     if (algo == 7) {
         if (nt == 1024 && r == 4) rc = launch_apply_list<LT, 1024, 4>(h, lab, J, np, low);
