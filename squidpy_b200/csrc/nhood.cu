@@ -3155,7 +3155,6 @@ struct sqb_nhood {
     DevBuf<uint32_t> d_cum;  // [nseg][n_cls + 1] class offsets of every segment's sorted labels (fast mode)
     DevBuf<uint32_t> d_bkt;  // per segment: class at the first value of every bucket (fast mode class lookup)
     std::vector<int64_t> h_seg_start, h_seg_len, h_bkt_off;
-    std::vector<uint32_t> h_grouped;  // base labels in library-grouped order (host copy for the fast-mode tables)
     bool philox_ready = false;
     std::vector<PhiloxSeg> h_pseg;
     // label matrices [chunk][stride] and [PB/32][n + 1][32] live in ctx->scratch[0..1]
@@ -3663,13 +3662,61 @@ static int run_chunk_philox(sqb_nhood* h, int64_t p0, int64_t np) {
     return launch_count<LT>(h, labT, PB, (int)np, h->d_counts.p + p0 * (int64_t)h->n_cls * h->n_cls);
 }
 
+// class histogram of one segment of the (library-grouped) base labels, for the fast-mode class tables
+template <typename LT>
+__global__ void nhood_class_hist_kernel(const LT* __restrict__ base, int64_t start, int64_t len, int C, uint32_t* __restrict__ out) {
+    extern __shared__ uint32_t s_h[];
+    const bool priv = C <= 4096;
+    if (priv) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) s_h[c] = 0u;
+        __syncthreads();
+    }
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < len; k += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t l = (uint32_t)base[start + k];
+        if (priv) atomicAdd(&s_h[l], 1u);
+        else atomicAdd(&out[l], 1u);
+    }
+    if (priv) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x)
+            if (s_h[c]) atomicAdd(&out[c], s_h[c]);
+    }
+}
+
 // fast RNG mode tables (built lazily: the exact mode never needs them)
 static int philox_prepare(sqb_nhood* h) {
     if (h->philox_ready) return SQB_OK;
     sqb_ctx* c = h->ctx;
     const std::vector<int64_t>& seg_start = h->h_seg_start;
     const std::vector<int64_t>& seg_len = h->h_seg_len;
-    const std::vector<uint32_t>& grouped = h->h_grouped;
+    // class counts of every segment, from the grouped base labels on the device (the host keeps no copy of the labels)
+    const int64_t C1h = (int64_t)h->n_cls + 1;
+    std::vector<uint32_t> hcnt((size_t)h->nseg * C1h, 0u);
+    {
+        DevBuf<uint32_t> d_hist;
+        d_hist.bind(c->stream);
+        SQB_TRY(d_hist.alloc(hcnt.size()));
+        cudaError_t e = cudaMemsetAsync(d_hist.p, 0, hcnt.size() * sizeof(uint32_t), c->stream);
+        for (int sgm = 0; sgm < h->nseg && e == cudaSuccess; ++sgm) {
+            const int64_t m = seg_len[sgm];
+            if (m <= 0) continue;
+            const unsigned g = (unsigned)(m < 256 * 296 ? ceil_div64(m, 256) : 296);
+            const size_t sm = h->n_cls <= 4096 ? (size_t)h->n_cls * 4 : 0;
+            if (h->lt_bytes == 1)
+                nhood_class_hist_kernel<uint8_t><<<g, 256, sm, c->stream>>>(h->d_base.p, seg_start[sgm], m, h->n_cls, d_hist.p + (size_t)sgm * C1h + 1);
+            else
+                nhood_class_hist_kernel<uint16_t><<<g, 256, sm, c->stream>>>(reinterpret_cast<const uint16_t*>(h->d_base.p), seg_start[sgm], m,
+                                                                              h->n_cls, d_hist.p + (size_t)sgm * C1h + 1);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hcnt.data(), d_hist.p, hcnt.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        d_hist.release();
+        if (e != cudaSuccess) {
+            sqb_set_error("fast RNG mode: class histogram failed: %s", cudaGetErrorString(e));
+            return SQB_ERR_CUDA;
+        }
+    }
     {  // fast RNG mode: per segment the class offsets of its labels sorted by class, the Feistel radices and a bucket table
        // (class at the first value of every bucket of 2^shift values) that shortens the class search to `steps` bisections
         const int64_t C1 = (int64_t)h->n_cls + 1;
@@ -3679,7 +3726,7 @@ static int philox_prepare(sqb_nhood* h) {
         for (int sgm = 0; sgm < h->nseg; ++sgm) {
             uint32_t* row = cum.data() + (size_t)sgm * C1;
             const int64_t m = seg_len[sgm];
-            for (int64_t k = seg_start[sgm]; k < seg_start[sgm] + m; ++k) row[grouped[k] + 1]++;
+            for (int64_t cc = 0; cc <= h->n_cls; ++cc) row[cc] = hcnt[(size_t)sgm * C1 + cc];  // row[c + 1] = labels of class c
             for (int64_t cc = 0; cc < h->n_cls; ++cc) row[cc + 1] += row[cc];
             PhiloxSeg& ps = h->h_pseg[sgm];
             ps.start = seg_start[sgm];
@@ -4083,11 +4130,17 @@ int sqb_nhood_set_base(sqb_nhood* h, const uint32_t* base_labels, const int32_t*
     sqb_ctx* c = h->ctx;
     SQB_CUDA(cudaSetDevice(c->device));
     const int64_t n = h->n;
-    for (int64_t i = 0; i < n; ++i)
-        SQB_CHECK(base_labels[i] < (uint32_t)h->n_cls, SQB_ERR_INVALID, "sqb_nhood_set_base: labels[%lld]=%u >= n_cls=%d",
-                  (long long)i, base_labels[i], h->n_cls);
+    {  // one branch-free pass (this runs inside the end-to-end call: 1M labels)
+        uint32_t mx = 0;
+        for (int64_t i = 0; i < n; ++i) mx = base_labels[i] > mx ? base_labels[i] : mx;
+        if (mx >= (uint32_t)h->n_cls)
+            for (int64_t i = 0; i < n; ++i)
+                SQB_CHECK(base_labels[i] < (uint32_t)h->n_cls, SQB_ERR_INVALID, "sqb_nhood_set_base: labels[%lld]=%u >= n_cls=%d",
+                          (long long)i, base_labels[i], h->n_cls);
+    }
     std::vector<int64_t> seg_start, seg_len;
-    std::vector<uint32_t> grouped(n);
+    std::vector<uint32_t> grouped;
+    const uint32_t* grouped_src = base_labels;  // no libraries: the labels are uploaded from the caller's buffer as they are
     h->h_order.clear();
     h->has_order = false;
     if (lib_codes && n_libs > 0) {
@@ -4101,6 +4154,8 @@ int sqb_nhood_set_base(sqb_nhood* h, const uint32_t* base_labels, const int32_t*
         }
         for (int l = 0; l < n_libs; ++l) cnt[l + 1] += cnt[l];
         h->h_order.resize(n);
+        grouped.resize(n);
+        grouped_src = grouped.data();
         std::vector<int64_t> cur(cnt.begin(), cnt.end() - 1);
         for (int64_t i = 0; i < n; ++i) {
             int64_t k = cur[lib_codes[i]]++;
@@ -4113,14 +4168,12 @@ int sqb_nhood_set_base(sqb_nhood* h, const uint32_t* base_labels, const int32_t*
         }
         h->has_order = true;
     } else {
-        for (int64_t i = 0; i < n; ++i) grouped[i] = base_labels[i];
         seg_start.push_back(0);
         seg_len.push_back(n);
     }
     h->nseg = (int)seg_start.size();
     h->h_seg_start = seg_start;
     h->h_seg_len = seg_len;
-    h->h_grouped = grouped;  // the fast RNG mode builds its class tables from these at its first upload
     h->philox_ready = false;
     SQB_TRY(h->d_seg_start.alloc(h->nseg));
     SQB_TRY(h->d_seg_len.alloc(h->nseg));
@@ -4128,7 +4181,7 @@ int sqb_nhood_set_base(sqb_nhood* h, const uint32_t* base_labels, const int32_t*
     SQB_TRY(h->d_base.alloc((size_t)h->stride * h->lt_bytes));
     SQB_CUDA(cudaMemcpyAsync(h->d_seg_start.p, seg_start.data(), h->nseg * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     SQB_CUDA(cudaMemcpyAsync(h->d_seg_len.p, seg_len.data(), h->nseg * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-    SQB_CUDA(cudaMemcpyAsync(h->d_tmp_u32.p, grouped.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    SQB_CUDA(cudaMemcpyAsync(h->d_tmp_u32.p, grouped_src, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     if (h->has_order) {
         SQB_TRY(h->d_order.alloc(n));
         SQB_CUDA(cudaMemcpyAsync(h->d_order.p, h->h_order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));

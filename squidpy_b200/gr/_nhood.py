@@ -11,6 +11,7 @@ Z-scores are computed on the host from the per-permutation uint32 counts exactly
 from __future__ import annotations
 
 import ctypes as C
+import threading
 import time
 from typing import Any, NamedTuple
 
@@ -218,20 +219,30 @@ def nhood_enrichment(
         raise ValueError(f"Expected `rng` to be 'numpy' or 'philox', found `{rng!r}`.")
     start = time.perf_counter()
     ctx = default_context(device)
+    rank, ws = world()
+    lo, hi = shard_range(int(n_perms), rank, ws)
+    seed = shared_seed(seed)  # seed=None: one entropy draw for all ranks (every rank must spawn the same family)
+    # the PCG64 states of this rank's generators are spawned on a host thread while the graph goes to the device
+    # (the C calls below release the GIL)
+    states_box: list = []
+    spawner = None
+    if hi > lo and rng == "numpy":
+        spawner = threading.Thread(target=lambda: states_box.append(spawn_states(seed, int(n_perms), lo, hi)), daemon=True)
+        spawner.start()
     with ctx.lock:
         plan = NhoodPlan(adj.indptr, adj.indices, n_cls, ctx)
         try:
             count = plan.count(int_clust)
-            rank, ws = world()
-            lo, hi = shard_range(int(n_perms), rank, ws)
             logg.info("Calculating neighborhood enrichment on cuda:%d (rank %d/%d, permutations %d..%d)", ctx.device, rank, ws, lo, hi)
-            seed = shared_seed(seed)  # seed=None: one entropy draw for all ranks (every rank must spawn the same family)
             if hi > lo:
                 plan.set_base(int_clust, lib_codes, n_libs)
                 if rng == "philox":
                     plan.upload_philox(int(np.random.SeedSequence(seed).generate_state(1, np.uint64)[0]), lo, hi - lo)
                 else:
-                    plan.upload(spawn_states(seed, int(n_perms), lo, hi))
+                    spawner.join()
+                    if not states_box:  # the spawn raised (e.g. too many children): repeat it here for the exception
+                        states_box.append(spawn_states(seed, int(n_perms), lo, hi))
+                    plan.upload(states_box[0])
                 plan.run_async()
             if ws == 1:
                 # single GPU: mean / std over the permutations on the device, in numpy's operation order (bit-identical to
