@@ -432,6 +432,19 @@ __global__ void ac_pack_rows_kernel(const int32_t* __restrict__ wp, const int32_
     }
 }
 
+// compact rows (FMT 3): 8 slots of 4 bytes = 7 columns (-1 = empty) + the float32 weight ALL entries of the row share (the
+// row-normalised binary graph of the standard pipeline): one 32-byte sector per row instead of a 64-byte line
+__global__ void ac_pack_rows32_kernel(const int32_t* __restrict__ wp, const int32_t* __restrict__ wi, const double* __restrict__ wd,
+                                      int64_t n, uint32_t* __restrict__ rows) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n * 8; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t >> 3;
+        const int s = (int)(t & 7);
+        const int32_t b = wp[r], e = wp[r + 1];
+        if (s < 7) rows[t] = b + s < e ? (uint32_t)wi[b + s] : 0xffffffffu;
+        else rows[t] = e > b ? __float_as_uint((float)wd[b]) : 0u;
+    }
+}
+
 // row permutation: int64 host layout -> int32, validated on the device (bitmap of seen sources)
 __global__ void ac_perm_prepare_kernel(const int64_t* __restrict__ in, int64_t n, int32_t* __restrict__ out,
                                        unsigned int* __restrict__ seen, int* __restrict__ err) {
@@ -495,7 +508,8 @@ __device__ __forceinline__ void ac_block_reduce(double (&q)[NQ], double (*s_red)
 }
 
 // FMT 0: packed rows, 8 lanes per row (<= 8 entries);  FMT 1: packed rows, 16 lanes per row (<= 16 entries);
-// FMT 2: CSR rows, 8 lanes per row (any length; float64 weights).
+// FMT 2: CSR rows, 8 lanes per row (any length; float64 weights);  FMT 3: compact rows, 8 lanes per row (<= 7 entries of one
+// common float32 weight: 32 bytes per row).
 template <typename XT, int MODE, int FMT, bool PERM, int GRP>
 __global__ void __launch_bounds__(AC_T, GRP == 8 ? 3 : 4) ac_sparse_kernel(const __grid_constant__ AcSparseParams p) {
     constexpr int LPR = FMT == 1 ? 16 : 8;
@@ -642,7 +656,15 @@ __global__ void __launch_bounds__(AC_T, GRP == 8 ? 3 : 4) ac_sparse_kernel(const
                         ri[s] = __shfl_sync(0xffffffffu, my_i, src);
                         rx[s] = (double)__shfl_sync(0xffffffffu, my_x, src);
                         rs[s] = make_uint2(0xffffffffu, 0u);
-                        if (ri[s] >= 0) {
+                        if (FMT == 3) {  // 7 columns + the row's weight: 4 bytes per lane, the weight comes from lane 7 of the row
+                            unsigned int cw = 0xffffffffu;
+                            if (ri[s] >= 0) {
+                                const int64_t r = PERM ? (int64_t)__ldg(perm + ri[s]) : (int64_t)ri[s];
+                                cw = __ldg(reinterpret_cast<const unsigned int*>(p.rows) + r * 8 + slot);
+                            }
+                            const unsigned int wb = __shfl_sync(0xffffffffu, cw, (lane & ~7) | 7);
+                            rs[s] = make_uint2(slot == 7 ? 0xffffffffu : cw, wb);
+                        } else if (ri[s] >= 0) {
                             const int64_t r = PERM ? (int64_t)__ldg(perm + ri[s]) : (int64_t)ri[s];
                             rs[s] = __ldg(p.rows + r * LPR + slot);
                         }
@@ -763,7 +785,7 @@ struct sqb_autocorr {
     sqb_ctx* ctx = nullptr;
     int64_t n = 0, nnz = 0;
     double s0 = 0.0;
-    int w_fmt = 2;  // 0 packed 8 lanes, 1 packed 16 lanes, 2 CSR
+    int w_fmt = 2;  // 0 packed 8 lanes, 1 packed 16 lanes, 2 CSR, 3 compact (7 columns + one common weight in 32 bytes)
     DevBuf<int32_t> d_wp, d_wi;
     DevBuf<double> d_wd, d_csum;
     DevBuf<uint2> d_rows;
@@ -849,6 +871,7 @@ static int ac_sparse_fmt(sqb_autocorr* h, const AcSparseParams& p) {
     switch (h->w_fmt) {
         case 0: return ac_sparse_launch<XT, MODE, 0, PERM>(h, p);
         case 1: return ac_sparse_launch<XT, MODE, 1, PERM>(h, p);
+        case 3: return ac_sparse_launch<XT, MODE, 3, PERM>(h, p);
         default: return ac_sparse_launch<XT, MODE, 2, PERM>(h, p);
     }
 }
@@ -1172,6 +1195,17 @@ int sqb_autocorr_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const int32_t* w_i
         s0 += wd[e];
         csum[j] += wd[e];
     }
+    // rows of at most 7 entries that all carry the same float32 weight (a row-normalised binary graph) take the compact format
+    bool uniform7 = (w_dtype == 0 && maxdeg <= 7 && nnz > 0);
+    if (uniform7) {
+        const uint32_t* wb = reinterpret_cast<const uint32_t*>(w_data);
+        for (int64_t r = 0; r < n && uniform7; ++r)
+            for (int64_t e = (int64_t)w_indptr[r] + 1; e < (int64_t)w_indptr[r + 1]; ++e)
+                if (wb[e] != wb[w_indptr[r]]) {
+                    uniform7 = false;
+                    break;
+                }
+    }
     SQB_CUDA(cudaSetDevice(ctx->device));
     sqb_autocorr* h = new sqb_autocorr();
     h->ctx = ctx;
@@ -1187,8 +1221,8 @@ int sqb_autocorr_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const int32_t* w_i
     h->nnz = nnz;
     h->s0 = s0;
     // packed rows hold float32 weights: only for float32 W (lossless); float64 W walks the CSR
-    h->w_fmt = (w_dtype == 0 && maxdeg <= 8) ? 0 : (w_dtype == 0 && maxdeg <= 16) ? 1 : 2;
-    const int lpr = h->w_fmt == 0 ? 8 : 16;
+    h->w_fmt = uniform7 ? 3 : (w_dtype == 0 && maxdeg <= 8) ? 0 : (w_dtype == 0 && maxdeg <= 16) ? 1 : 2;
+    const int lpr = h->w_fmt == 3 ? 4 : h->w_fmt == 0 ? 8 : 16;  // uint2 units per row
     int rc;
     if ((rc = h->d_wp.alloc(n + 1)) || (rc = h->d_wi.alloc(nnz > 0 ? nnz : 1)) || (rc = h->d_wd.alloc(nnz > 0 ? nnz : 1)) ||
         (rc = h->d_csum.alloc(n)) || (rc = h->d_flags.alloc(2)) || (h->w_fmt != 2 && (rc = h->d_rows.alloc((size_t)n * lpr)))) {
@@ -1202,7 +1236,10 @@ int sqb_autocorr_create(sqb_ctx* ctx, int64_t n, int64_t nnz, const int32_t* w_i
     if (e == cudaSuccess) e = cudaMemsetAsync(h->d_flags.p, 0, 2 * sizeof(int), ctx->stream);
     if (e == cudaSuccess && h->w_fmt != 2) {
         ctx->launches += 1;
-        if (h->w_fmt == 0)
+        if (h->w_fmt == 3)
+            ac_pack_rows32_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(h->d_wp.p, h->d_wi.p, h->d_wd.p, n,
+                                                                             reinterpret_cast<uint32_t*>(h->d_rows.p));
+        else if (h->w_fmt == 0)
             ac_pack_rows_kernel<8><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(h->d_wp.p, h->d_wi.p, h->d_wd.p, n, h->d_rows.p);
         else
             ac_pack_rows_kernel<16><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(h->d_wp.p, h->d_wi.p, h->d_wd.p, n, h->d_rows.p);
