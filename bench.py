@@ -5,8 +5,8 @@ Headline (BASELINE.json `metric`, quoted on configs[1]): permutations/s of `nhoo
 30 clusters, k=6 hexagonal neighbour graph (nnz = 5 992 002), n_perms = 1000 per GPU, exact numpy-RNG replay.
 A "step" = one pass of the permutation test: the five kernels of the 1000 permutations (fill, swap-target generation,
 apply, transpose, count) PLUS the per-bin mean / std over all permutations of the job — on one GPU the device statistics
-kernel, on N GPUs the NCCL all-reduce of the exact int64 sums and the variance accumulation chained rank to rank
-(device tensors; `squidpy_b200._dist.sequential_stats_device`) — with graph, base labels and generator states resident in
+kernel, on N GPUs one NCCL all-gather of the per-permutation counts and the same statistics kernel over the gathered rows
+(device tensors; `squidpy_b200._dist.stats_device`) — with graph, base labels and generator states resident in
 HBM.  `e2e` = the same metric through the public API (`squidpy_b200.gr.nhood_enrichment(adata, ...)`) with host buffers.
 Further top-level keys of the same JSON line (each with its own roofline / e2e / cpu_baseline):
   `fast` / `roofline_fast`  — the same workload with `rng="philox"` (keyed-bijection permutations, not the reference's draws);
@@ -40,7 +40,7 @@ METRIC = "nhood_enrichment permutations/s (1M spots, 30 clusters, k=6, n_perms=1
 WORKLOAD = "configs[1]: 1M-spot hex grid (nnz=5992002), 30 clusters, k=6, nhood_enrichment n_perms=1000 per GPU"
 CONFIG = {"workload": WORKLOAD, "n_perms_per_gpu": CFG2["n_perms"], "rng": "numpy PCG64 exact replay",
           "l2": "flushed between steps (256 MiB read+write); working set per step 2 GB > L2",
-          "timing": "CUDA events per step on the launch stream, max over ranks; the step includes the mean/std statistics (N>1: NCCL all-reduce + chained variance)"}
+          "timing": "CUDA events per step on the launch stream, max over ranks; the step includes the mean/std statistics (N>1: NCCL all-gather of the counts + the statistics kernel)"}
 # warp instructions per evaluated unordered pair of the tiled pair kernel (profiles/r01_prof_cooc_metrics.csv:
 # smsp__inst_executed.sum = 2.448e10 for 200 000 points = 2.0e10 pair evaluations) and the issue peak they are held against
 PAIR_WARP_INSTR = 2.448e10 / (200_000 * 199_999 / 2)
@@ -468,7 +468,7 @@ def main():
     import torch
 
     import squidpy_b200 as sq
-    from squidpy_b200._dist import sequential_stats_device
+    from squidpy_b200._dist import stats_device
     from squidpy_b200._rng import spawn_states
     from squidpy_b200.gr import NhoodPlan
     from tools import synth
@@ -504,7 +504,7 @@ def main():
         if ws == 1:
             plan.stats_dev(stat[0].data_ptr(), stat[1].data_ptr())
         else:
-            last["mean"], last["std"] = sequential_stats_device(plan, P * ws, True)
+            last["mean"], last["std"] = stats_device(plan, P * ws, True)
 
     def run_mode(fast: bool):
         if fast:
@@ -587,7 +587,7 @@ def main():
     h2d = int(g.indptr.nbytes + g.indices.nbytes + 2 * base.nbytes + states.nbytes)
     d2h = int(3 * n_cls * n_cls * 8)  # observed counts + mean + std (the per-permutation counts stay on the device)
     e2e = {"value": ws * P / t_e2e, "unit": "permutations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "seconds_per_call": t_e2e,
-           "note": "sq.gr.nhood_enrichment(adata, n_perms=1000*N, seed, copy=True): CSR + labels + PCG64 states H2D (pageable scipy/numpy buffers), kernels, device statistics (N>1: NCCL all-reduce of int64 sums + chained variance), z-scores"}
+           "note": "sq.gr.nhood_enrichment(adata, n_perms=1000*N, seed, copy=True): CSR + labels + PCG64 states H2D (pageable scipy/numpy buffers), kernels, device statistics (N>1: NCCL all-gather of the per-permutation counts + the statistics kernel), z-scores"}
     assert np.isfinite(res.zscore).all() and (res.counts == observed).all()
     with np.errstate(divide="ignore", invalid="ignore"):
         z_dev = (observed.ravel() - mean_x) / std_x
@@ -618,7 +618,7 @@ def main():
             if ws == 1:
                 plan5.stats_dev(stat5[0].data_ptr(), stat5[1].data_ptr())
             else:
-                sequential_stats_device(plan5, P5, True)
+                stats_device(plan5, P5, True)
 
         stat5 = torch.empty((2, 144), dtype=torch.float64, device="cuda")
         step5()
@@ -658,7 +658,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "permutations/s", "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 labels / u32 counts", "data": "synthetic",
                 "config": dict(CONFIG, shuffle_algo=args.shuffle_algo) if args.shuffle_algo != -1 else CONFIG,
-                "collective": None if ws == 1 else "NCCL all_reduce(int64[C*C] sums) + send/recv chain + broadcast of float64[C*C] (inside the timed step)",
+                "collective": None if ws == 1 else "NCCL all_gather of the per-permutation counts (uint32[P, C*C] per rank, device tensors) + the statistics kernel over the gathered rows (inside the timed step)",
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "fast": fast, "roofline_fast": roofline_fast, "nhood_cfg5_strong": cfg5, "moran": moran, "co_occurrence": cooc, "ripley_L": rip}
         print(json.dumps(line), flush=True)

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SQB_ABI_VERSION 2
+#define SQB_ABI_VERSION 3
 
 typedef enum {
     SQB_OK = 0,
@@ -124,6 +124,12 @@ int sqb_nhood_permute_var_chain(sqb_nhood* h, const double* mean, const double* 
 int sqb_nhood_permute_stats_dev(sqb_nhood* h, double* d_mean, double* d_std);
 int sqb_nhood_permute_sums_dev(sqb_nhood* h, int64_t* d_sums);
 int sqb_nhood_permute_var_chain_dev(sqb_nhood* h, const double* d_mean, const double* d_acc_in, double* d_acc_out);
+/* Multi-GPU statistics by gathering (what squidpy_b200._dist does under NCCL): the per-permutation counts [n_perms][n_cls^2] as an
+ * asynchronous device-to-device copy on the context's stream into a caller-owned buffer (the block a collective sends), and the
+ * mean / std over the rows of any device array of counts (the gathered blocks, rows in global permutation order) -- the kernel of
+ * sqb_nhood_permute_stats, i.e. `perms.mean(0)` / `perms.std(0)` of gr/_nhood.py:231 in numpy's operation order.          */
+int sqb_nhood_permute_counts_dev(sqb_nhood* h, uint32_t* d_dst);
+int sqb_nhood_stats_rows_dev(sqb_ctx* ctx, const uint32_t* d_counts, int64_t rows, int n_cls, double* d_mean, double* d_std);
 
 /* Test hook: shuffled label vectors of permutations [p0, p1) of the last upload, recomputed on the device
  * (original node order), out: (p1-p0) x n uint32.                                                        */

@@ -135,6 +135,58 @@ def nccl_cuda() -> bool:
         return False
 
 
+GATHER_LIMIT_BYTES = 2 << 30  # gathered counts larger than this go through the rank-to-rank chain instead
+
+
+def gathered_stats_device(plan, n_total: int, has_rows: bool) -> tuple[np.ndarray, np.ndarray]:
+    """Per-bin mean and standard deviation over the permutation counts of ALL ranks under NCCL, with ONE collective: every rank
+    copies its block of counts (device to device) into a buffer padded to ``ceil(n_total / world)`` rows, the blocks are
+    all-gathered as device tensors (3.6 MB per rank at 30 clusters x 1000 permutations; the blocks of ``shard_range`` are
+    contiguous, so row g of the gathered array is global permutation g), and every rank runs the single-GPU statistics kernel
+    over the first ``n_total`` rows -- bit-identical to numpy's ``mean`` / ``std`` over the concatenated float64 counts.
+    (The rank-to-rank chain of :func:`sequential_stats_device` moves less data but costs a send/recv per rank: measured
+    38 ms per step instead of 22 at 4 GPUs.)"""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from ._lib import check
+
+    rank, ws = world()
+    dev = torch.device("cuda", plan.ctx.device)
+    cc = plan.n_cls * plan.n_cls
+    step = -(-n_total // ws)
+    stream = torch.cuda.current_stream(dev)
+    shared = plan.ctx.stream == stream.cuda_stream  # the library launches on torch's current stream: everything is ordered
+    local = torch.zeros((step, cc), dtype=torch.int32, device=dev)
+    if has_rows:
+        if not shared:
+            stream.synchronize()
+        plan.counts_dev(local.data_ptr())
+        if not shared:
+            plan.ctx.sync()
+    full = torch.empty((ws * step, cc), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(full, local)
+    stat = torch.empty((2, cc), dtype=torch.float64, device=dev)
+    if not shared:
+        stream.synchronize()
+    check(plan._lib.sqb_nhood_stats_rows_dev(plan.ctx.handle, C.c_void_p(full.data_ptr()), n_total, plan.n_cls,
+                                             C.c_void_p(stat[0].data_ptr()), C.c_void_p(stat[1].data_ptr())))
+    if not shared:
+        plan.ctx.sync()
+    res = stat.cpu().numpy()
+    return res[0].reshape(plan.n_cls, plan.n_cls), res[1].reshape(plan.n_cls, plan.n_cls)
+
+
+def stats_device(plan, n_total: int, has_rows: bool) -> tuple[np.ndarray, np.ndarray]:
+    """Multi-GPU statistics under NCCL: gather when the gathered counts are small (the usual case), else the chain."""
+    _, ws = world()
+    if (-(-n_total // ws)) * ws * plan.n_cls * plan.n_cls * 4 <= GATHER_LIMIT_BYTES:
+        return gathered_stats_device(plan, n_total, has_rows)
+    return sequential_stats_device(plan, n_total, has_rows)
+
+
 def sequential_stats_device(plan, n_total: int, has_rows: bool) -> tuple[np.ndarray, np.ndarray]:
     """:func:`sequential_stats` with everything on the device (NCCL): the exact int64 per-bin sums of ``plan``'s permutation
     counts are all-reduced as a device tensor, the mean is formed on the device, the variance accumulation travels rank to

@@ -1,4 +1,5 @@
 // capi.cu — context management and error plumbing of the C ABI (include/squidpy_b200.h).
+#include <sched.h>
 #include <stdarg.h>
 #include <stdlib.h>
 
@@ -6,6 +7,22 @@
 #include <thread>
 
 #include "common.cuh"
+
+// Host threads the staging copies may use: the CPUs this PROCESS may run on (the affinity mask -- a GPU box often grants a
+// container 2 of its 128 logical CPUs, which std::thread::hardware_concurrency() does not see), shared between the ranks of a
+// torchrun launch, one per ~8 CPUs (a thread fills ~10 GB/s of pinned buffers), at least 1.
+static int sqb_host_threads(int at_most) {
+    int cpus = 0;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
+    if (cpus <= 0) cpus = (int)std::thread::hardware_concurrency();
+    int ranks = 1;
+    if (const char* lws = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(lws));
+    cpus = std::max(1, cpus / ranks);
+    int t = cpus >= 16 ? cpus / 8 : std::min(cpus, 2);
+    return std::max(1, std::min(t, at_most));
+}
 
 static thread_local char g_err[1024] = "";
 
@@ -46,8 +63,7 @@ int sqb_h2d(sqb_ctx* c, void* dst, const void* src, size_t bytes) {
     // on the ctx stream itself (chunks go to disjoint destination ranges, so their order on the stream does not matter).
     // One thread fills ~10 GB/s; 8 of them keep a PCIe 5 x16 link busy.  (Round 1 filled one buffer at a time with a
     // fork/join per 16 MB chunk: 12 GB/s for the 3.2 GB expression matrix.)
-    int T = (int)std::thread::hardware_concurrency() / 8;
-    T = std::max(2, std::min(T, sqb_ctx::kStage / 2));
+    int T = sqb_host_threads(sqb_ctx::kStage / 2);
     const size_t chunks = (bytes + kStageBytes - 1) / kStageBytes;
     if ((size_t)T > chunks) T = (int)chunks;
     std::vector<cudaError_t> errs((size_t)T, cudaSuccess);
@@ -85,8 +101,7 @@ int sqb_h2d_gather(sqb_ctx* c, void* dst, const void* src, size_t elem, const in
             SQB_CUDA(cudaEventCreateWithFlags(&c->stage_ev[b], cudaEventDisableTiming));
         }
     }
-    int threads = (int)std::thread::hardware_concurrency() / 8;
-    threads = std::max(2, std::min(threads, 8));
+    int threads = sqb_host_threads(8);
     const int64_t cap = (int64_t)(kStageBytes / elem);
     int64_t r0 = 0;
     for (int k = 0; r0 < rows; ++k) {

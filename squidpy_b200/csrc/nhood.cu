@@ -4427,6 +4427,31 @@ int sqb_nhood_permute_stats_dev(sqb_nhood* h, double* d_mean, double* d_std) {
     return SQB_OK;
 }
 
+// Multi-GPU statistics by gathering: the per-permutation counts of this handle as a device array (asynchronous copy on the ctx
+// stream into a caller-owned buffer, e.g. the padded block a torch all_gather_into_tensor sends) ...
+int sqb_nhood_permute_counts_dev(sqb_nhood* h, uint32_t* d_dst) {
+    SQB_CHECK(h && d_dst, SQB_ERR_INVALID, "sqb_nhood_permute_counts_dev: null argument");
+    SQB_CHECK(h->ran, SQB_ERR_STATE, "sqb_nhood_permute_counts_dev: nothing has run");
+    sqb_ctx* c = h->ctx;
+    SQB_CUDA(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)h->n_perms * h->n_cls * h->n_cls * sizeof(uint32_t);
+    SQB_CUDA(cudaMemcpyAsync(d_dst, h->d_counts.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return SQB_OK;
+}
+
+// ... and mean / std over the rows of ANY device array of counts [rows][n_cls * n_cls] (the gathered blocks of all ranks, rows in
+// global permutation order): the same kernel as the single-GPU statistics, hence numpy's operation order.
+int sqb_nhood_stats_rows_dev(sqb_ctx* ctx, const uint32_t* d_counts, int64_t rows, int n_cls, double* d_mean, double* d_std) {
+    SQB_CHECK(ctx && d_counts && d_mean && d_std, SQB_ERR_INVALID, "sqb_nhood_stats_rows_dev: null argument");
+    SQB_CHECK(rows >= 1 && n_cls >= 1, SQB_ERR_INVALID, "sqb_nhood_stats_rows_dev: rows=%lld, n_cls=%d", (long long)rows, n_cls);
+    SQB_CUDA(cudaSetDevice(ctx->device));
+    const int CC = n_cls * n_cls;
+    SqbLaunchScope scope(ctx, SQB_K_MISC);
+    nhood_stats_kernel<<<(unsigned)ceil_div64(CC, 64), 64, 0, ctx->stream>>>(d_counts, rows, CC, d_mean, d_std);
+    SQB_POST_LAUNCH();
+    return SQB_OK;
+}
+
 int sqb_nhood_permute_sums_dev(sqb_nhood* h, int64_t* d_sums) {
     SQB_CHECK(h && d_sums, SQB_ERR_INVALID, "sqb_nhood_permute_sums_dev: null argument");
     SQB_CHECK(h->ran, SQB_ERR_STATE, "sqb_nhood_permute_sums_dev: nothing has run");

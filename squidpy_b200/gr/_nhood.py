@@ -18,7 +18,7 @@ from typing import Any, NamedTuple
 import numpy as np
 
 from .._constants import Key
-from .._dist import nccl_cuda, sequential_stats, sequential_stats_device, shard_range, shared_seed, world
+from .._dist import nccl_cuda, sequential_stats, shard_range, shared_seed, stats_device, world
 from .._lib import Context, check, default_context, load
 from .._rng import spawn_states
 from .._validators import assert_categorical_obs, assert_connectivity_key, assert_positive, extract_adata_if_sdata
@@ -141,6 +141,10 @@ class NhoodPlan:
     def sums_dev(self, d_sums: int) -> None:
         check(self._lib.sqb_nhood_permute_sums_dev(self._h, C.c_void_p(d_sums)))
 
+    def counts_dev(self, d_dst: int) -> None:
+        """Asynchronous device-to-device copy of the per-permutation counts [n_perms, C*C] (uint32) to ``d_dst``."""
+        check(self._lib.sqb_nhood_permute_counts_dev(self._h, C.c_void_p(d_dst)))
+
     def var_chain_dev(self, d_mean: int, d_acc_in: int, d_acc_out: int) -> None:
         check(self._lib.sqb_nhood_permute_var_chain_dev(self._h, C.c_void_p(d_mean), C.c_void_p(d_acc_in), C.c_void_p(d_acc_out)))
 
@@ -249,10 +253,11 @@ def nhood_enrichment(
                 # the host expression of the reference); the per-permutation counts never leave the GPU
                 mean, std = plan.stats()
             elif nccl_cuda():
-                # several GPUs: exact integer sums all-reduced, the order-dependent variance accumulation chained through the
-                # ranks in permutation order — device tensors end to end, one [2, C, C] download (bit-identical to mean/std of
-                # the gathered counts; nothing but [C, C] tensors moves)
-                mean, std = sequential_stats_device(plan, int(n_perms), hi > lo)
+                # several GPUs: the per-permutation counts of all ranks are all-gathered as device tensors (one collective) and
+                # every rank runs the same statistics kernel over them; one [2, C, C] download.  (Very large count arrays: exact
+                # integer sums all-reduced + the order-dependent variance accumulation chained through the ranks.)  Either way
+                # bit-identical to mean/std of the gathered counts.
+                mean, std = stats_device(plan, int(n_perms), hi > lo)
             else:  # gloo (CPU tests of the host logic): the same chain through host buffers
                 if hi > lo:
                     sums_local, step = plan.sums(), plan.var_chain
