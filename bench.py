@@ -85,13 +85,54 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        # In-process NVML (a few microseconds per sample).  A looping `nvidia-smi` child costs nothing on a one-GPU box, but on a
+        # multi-GPU box its queries contend with every rank's kernel launches: measured at 4 GPUs, 36.6 ms per step with it and
+        # 22.7 ms without (tools/dist_diag.py, same kernels, same collective).  nvidia-smi stays as the fallback.
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+            import pynvml
+
+            pynvml.nvmlInit()
+            handle = None
+            try:
+                import torch
+
+                pr = torch.cuda.get_device_properties(self.index)
+                handle = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml, self.handle, self.halt = pynvml, handle, threading.Event()
+            self.proc = "nvml"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        bits = [getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8), getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)]
+        while True:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append([str(sm), str(mx), "%.1f" % pw] + [("Active" if rs & b else "Not Active") for b in bits])
+            except Exception:
+                pass
+            if self.halt.wait(0.1):
+                break
 
     def _read(self):
         for line in self.proc.stdout:
@@ -101,7 +142,11 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
-        self.proc.terminate()
+        if self.proc == "nvml":
+            self.halt.set()
+            self.t.join(timeout=2.0)
+        else:
+            self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -113,7 +158,8 @@ class ClockSampler:
                         reasons.add(nm)
             except Exception:
                 continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "NVML in-process, 10 Hz" if self.proc == "nvml" else "nvidia-smi -lms 200"}
 
 
 def _dist_setup():
@@ -173,9 +219,32 @@ def _timed_steps(fn, steps, flush, ws):
 # CPU arms (the oracle C port of the reference algorithms on the box's host cores)
 # ---------------------------------------------------------------------------------------------------------------
 def _pin_openmp():
-    # must happen before liboracle.so (libgomp) is loaded: threads bound to cores, no migration between runs
+    # must happen before liboracle.so (its libgomp) is loaded: threads bound to cores, no migration between runs.  It must NOT
+    # happen before torch is imported: an OpenMP runtime that sees OMP_PROC_BIND binds the thread that initialises it -- the
+    # main thread of every rank -- to the first place, and every thread created afterwards inherits that one-core mask
+    # (measured under torchrun: 4 ranks launching from the same core, 36.6 ms per step instead of 22.7).
     os.environ.setdefault("OMP_PROC_BIND", "close")
     os.environ.setdefault("OMP_PLACES", "cores")
+
+
+class _cpu_leg:
+    """A CPU-baseline leg: OpenMP pinning for the oracle library only, and the main thread gets its CPU mask back afterwards
+    (the OpenMP master thread is bound to the first place while it works)."""
+
+    cores = None  # CPUs this process may use, read BEFORE the OpenMP runtime narrows the main thread's mask
+
+    def __enter__(self):
+        self.mask = os.sched_getaffinity(0)
+        _cpu_leg.cores = len(self.mask)
+        _pin_openmp()
+        return self
+
+    def __exit__(self, *exc):
+        try:
+            os.sched_setaffinity(0, self.mask)
+        except OSError:
+            pass
+        return False
 
 
 def cpu_reference_nhood(g, base, n_cls, seed, reps=3, sample=None):
@@ -184,7 +253,7 @@ def cpu_reference_nhood(g, base, n_cls, seed, reps=3, sample=None):
     from oracle import ref
     from squidpy_b200._rng import spawn_states
 
-    cores = len(os.sched_getaffinity(0))
+    cores = _cpu_leg.cores or len(os.sched_getaffinity(0))
     ref.nhood_perm_counts(g.indptr, g.indices, base, n_cls, spawn_states(seed, cores), n_threads=cores)  # warm-up
     t0 = time.perf_counter()
     ref.nhood_perm_counts(g.indptr, g.indices, base, n_cls, spawn_states(seed, 1), n_threads=1)
@@ -205,6 +274,7 @@ def run_reference(args, rank, ws):
     box) on the host cores, same config/metric; each step = a bounded sample (512 of the 1000 permutations)."""
     if rank != 0:
         return
+    _cpu_leg.cores = len(os.sched_getaffinity(0))  # before the OpenMP runtime is loaded
     _pin_openmp()
     from oracle import ref
     from squidpy_b200._rng import spawn_states
@@ -212,7 +282,7 @@ def run_reference(args, rank, ws):
 
     g = synth.hex_graph(CFG2["rows"], CFG2["cols"])
     base = synth.categorical_labels(g.shape[0], CFG2["n_cls"], seed=0).cat.codes.to_numpy().astype(np.uint32)
-    cores = len(os.sched_getaffinity(0))
+    cores = _cpu_leg.cores or len(os.sched_getaffinity(0))
     p_s = max(cores, min(512, 4 * cores))
     for _ in range(max(args.warmup, 1)):
         ref.nhood_perm_counts(g.indptr, g.indices, base, CFG2["n_cls"], spawn_states(0, cores), n_threads=cores)
@@ -306,9 +376,10 @@ def bench_moran(ctx, rank, ws, steps, warmup, flush, skip_cpu):
         out["n_perms_100_seconds"] = time.perf_counter() - t0
         if not skip_cpu:
             try:
+              with _cpu_leg():
                 from oracle import ref
 
-                cores = len(os.sched_getaffinity(0))
+                cores = _cpu_leg.cores or len(os.sched_getaffinity(0))
                 ns = 2 * cores
                 sub = x[:, :ns].T.tocsr()
                 ref.morans_i(gn, sub[:cores], n_threads=cores)
@@ -366,10 +437,11 @@ def bench_cooc(ctx, rank, ws, skip_cpu):
            "finite": bool(np.isfinite(occ).all()), "interval_len": int(len(iv))}
     if rank == 0 and ws == 1 and not skip_cpu:
         try:
+          with _cpu_leg():
             from oracle import ref
             from squidpy_b200.gr._ppatterns import _find_min_max
 
-            cores = len(os.sched_getaffinity(0))
+            cores = _cpu_leg.cores or len(os.sched_getaffinity(0))
             p32 = pts.astype(np.float32)
             labs = labels.cat.codes.to_numpy().astype(np.int32)
             tmin, tmax = _find_min_max(p32)
@@ -423,9 +495,10 @@ def bench_ripley(ctx, rank, ws, skip_cpu):
            "pvalues_finite": bool(np.isfinite(res["pvalues"]).all())}
     if rank == 0 and ws == 1 and not skip_cpu:
         try:
+          with _cpu_leg():
             from oracle import ref
 
-            cores = len(os.sched_getaffinity(0))
+            cores = _cpu_leg.cores or len(os.sched_getaffinity(0))
             big = pts[lab == int(np.argmax(sizes))]
             sup = res["bins"]
             ns, secs = [15000, 30000], []
@@ -464,7 +537,6 @@ def main():
         run_reference(args, rank, ws)
         return
 
-    _pin_openmp()
     import torch
 
     import squidpy_b200 as sq
@@ -652,7 +724,8 @@ def main():
         cpu = None
         if not args.skip_cpu and ws == 1:  # the CPU baseline is timed on rank 0 at N = 1 only
             try:
-                cpu = cpu_reference_nhood(g, base, n_cls, CFG2["seed"])
+                with _cpu_leg():
+                    cpu = cpu_reference_nhood(g, base, n_cls, CFG2["seed"])
             except Exception as e:  # pragma: no cover
                 cpu = {"error": repr(e)}
         line = {"metric": METRIC, "value": value, "unit": "permutations/s", "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
