@@ -212,3 +212,25 @@ def test_ppp_block_sampling_is_the_scalar_stream():
         a, b = np.random.default_rng(5), np.random.default_rng(5)
         np.testing.assert_array_equal(scalar(hull, 2, n_obs, a), _ppp(hull, 2, n_obs, b))
         assert a.random() == b.random()
+
+
+def test_gathered_blocks_are_in_global_permutation_order():
+    """`_dist.gathered_stats_device` relies on this: every rank pads its block of rows to `step = ceil(n / world)` rows, the blocks
+    are concatenated in rank order (all_gather_into_tensor), and the FIRST n rows of the result are then the rows of the global
+    job in order -- because `shard_range` hands out contiguous blocks of `step` rows and only the last non-empty one is short."""
+    from squidpy_b200._dist import shard_range
+
+    for n in (1, 2, 7, 8, 9, 100, 1000, 1001):
+        for ws in (1, 2, 3, 4, 8, 16):
+            step = -(-n // ws)
+            full = np.full((ws * step,), -1, dtype=np.int64)
+            covered = 0
+            for r in range(ws):
+                lo, hi = shard_range(n, r, ws)
+                assert 0 <= lo <= hi <= n and hi - lo <= step
+                assert lo == min(r * step, n)  # contiguous blocks of `step`
+                full[r * step : r * step + (hi - lo)] = np.arange(lo, hi)
+                covered += hi - lo
+            assert covered == n
+            np.testing.assert_array_equal(full[:n], np.arange(n))
+            assert (full[n:] == -1).all()
