@@ -234,3 +234,48 @@ def test_gathered_blocks_are_in_global_permutation_order():
             assert covered == n
             np.testing.assert_array_equal(full[:n], np.arange(n))
             assert (full[n:] == -1).all()
+
+
+def test_row_record_count_identity():
+    """The algorithm of nhood_count_recs_kernel, restated in numpy and held against the oracle: the stored entries with j >= i of a
+    structurally symmetric graph are cut into row records {i, j0, j1, j2} (unused slots point at the spare node n, which carries
+    the spare label C); ONE increment U[l_i][l_j] per slot into a histogram with C + 1 columns; the flush adds the mirror,
+    counts = U + U^T over the first C columns, and every self loop is taken off the diagonal once.  Directed graphs: records of
+    all entries, no mirror."""
+    import scipy.sparse as sp
+
+    from oracle import ref
+
+    rng = np.random.default_rng(12)
+    for trial in range(20):
+        n, C = int(rng.integers(5, 300)), int(rng.integers(2, 9))
+        a = sp.random(n, n, density=float(rng.uniform(0.01, 0.2)), format="csr", random_state=int(rng.integers(1 << 30)), dtype=np.float32)
+        sym = trial % 2 == 0
+        if sym:
+            a = ((a + a.T) > 0).astype(np.float32) + sp.diags((rng.random(n) < 0.3).astype(np.float32))
+        a = sp.csr_matrix(a)
+        a.eliminate_zeros()
+        a.sort_indices()
+        lab = rng.integers(0, C, n)
+        lab1 = np.append(lab, C)  # the spare row
+        recs = []
+        for i in range(n):
+            cols = a.indices[a.indptr[i] : a.indptr[i + 1]]
+            if sym:
+                cols = cols[cols >= i]
+            for k in range(0, len(cols), 3):
+                slot = list(cols[k : k + 3]) + [n] * (3 - len(cols[k : k + 3]))
+                recs.append((i, *slot))
+        hist = np.zeros((C, C + 1), dtype=np.int64)
+        for i, j0, j1, j2 in recs:
+            for j in (j0, j1, j2):
+                hist[lab1[i], lab1[j]] += 1
+        u = hist[:, :C]
+        if sym:
+            got = u + u.T
+            for i in np.flatnonzero(a.diagonal() != 0):
+                got[lab[i], lab[i]] -= 1
+        else:
+            got = u
+        exp = ref.nhood_count(a.indptr, a.indices, lab.astype(np.uint32), C)
+        np.testing.assert_array_equal(got, exp)
